@@ -1,0 +1,104 @@
+// abi_common.h -- host-side helpers shared by the translation units that
+// implement include/dfgnn_b200.h: error reporting, launch accounting, layout
+// dispatch and schedule heuristics.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <type_traits>
+
+#include "../../include/dfgnn_b200.h"
+#include "common.cuh"
+#include "rowblock.cuh"
+
+namespace dfgnn {
+
+void set_error(const char* fmt, ...);
+std::atomic<uint64_t>& launch_counter();
+
+inline int check_launch(const char* what) {
+  launch_counter().fetch_add(1, std::memory_order_relaxed);
+  const cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(err));
+    return (int)err;
+  }
+  return DFGNN_OK;
+}
+
+template <class T>
+struct Tag { using type = T; };
+
+// Picks the register layout for a feature width.  Returns false for f > 512.
+template <class Fn>
+inline bool dispatch_layout(int f, Fn&& fn) {
+  if (f == 32) fn(Tag<VecLayout<8>>{});
+  else if (f == 64) fn(Tag<VecLayout<16>>{});
+  else if (f == 128) fn(Tag<VecLayout<32>>{});
+  else if (f == 256) fn(Tag<VecLayout<64>>{});
+  else if (f == 512) fn(Tag<VecLayout<128>>{});
+  else if (f <= 32) fn(Tag<ScalarLayout<1>>{});
+  else if (f <= 64) fn(Tag<ScalarLayout<2>>{});
+  else if (f <= 96) fn(Tag<ScalarLayout<3>>{});
+  else if (f <= 128) fn(Tag<ScalarLayout<4>>{});
+  else if (f <= 256) fn(Tag<ScalarLayout<8>>{});
+  else if (f <= 512) fn(Tag<ScalarLayout<16>>{});
+  else return false;
+  return true;
+}
+
+// Segments (rows / columns) per CTA: aim at ~64 entries per warp, within [8, kMaxRB].
+inline int pick_rb(int m, int nnz) {
+  const double avg = m > 0 ? (double)nnz / (double)m : 0.0;
+  int rb = 8;
+  while (rb < kMaxRB && avg * rb < 64.0 * kNW) rb <<= 1;
+  return rb;
+}
+
+inline int check_common(const char* fn, int m, int nnz, int h, int f) {
+  if (m < 0 || nnz < 0 || h < 1 || f < 1) {
+    set_error("%s: invalid sizes m=%d nnz=%d h=%d f=%d", fn, m, nnz, h, f);
+    return DFGNN_ERR_INVALID_ARGUMENT;
+  }
+  if (f > 512) {
+    set_error("%s: feature width f=%d is not supported (max 512)", fn, f);
+    return DFGNN_ERR_UNSUPPORTED_DIM;
+  }
+  if (h > 65535) {
+    set_error("%s: h=%d exceeds the grid limit", fn, h);
+    return DFGNN_ERR_INVALID_ARGUMENT;
+  }
+  return DFGNN_OK;
+}
+
+#define DFGNN_REQUIRE(ptr, fn)                                        \
+  do {                                                                \
+    if ((ptr) == nullptr) {                                           \
+      ::dfgnn::set_error("%s: argument `%s` is NULL", fn, #ptr);      \
+      return DFGNN_ERR_INVALID_ARGUMENT;                              \
+    }                                                                 \
+  } while (0)
+
+template <int NV>
+constexpr size_t slot_bytes() { return (size_t)kNW * 2 * Slot<NV>::kFloats * sizeof(float); }
+
+// kernels whose partial-result slots exceed the 48 KB default need the opt-in
+template <class K>
+inline void ensure_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024)
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+// internal launchers (one per kernel family), defined in gt.cu / gat.cu
+int launch_dot_fwd(bool agnn, int m, int nnz, int h, int f, const int* row_ptr, const int* col_ind,
+                   const float* val, const float* Q, const float* K, const float* V,
+                   const float* rn, float* out, float* attn, cudaStream_t st, const char* fn);
+int launch_gat_fwd(int m, int nnz, int h, int f, const float* ar, const float* ac,
+                   const int* row_ptr, const int* col_ind, float slope, const float* feat,
+                   float drop, uint64_t seed, float* out, float* emax, float* esum, float* emask,
+                   cudaStream_t st, const char* fn);
+
+}  // namespace dfgnn

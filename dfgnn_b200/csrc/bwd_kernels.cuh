@@ -1,0 +1,499 @@
+// bwd_kernels.cuh -- backward kernels (row side over the CSR, column side over the CSC).
+//
+// GT / AGNN (restating fused_gtconv_backward.cu:40-191):
+//   row side   dA_e = <dO_i, V_j>; t_e = dA_e p_e; s_i = sum_e t_e;
+//              dS_e = t_e - s_i p_e -> grad_edge;  dQ_i = sum_e dS_e K_j
+//              (computed in ONE pass over the row as  sum_e t_e K_j - s_i sum_e p_e K_j)
+//   col side   dV_j = sum_i p_ij dO_i;  dK_j = sum_i dS_ij Q_i   (deterministic, no atomics)
+// GAT (restating fused_gatconv_kernel.cu:609-660, 711-865):
+//   row side   g_e = keep_e/(1-drop) <dO_i, feat_j>; t_e = p_e g_e; w_i = sum_e t_e;
+//              de_e = (t_e - w_i p_e) * (e_ij < 0 ? slope : 1) -> grad_edge;
+//              grad_attn_row_i = sum_e de_e
+//   col side   grad_feat_j = sum_i keep/(1-drop) p_ij dO_i;  grad_attn_col_j = sum_i de_ij
+//              (the reference scatters grad_attn_col with atomicAdd, l.854; here it is
+//               a column-side sum through `permute`, bit-reproducible)
+#pragma once
+
+#include "rowblock.cuh"
+
+namespace dfgnn {
+
+struct GtBwdParams {
+  int m, nnz, h, f, rb;
+  const int* row_ptr;
+  const int* col_ind;
+  const int* col_ptr;
+  const int* row_ind;
+  const int* val_idx;
+  const float* Q;
+  const float* K;
+  const float* V;
+  const float* attn;   // [h, nnz] probabilities
+  const float* dO;
+  float* dQ;
+  float* dK;
+  float* dV;
+  float* grad_edge;    // [h, nnz]
+};
+
+// Sum-merge of split segments: NV floats per lane + one scalar (slot.a).
+template <int NV, class Fin>
+__device__ __forceinline__ void sum_merge_slots(float* s_slot, Fin fin) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  Slot<NV> mine(s_slot, w, 1);
+  const int seg = mine.seg();
+  if (seg < 0) return;
+  float a = mine.a(), acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = mine.v(i, lane);
+  for (int w2 = w + 1; w2 < kNW; ++w2) {
+    Slot<NV> s(s_slot, w2, 0);
+    if (s.seg() != seg) break;
+    a += s.a();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] += s.v(i, lane);
+  }
+  fin(seg, a, acc);
+}
+
+template <class L, int C>
+__global__ void __launch_bounds__(kNW * 32, 2) gt_bwd_row_kernel(const GtBwdParams p) {
+  constexpr int NR = L::NR, LPR = L::LPR, G = L::G, EPS = G * C;
+  static_assert(32 % EPS == 0, "edges per step must divide 32");
+  __shared__ int s_rp[kMaxRB + 1];
+  __shared__ float s_s[kMaxRB];
+  extern __shared__ float s_slot[];
+
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int grp = lane / LPR, gl = lane % LPR;
+  const int hid = blockIdx.y, h = p.h, f = p.f;
+  const float* attn = p.attn + (size_t)hid * p.nnz;
+  float* gedge = p.grad_edge + (size_t)hid * p.nnz;
+
+  slots_clear<2 * NR>(s_slot);
+  RowBlock b = rowblock_init(s_rp, p.row_ptr, p.m, p.rb);
+
+  // acc2 = [A1 | A2]:  dQ = A1 - s * A2
+  auto finish = [&](int r, float s, float (&acc2)[2 * NR]) {
+    float dq[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) dq[i] = fmaf(-s, acc2[NR + i], acc2[i]);
+    if (grp == 0) L::store(p.dQ + ((size_t)(b.seg_lb + r) * h + hid) * f, dq, gl, f);
+    if (lane == 0) s_s[r] = s;
+  };
+
+  for (int r = w; r < b.nseg; r += kNW)
+    if (s_rp[r + 1] == s_rp[r]) {
+      float z[2 * NR];
+      zero(z);
+      finish(r, 0.f, z);
+    }
+
+  int e = b.e;
+  if (e < b.e_end) {
+    int r = find_row(s_rp, b.nseg, e);
+    while (e < b.e_end) {
+      while (s_rp[r + 1] <= e) ++r;
+      const int rs = s_rp[r], re = s_rp[r + 1];
+      const int seg_end = min(re, b.e_end);
+      const bool starts = (e == rs), ends = (seg_end == re);
+
+      float g[NR], acc2[2 * NR];
+      L::load(g, p.dO + ((size_t)(b.seg_lb + r) * h + hid) * f, gl, f);
+      zero(acc2);
+      float s_part = 0.f;
+
+      for (int base = e; base < seg_end; base += 32) {
+        const int cnt = min(32, seg_end - base);
+        int my_col = 0;
+        float my_p = 0.f;
+        if (lane < cnt) {
+          my_col = __ldg(p.col_ind + base + lane);
+          my_p = __ldg(attn + base + lane);
+        }
+        for (int s = 0; s < cnt; s += EPS) {
+          float kk[C][NR], vv[C][NR];
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const int idx = s + c * G + grp;
+            const int col = __shfl_sync(kFull, my_col, idx);
+            const size_t off = ((size_t)col * h + hid) * f;
+            if (idx < cnt) {
+              L::load(vv[c], p.V + off, gl, f);
+              L::load(kk[c], p.K + off, gl, f);
+            } else {
+              zero(vv[c]);
+              zero(kk[c]);
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const int idx = s + c * G + grp;
+            const float pc = __shfl_sync(kFull, my_p, idx);  // 0 beyond cnt
+            const float t = group_sum<LPR>(dot<NR>(g, vv[c])) * pc;
+            if (gl == 0 && idx < cnt) gedge[base + idx] = t;
+            s_part += t;
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+              acc2[i] = fmaf(t, kk[c][i], acc2[i]);
+              acc2[NR + i] = fmaf(pc, kk[c][i], acc2[NR + i]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int off = LPR; off < 32; off <<= 1) {
+        s_part += __shfl_xor_sync(kFull, s_part, off);
+#pragma unroll
+        for (int i = 0; i < 2 * NR; ++i) acc2[i] += __shfl_xor_sync(kFull, acc2[i], off);
+      }
+      if (starts && ends) {
+        finish(r, s_part, acc2);
+      } else {
+        Slot<2 * NR> sl(s_slot, w, starts ? 1 : 0);
+#pragma unroll
+        for (int i = 0; i < 2 * NR; ++i) sl.v(i, lane) = acc2[i];
+        if (lane == 0) { sl.a() = s_part; sl.set_seg(r); }
+      }
+      e = seg_end;
+    }
+  }
+  __syncthreads();
+  sum_merge_slots<2 * NR>(s_slot, finish);
+  __syncthreads();
+  // t_e -> dS_e = t_e - s_i p_e   (fused_gtconv_backward.cu:171-176)
+  for (int i = b.E0 + threadIdx.x; i < b.E1; i += kNW * 32) {
+    const int r = find_row(s_rp, b.nseg, i);
+    gedge[i] = fmaf(-s_s[r], __ldg(attn + i), gedge[i]);
+  }
+}
+
+// Column side: segments are CSC columns.  dV_j = sum p dO_i, dK_j = sum dS Q_i.
+template <class L, int C>
+__global__ void __launch_bounds__(kNW * 32, 2) gt_bwd_col_kernel(const GtBwdParams p) {
+  constexpr int NR = L::NR, LPR = L::LPR, G = L::G, EPS = G * C;
+  static_assert(32 % EPS == 0, "edges per step must divide 32");
+  __shared__ int s_cp[kMaxRB + 1];
+  extern __shared__ float s_slot[];
+
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int grp = lane / LPR, gl = lane % LPR;
+  const int hid = blockIdx.y, h = p.h, f = p.f;
+  const float* attn = p.attn + (size_t)hid * p.nnz;
+  const float* gedge = p.grad_edge + (size_t)hid * p.nnz;
+
+  slots_clear<2 * NR>(s_slot);
+  RowBlock b = rowblock_init(s_cp, p.col_ptr, p.m, p.rb);
+
+  // acc2 = [dV | dK]
+  auto finish = [&](int c, float, float (&acc2)[2 * NR]) {
+    if (grp == 0) {
+      float t[NR];
+      const size_t off = ((size_t)(b.seg_lb + c) * h + hid) * f;
+#pragma unroll
+      for (int i = 0; i < NR; ++i) t[i] = acc2[i];
+      L::store(p.dV + off, t, gl, f);
+#pragma unroll
+      for (int i = 0; i < NR; ++i) t[i] = acc2[NR + i];
+      L::store(p.dK + off, t, gl, f);
+    }
+  };
+
+  for (int c = w; c < b.nseg; c += kNW)
+    if (s_cp[c + 1] == s_cp[c]) {
+      float z[2 * NR];
+      zero(z);
+      finish(c, 0.f, z);
+    }
+
+  int e = b.e;
+  if (e < b.e_end) {
+    int c0 = find_row(s_cp, b.nseg, e);
+    while (e < b.e_end) {
+      while (s_cp[c0 + 1] <= e) ++c0;
+      const int rs = s_cp[c0], re = s_cp[c0 + 1];
+      const int seg_end = min(re, b.e_end);
+      const bool starts = (e == rs), ends = (seg_end == re);
+
+      float acc2[2 * NR];
+      zero(acc2);
+      for (int base = e; base < seg_end; base += 32) {
+        const int cnt = min(32, seg_end - base);
+        int my_rid = 0;
+        float my_p = 0.f, my_ds = 0.f;
+        if (lane < cnt) {
+          my_rid = __ldg(p.row_ind + base + lane);
+          const int eid = __ldg(p.val_idx + base + lane);
+          my_p = __ldg(attn + eid);
+          my_ds = __ldg(gedge + eid);
+        }
+        for (int s = 0; s < cnt; s += EPS) {
+          float go[C][NR], qq[C][NR];
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const int idx = s + c * G + grp;
+            const int rid = __shfl_sync(kFull, my_rid, idx);
+            const size_t off = ((size_t)rid * h + hid) * f;
+            if (idx < cnt) {
+              L::load(go[c], p.dO + off, gl, f);
+              L::load(qq[c], p.Q + off, gl, f);
+            } else {
+              zero(go[c]);
+              zero(qq[c]);
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const int idx = s + c * G + grp;
+            const float pc = __shfl_sync(kFull, my_p, idx);
+            const float ds = __shfl_sync(kFull, my_ds, idx);
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+              acc2[i] = fmaf(pc, go[c][i], acc2[i]);
+              acc2[NR + i] = fmaf(ds, qq[c][i], acc2[NR + i]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int off = LPR; off < 32; off <<= 1)
+#pragma unroll
+        for (int i = 0; i < 2 * NR; ++i) acc2[i] += __shfl_xor_sync(kFull, acc2[i], off);
+      if (starts && ends) {
+        finish(c0, 0.f, acc2);
+      } else {
+        Slot<2 * NR> sl(s_slot, w, starts ? 1 : 0);
+#pragma unroll
+        for (int i = 0; i < 2 * NR; ++i) sl.v(i, lane) = acc2[i];
+        if (lane == 0) { sl.a() = 0.f; sl.set_seg(c0); }
+      }
+      e = seg_end;
+    }
+  }
+  __syncthreads();
+  sum_merge_slots<2 * NR>(s_slot, finish);
+}
+
+// ------------------------------------------------------------------------- //
+
+struct GatBwdParams {
+  int m, nnz, h, f, rb;
+  float slope, drop;
+  const int* row_ptr;
+  const int* col_ind;
+  const int* col_ptr;
+  const int* row_ind;
+  const int* permute;
+  const float* emax;
+  const float* esum;
+  const float* emask;   // [nnz, h] or null (keep all)
+  const float* feat;
+  const float* ar;
+  const float* ac;
+  const float* dO;
+  float* grad_feat;
+  float* grad_ar;
+  float* grad_ac;
+  float* grad_edge;     // [nnz, h] scratch: t_e, then de_e
+};
+
+template <class L, int C>
+__global__ void __launch_bounds__(kNW * 32, 3) gat_bwd_row_kernel(const GatBwdParams p) {
+  constexpr int NR = L::NR, LPR = L::LPR, G = L::G, EPS = G * C;
+  static_assert(32 % EPS == 0, "edges per step must divide 32");
+  __shared__ int s_rp[kMaxRB + 1];
+  __shared__ float s_w[kMaxRB];
+  extern __shared__ float s_slot[];
+
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int grp = lane / LPR, gl = lane % LPR;
+  const int hid = blockIdx.y, h = p.h, f = p.f;
+  const float keep_scale = 1.f / (1.f - p.drop);
+
+  slots_clear<1>(s_slot);
+  RowBlock b = rowblock_init(s_rp, p.row_ptr, p.m, p.rb);
+
+  for (int r = w; r < b.nseg; r += kNW)
+    if (s_rp[r + 1] == s_rp[r] && lane == 0) s_w[r] = 0.f;
+
+  int e = b.e;
+  if (e < b.e_end) {
+    int r = find_row(s_rp, b.nseg, e);
+    while (e < b.e_end) {
+      while (s_rp[r + 1] <= e) ++r;
+      const int rs = s_rp[r], re = s_rp[r + 1];
+      const int seg_end = min(re, b.e_end);
+      const bool starts = (e == rs), ends = (seg_end == re);
+      const size_t node = (size_t)(b.seg_lb + r) * h + hid;
+
+      float g[NR];
+      L::load(g, p.dO + node * f, gl, f);
+      const float ar_i = __ldg(p.ar + node);
+      const float mx = __ldg(p.emax + node);
+      const float inv = 1.f / __ldg(p.esum + node);
+      float w_part = 0.f;
+
+      for (int base = e; base < seg_end; base += 32) {
+        const int cnt = min(32, seg_end - base);
+        int my_col = 0;
+        float my_p = 0.f;  // p_e * keep_e / (1 - drop)
+        if (lane < cnt) {
+          my_col = __ldg(p.col_ind + base + lane);
+          const float sc = leaky(ar_i + __ldg(p.ac + (size_t)my_col * h + hid), p.slope);
+          my_p = __expf(sc - mx) * inv;
+          if (p.emask)
+            my_p = (__ldg(p.emask + (size_t)(base + lane) * h + hid) > p.drop) ? my_p * keep_scale : 0.f;
+        }
+        for (int s = 0; s < cnt; s += EPS) {
+          float ff[C][NR];
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const int idx = s + c * G + grp;
+            const int col = __shfl_sync(kFull, my_col, idx);
+            if (idx < cnt) L::load(ff[c], p.feat + ((size_t)col * h + hid) * f, gl, f);
+            else zero(ff[c]);
+          }
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const int idx = s + c * G + grp;
+            const float pc = __shfl_sync(kFull, my_p, idx);
+            const float t = group_sum<LPR>(dot<NR>(g, ff[c])) * pc;
+            if (gl == 0 && idx < cnt) p.grad_edge[(size_t)(base + idx) * h + hid] = t;
+            w_part += t;
+          }
+        }
+      }
+#pragma unroll
+      for (int off = LPR; off < 32; off <<= 1) w_part += __shfl_xor_sync(kFull, w_part, off);
+      if (starts && ends) {
+        if (lane == 0) s_w[r] = w_part;
+      } else {
+        Slot<1> sl(s_slot, w, starts ? 1 : 0);
+        if (lane == 0) { sl.a() = w_part; sl.set_seg(r); }
+      }
+      e = seg_end;
+    }
+  }
+  __syncthreads();
+  {
+    auto fin = [&](int r, float a, float (&)[1]) { if (lane == 0) s_w[r] = a; };
+    sum_merge_slots<1>(s_slot, fin);
+  }
+  __syncthreads();
+  // de_e and grad_attn_row, row-wise (fused_gatconv_kernel.cu:830-864)
+  for (int r = w; r < b.nseg; r += kNW) {
+    const size_t node = (size_t)(b.seg_lb + r) * h + hid;
+    const int rs = s_rp[r], re = s_rp[r + 1];
+    float rsum = 0.f;
+    if (re > rs) {
+      const float ar_i = __ldg(p.ar + node);
+      const float mx = __ldg(p.emax + node);
+      const float inv = 1.f / __ldg(p.esum + node);
+      const float wr = s_w[r];
+      for (int i = rs + lane; i < re; i += 32) {
+        const int col = __ldg(p.col_ind + i);
+        const float x = ar_i + __ldg(p.ac + (size_t)col * h + hid);
+        const float pe = __expf(leaky(x, p.slope) - mx) * inv;
+        const size_t eid = (size_t)i * h + hid;
+        float de = fmaf(-wr, pe, p.grad_edge[eid]);
+        if (leaky(x, p.slope) < 0.f) de *= p.slope;
+        p.grad_edge[eid] = de;
+        rsum += de;
+      }
+      rsum = warp_sum(rsum);
+    }
+    if (lane == 0) p.grad_ar[node] = rsum;
+  }
+}
+
+template <class L, int C>
+__global__ void __launch_bounds__(kNW * 32, 3) gat_bwd_col_kernel(const GatBwdParams p) {
+  constexpr int NR = L::NR, LPR = L::LPR, G = L::G, EPS = G * C;
+  static_assert(32 % EPS == 0, "edges per step must divide 32");
+  __shared__ int s_cp[kMaxRB + 1];
+  extern __shared__ float s_slot[];
+
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int grp = lane / LPR, gl = lane % LPR;
+  const int hid = blockIdx.y, h = p.h, f = p.f;
+  const float keep_scale = 1.f / (1.f - p.drop);
+
+  slots_clear<NR>(s_slot);
+  RowBlock b = rowblock_init(s_cp, p.col_ptr, p.m, p.rb);
+
+  auto finish = [&](int c, float dac, float (&acc)[NR]) {
+    const size_t node = (size_t)(b.seg_lb + c) * h + hid;
+    if (grp == 0) L::store(p.grad_feat + node * f, acc, gl, f);
+    if (lane == 0) p.grad_ac[node] = dac;
+  };
+
+  for (int c = w; c < b.nseg; c += kNW)
+    if (s_cp[c + 1] == s_cp[c]) {
+      float z[NR];
+      zero(z);
+      finish(c, 0.f, z);
+    }
+
+  int e = b.e;
+  if (e < b.e_end) {
+    int c0 = find_row(s_cp, b.nseg, e);
+    while (e < b.e_end) {
+      while (s_cp[c0 + 1] <= e) ++c0;
+      const int rs = s_cp[c0], re = s_cp[c0 + 1];
+      const int seg_end = min(re, b.e_end);
+      const bool starts = (e == rs), ends = (seg_end == re);
+      const float ac_j = __ldg(p.ac + (size_t)(b.seg_lb + c0) * h + hid);
+
+      float acc[NR];
+      zero(acc);
+      float dac = 0.f;
+      for (int base = e; base < seg_end; base += 32) {
+        const int cnt = min(32, seg_end - base);
+        int my_rid = 0;
+        float my_p = 0.f;
+        if (lane < cnt) {
+          my_rid = __ldg(p.row_ind + base + lane);
+          const size_t eid = (size_t)__ldg(p.permute + base + lane) * h + hid;
+          const size_t rn = (size_t)my_rid * h + hid;
+          const float sc = leaky(__ldg(p.ar + rn) + ac_j, p.slope);
+          my_p = __expf(sc - __ldg(p.emax + rn)) / __ldg(p.esum + rn);
+          if (p.emask) my_p = (__ldg(p.emask + eid) > p.drop) ? my_p * keep_scale : 0.f;
+          dac += __ldg(p.grad_edge + eid);
+        }
+        for (int s = 0; s < cnt; s += EPS) {
+          float go[C][NR], pc[C];
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const int idx = s + c * G + grp;
+            const int rid = __shfl_sync(kFull, my_rid, idx);
+            pc[c] = __shfl_sync(kFull, my_p, idx);
+            if (idx < cnt) L::load(go[c], p.dO + ((size_t)rid * h + hid) * f, gl, f);
+            else zero(go[c]);
+          }
+#pragma unroll
+          for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int i = 0; i < NR; ++i) acc[i] = fmaf(pc[c], go[c][i], acc[i]);
+        }
+      }
+      dac = warp_sum(dac);
+#pragma unroll
+      for (int off = LPR; off < 32; off <<= 1)
+#pragma unroll
+        for (int i = 0; i < NR; ++i) acc[i] += __shfl_xor_sync(kFull, acc[i], off);
+      if (starts && ends) {
+        finish(c0, dac, acc);
+      } else {
+        Slot<NR> sl(s_slot, w, starts ? 1 : 0);
+#pragma unroll
+        for (int i = 0; i < NR; ++i) sl.v(i, lane) = acc[i];
+        if (lane == 0) { sl.a() = dac; sl.set_seg(c0); }
+      }
+      e = seg_end;
+    }
+  }
+  __syncthreads();
+  sum_merge_slots<NR>(s_slot, finish);
+}
+
+}  // namespace dfgnn

@@ -1,0 +1,145 @@
+// common.cuh -- shared device helpers for the dfgnn_b200 kernels (sm_100a only).
+//
+// Design: every conv kernel is a "segmented row-block" kernel.
+// A CTA owns RB consecutive rows of the CSR (or columns of the CSC); the CTA's
+// contiguous edge range is split EVENLY over its warps, so a warp's range may
+// cover several short rows or a slice of one long row.  Each warp walks the
+// row pieces inside its range with a flash-style online softmax, neighbour
+// feature rows are gathered with 16-byte vector loads spread over LPR lanes,
+// and pieces of rows that straddle warps are merged through shared memory.
+// Scores never touch HBM (training forward stores them once, as the
+// reference's API requires attn_edge).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dfgnn {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr float kNeg = -1e30f;  // "minus infinity" that survives subtraction
+
+// ------------------------------------------------------------------------- //
+// Feature-row layouts: how the f floats of one node row are spread over a    //
+// warp.  LPR lanes cooperate on one row, G = 32/LPR rows are in flight per   //
+// load instruction, every lane keeps NR floats of the row in registers.      //
+// ------------------------------------------------------------------------- //
+
+// f = 4*F4 with F4 a power of two <= 32, or a multiple of 32: 16-byte loads.
+template <int F4_>
+struct VecLayout {
+  static_assert(F4_ >= 1 && ((F4_ < 32 && (F4_ & (F4_ - 1)) == 0) || F4_ % 32 == 0), "bad F4");
+  static constexpr int F4 = F4_;
+  static constexpr int LPR = F4 < 32 ? F4 : 32;
+  static constexpr int VPL = F4 / LPR;
+  static constexpr int G = 32 / LPR;
+  static constexpr int NR = 4 * VPL;
+
+  __device__ __forceinline__ static void load(float (&r)[NR], const float* __restrict__ row,
+                                              int gl, int /*f*/) {
+    const float4* p = reinterpret_cast<const float4*>(row);
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const float4 t = __ldg(p + v * LPR + gl);
+      r[4 * v + 0] = t.x; r[4 * v + 1] = t.y; r[4 * v + 2] = t.z; r[4 * v + 3] = t.w;
+    }
+  }
+  __device__ __forceinline__ static void store(float* __restrict__ row, const float (&r)[NR],
+                                               int gl, int /*f*/) {
+    float4* p = reinterpret_cast<float4*>(row);
+#pragma unroll
+    for (int v = 0; v < VPL; ++v)
+      p[v * LPR + gl] = make_float4(r[4 * v + 0], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+  }
+};
+
+// any f <= 32*NT: scalar loads, lane l owns features l, l+32, ...
+template <int NT_>
+struct ScalarLayout {
+  static constexpr int LPR = 32;
+  static constexpr int G = 1;
+  static constexpr int NR = NT_;
+
+  __device__ __forceinline__ static void load(float (&r)[NR], const float* __restrict__ row,
+                                              int gl, int f) {
+#pragma unroll
+    for (int t = 0; t < NR; ++t) {
+      const int d = t * 32 + gl;
+      r[t] = d < f ? __ldg(row + d) : 0.f;
+    }
+  }
+  __device__ __forceinline__ static void store(float* __restrict__ row, const float (&r)[NR],
+                                               int gl, int f) {
+#pragma unroll
+    for (int t = 0; t < NR; ++t) {
+      const int d = t * 32 + gl;
+      if (d < f) row[d] = r[t];
+    }
+  }
+};
+
+// edges a lane group keeps in flight per step: bounded by registers (2 rows of
+// NR floats per edge in the forward) and by the requirement G*C | 32.
+template <class L>
+struct ChunkOf {
+  static constexpr int kMax = L::NR <= 4 ? 8 : (L::NR <= 8 ? 4 : (L::NR <= 16 ? 2 : 1));
+  static constexpr int kByG = 32 / L::G;
+  static constexpr int C = kMax < kByG ? kMax : kByG;
+};
+
+template <int N>
+__device__ __forceinline__ void zero(float (&r)[N]) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) r[i] = 0.f;
+}
+
+template <int N>
+__device__ __forceinline__ float dot(const float (&a)[N], const float (&b)[N]) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) s = fmaf(a[i], b[i], s);
+  return s;
+}
+
+// all-reduce (sum) inside an aligned group of LPR lanes
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int off = LPR / 2; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off);
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) { return group_sum<32>(v); }
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, off));
+  return v;
+}
+
+// largest r in [0, n) with a[r] <= e, for a non-decreasing smem array a[0..n]
+// with a[0] <= e < a[n].  Skips empty rows (a[r] == a[r+1]) by construction.
+__device__ __forceinline__ int find_row(const int* a, int n, int e) {
+  int lo = 0, hi = n;  // invariant: a[lo] <= e < a[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] <= e) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ float leaky(float x, float slope) { return x > 0.f ? x : x * slope; }
+
+// counter-based uniform in (0, 1]: two rounds of a 64-bit mix (splitmix64
+// finaliser) over (seed, edge index).  Replaces the cuRAND stream the reference
+// draws edge_mask from (fused_gatconv_kernel.cu:1073-1081).
+__device__ __forceinline__ float uniform01(uint64_t seed, uint64_t idx) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (float)((z >> 40) + 1) * (1.0f / 16777216.0f);  // (0, 1]
+}
+
+}  // namespace dfgnn

@@ -1,0 +1,31 @@
+// core.cu -- error reporting / bookkeeping for the C ABI (include/dfgnn_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "abi_common.h"
+
+namespace dfgnn {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+std::atomic<uint64_t>& launch_counter() {
+  static std::atomic<uint64_t> c{0};
+  return c;
+}
+
+}  // namespace dfgnn
+
+extern "C" {
+
+int dfgnn_abi_version(void) { return DFGNN_ABI_VERSION; }
+const char* dfgnn_last_error(void) { return dfgnn::g_err; }
+uint64_t dfgnn_launch_count(void) { return dfgnn::launch_counter().load(); }
+
+}  // extern "C"

@@ -1,0 +1,50 @@
+// gat_bwd.cu -- GAT backward entry point of include/dfgnn_b200.h.
+#include "abi_common.h"
+#include "bwd_kernels.cuh"
+
+using namespace dfgnn;
+
+extern "C" int dfgnn_gat_backward(int m, int nnz, int h, int f, float negative_slope,
+                                  float attn_drop, const int32_t* row_ptr, const int32_t* col_ind,
+                                  const int32_t* col_ptr, const int32_t* row_ind,
+                                  const int32_t* permute, const float* edge_max,
+                                  const float* edge_sum, const float* edge_mask,
+                                  const float* in_feat, const float* attn_row,
+                                  const float* attn_col, const float* grad_out, float* grad_feat,
+                                  float* grad_attn_row, float* grad_attn_col, float* grad_edge,
+                                  void* stream) {
+  const char* fn = "dfgnn_gat_backward";
+  if (int rc = check_common(fn, m, nnz, h, f)) return rc;
+  DFGNN_REQUIRE(row_ptr, fn); DFGNN_REQUIRE(col_ptr, fn);
+  if (nnz > 0) {
+    DFGNN_REQUIRE(col_ind, fn); DFGNN_REQUIRE(row_ind, fn); DFGNN_REQUIRE(permute, fn);
+    DFGNN_REQUIRE(grad_edge, fn);
+    if (attn_drop > 0.f) DFGNN_REQUIRE(edge_mask, fn);
+  }
+  DFGNN_REQUIRE(edge_max, fn); DFGNN_REQUIRE(edge_sum, fn); DFGNN_REQUIRE(in_feat, fn);
+  DFGNN_REQUIRE(attn_row, fn); DFGNN_REQUIRE(attn_col, fn); DFGNN_REQUIRE(grad_out, fn);
+  DFGNN_REQUIRE(grad_feat, fn); DFGNN_REQUIRE(grad_attn_row, fn); DFGNN_REQUIRE(grad_attn_col, fn);
+  if (!(attn_drop >= 0.f && attn_drop < 1.f)) {
+    set_error("%s: attn_drop=%g must be in [0, 1)", fn, (double)attn_drop);
+    return DFGNN_ERR_INVALID_ARGUMENT;
+  }
+  if (m == 0) return DFGNN_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  // with attn_drop == 0 every edge is kept: skip the mask reads entirely
+  const float* mask = attn_drop > 0.f ? edge_mask : nullptr;
+  GatBwdParams p{m, nnz, h, f, pick_rb(m, nnz), negative_slope, attn_drop, row_ptr, col_ind,
+                 col_ptr, row_ind, permute, edge_max, edge_sum, mask, in_feat, attn_row,
+                 attn_col, grad_out, grad_feat, grad_attn_row, grad_attn_col, grad_edge};
+  const dim3 grid((m + p.rb - 1) / p.rb, h);
+  int rc = DFGNN_OK;
+  dispatch_layout(f, [&](auto tag) {
+    using L = typename decltype(tag)::type;
+    constexpr int C = ChunkOf<L>::C;
+    gat_bwd_row_kernel<L, C><<<grid, kNW * 32, slot_bytes<1>(), st>>>(p);
+    rc = check_launch(fn);
+    if (rc) return;
+    gat_bwd_col_kernel<L, C><<<grid, kNW * 32, slot_bytes<L::NR>(), st>>>(p);
+    rc = check_launch(fn);
+  });
+  return rc;
+}

@@ -1,0 +1,43 @@
+// gt_bwd.cu -- GT / AGNN backward entry point of include/dfgnn_b200.h.
+#include "abi_common.h"
+#include "bwd_kernels.cuh"
+
+using namespace dfgnn;
+
+extern "C" int dfgnn_gt_backward(int m, int nnz, int h, int f, const int32_t* row_ptr,
+                                 const int32_t* col_ind, const int32_t* /*rows*/,
+                                 const float* /*val*/, const int32_t* col_ptr,
+                                 const int32_t* row_ind, const int32_t* val_idx,
+                                 int /*smem_consume*/, const float* Q, const float* K,
+                                 const float* V, const float* attn_edge, const float* grad_out,
+                                 float* grad_Q, float* grad_K, float* grad_V, float* grad_edge,
+                                 void* stream) {
+  const char* fn = "dfgnn_gt_backward";
+  if (int rc = check_common(fn, m, nnz, h, f)) return rc;
+  DFGNN_REQUIRE(row_ptr, fn); DFGNN_REQUIRE(col_ptr, fn);
+  if (nnz > 0) {
+    DFGNN_REQUIRE(col_ind, fn); DFGNN_REQUIRE(row_ind, fn); DFGNN_REQUIRE(val_idx, fn);
+    DFGNN_REQUIRE(attn_edge, fn); DFGNN_REQUIRE(grad_edge, fn);
+  }
+  DFGNN_REQUIRE(Q, fn); DFGNN_REQUIRE(K, fn); DFGNN_REQUIRE(V, fn); DFGNN_REQUIRE(grad_out, fn);
+  DFGNN_REQUIRE(grad_Q, fn); DFGNN_REQUIRE(grad_K, fn); DFGNN_REQUIRE(grad_V, fn);
+  if (m == 0) return DFGNN_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  GtBwdParams p{m, nnz, h, f, pick_rb(m, nnz), row_ptr, col_ind, col_ptr, row_ind, val_idx,
+                Q, K, V, attn_edge, grad_out, grad_Q, grad_K, grad_V, grad_edge};
+  const dim3 grid((m + p.rb - 1) / p.rb, h);
+  int rc = DFGNN_OK;
+  dispatch_layout(f, [&](auto tag) {
+    using L = typename decltype(tag)::type;
+    constexpr int C = ChunkOf<L>::C;
+    const size_t smem = slot_bytes<2 * L::NR>();
+    ensure_smem(gt_bwd_row_kernel<L, C>, smem);
+    ensure_smem(gt_bwd_col_kernel<L, C>, smem);
+    gt_bwd_row_kernel<L, C><<<grid, kNW * 32, smem, st>>>(p);
+    rc = check_launch(fn);
+    if (rc) return;
+    gt_bwd_col_kernel<L, C><<<grid, kNW * 32, smem, st>>>(p);
+    rc = check_launch(fn);
+  });
+  return rc;
+}

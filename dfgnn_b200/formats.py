@@ -1,0 +1,100 @@
+"""Index-format construction on the GPU (COO -> CSR / CSR+COO "hyper" / CSC).
+
+Host-side mirror of what the reference gets from ``dgl.sparse``
+(``DFGNN/layers/util.py:52-162``): ``A.csr()``, ``torch.sort(A.row)``,
+``A.val[val_idx]`` and ``dglsp.from_csr(...).csc()``.  The work is done by
+``dfgnn_coo_to_csr`` / ``dfgnn_csr_to_csc`` of the C-ABI library (stable radix
+sorts, bit-exact by definition -- SURVEY.md 8c).  There is no CPU path.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+
+from . import _lib
+
+
+class SparseMatrix:
+    """The few attributes of ``dgl.sparse.SparseMatrix`` the reference reads
+    (``A.row``, ``A.col``, ``A.val``, ``A.shape``): the raw COO of the graph."""
+
+    def __init__(self, row: torch.Tensor, col: torch.Tensor, shape: Tuple[int, int]):
+        self.row = row
+        self.col = col
+        self.shape = tuple(shape)
+        self.val = torch.ones(row.numel(), dtype=torch.float32, device=row.device)
+
+    @property
+    def nnz(self) -> int:
+        return int(self.row.numel())
+
+    @property
+    def device(self):
+        return self.row.device
+
+    def csr(self):
+        """-> (indptr, indices, value_indices) like dgl.sparse (int64, as DGL returns)."""
+        row_ptr, col_ind, _, perm, _ = coo_to_csr(self.row, self.col, self.shape[0])
+        return row_ptr.long(), col_ind.long(), perm.long()
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if t.device.type != "cuda":
+        raise RuntimeError(f"{name} must be on CUDA: format construction runs on the GPU only")
+
+
+def coo_to_csr(row: torch.Tensor, col: torch.Tensor, n: int):
+    """-> row_ptr[n+1] i32, col_ind[E] i32, rows[E] i32, perm[E] i32, val[E] f32 (ones)."""
+    _require_cuda(row, "row")
+    _require_cuda(col, "col")
+    row = row.contiguous().to(torch.int64)
+    col = col.contiguous().to(torch.int64)
+    if row.shape != col.shape or row.dim() != 1:
+        raise RuntimeError("row and col must be 1-D tensors of equal length")
+    nnz = row.numel()
+    dev = row.device
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        row_ptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        col_ind = torch.empty(nnz, dtype=torch.int32, device=dev)
+        rows = torch.empty(nnz, dtype=torch.int32, device=dev)
+        perm = torch.empty(nnz, dtype=torch.int32, device=dev)
+        val = torch.empty(nnz, dtype=torch.float32, device=dev)
+        ws_bytes = int(L.dfgnn_format_workspace_bytes(n, nnz))
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        rc = L.dfgnn_coo_to_csr(n, nnz, row.data_ptr() if nnz else None,
+                                col.data_ptr() if nnz else None, row_ptr.data_ptr(),
+                                col_ind.data_ptr() if nnz else None,
+                                rows.data_ptr() if nnz else None,
+                                perm.data_ptr() if nnz else None,
+                                val.data_ptr() if nnz else None, ws.data_ptr(), ws_bytes,
+                                torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "coo_to_csr")
+    return row_ptr, col_ind, rows, perm, val
+
+
+def csr_to_csc(row_ptr: torch.Tensor, col_ind: torch.Tensor):
+    """-> col_ptr[n+1], row_ind[E], val_idx[E] (all int32); val_idx = CSC pos -> CSR pos."""
+    _require_cuda(row_ptr, "row_ptr")
+    _require_cuda(col_ind, "col_ind")
+    if row_ptr.dtype != torch.int32 or col_ind.dtype != torch.int32:
+        raise RuntimeError("row_ptr and col_ind must be int32")
+    row_ptr = row_ptr.contiguous()
+    col_ind = col_ind.contiguous()
+    n = row_ptr.numel() - 1
+    nnz = col_ind.numel()
+    dev = row_ptr.device
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        col_ptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        row_ind = torch.empty(nnz, dtype=torch.int32, device=dev)
+        val_idx = torch.empty(nnz, dtype=torch.int32, device=dev)
+        ws_bytes = int(L.dfgnn_format_workspace_bytes(n, nnz))
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        rc = L.dfgnn_csr_to_csc(n, nnz, row_ptr.data_ptr(), col_ind.data_ptr() if nnz else None,
+                                col_ptr.data_ptr(), row_ind.data_ptr() if nnz else None,
+                                val_idx.data_ptr() if nnz else None, ws.data_ptr(), ws_bytes,
+                                torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "csr_to_csc")
+    return col_ptr, row_ind, val_idx

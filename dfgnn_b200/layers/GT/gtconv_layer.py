@@ -1,0 +1,182 @@
+"""Graph-Transformer sparse multi-head attention modules.
+
+Same class names, constructor arguments, parameter names and ``forward(params, h,
+fuse)`` contract as ``DFGNN/layers/GT/*.py``; the fused branches call the
+operators of ``dfgnn_b200.operators`` (B200 kernels)."""
+import torch.nn as nn
+
+from ...operators.fused_gtconv import (GTConvFuse_hyper, GTConvFuse_inference_csr,
+                                       GTConvFuse_inference_csr_gm, GTConvFuse_inference_hyper,
+                                       GTConvFuse_inference_softmax,
+                                       GTConvFuse_inference_softmax_gm,
+                                       GTConvFuse_inference_tiling)
+from ...utils import benchmark
+from .._dglsp import bsddmm, bspmm, edge_softmax
+
+
+class SparseMHA(nn.Module):
+    """Sparse Multi-head Attention Module (layers/GT/gtconv_layer.py:6-33)."""
+
+    def __init__(self, in_size, out_size, num_heads):
+        super().__init__()
+        self.in_size = in_size
+        self.num_heads = num_heads
+        self.head_dim = out_size // num_heads
+        self.scaling = self.head_dim ** -0.5
+        self.q_proj = nn.Linear(in_size, out_size)
+        self.k_proj = nn.Linear(in_size, out_size)
+        self.v_proj = nn.Linear(in_size, out_size)
+
+    def prep_qkv(self, h):
+        """gtconv_layer.py:19-27: q, k, v as [N, head_dim, heads], q pre-scaled."""
+        N = len(h)
+        q = self.q_proj(h).reshape(N, self.head_dim, self.num_heads)
+        q *= self.scaling
+        k = self.k_proj(h).reshape(N, self.head_dim, self.num_heads)
+        v = self.v_proj(h).reshape(N, self.head_dim, self.num_heads)
+        return q, k, v
+
+    def forward_dglsp(self, A, q, k, v):
+        """gtconv_layer.py:29-33."""
+        attn = edge_softmax(A, bsddmm(A, q, k))
+        return bspmm(A, attn, v)
+
+    def _fused(self, op, h, *op_args):
+        """Shared body of the fused inference branches (gtconv_layer_fused.py:18-35)."""
+        q, k, v = self.prep_qkv(h)
+        q = q.transpose(1, 2).contiguous()
+        k = k.transpose(1, 2).contiguous()
+        v = v.transpose(1, 2).contiguous()
+        out, elapsed_time = benchmark(op, *op_args, q, k, v)
+        return out.transpose(1, 2), elapsed_time
+
+    def _nonfused(self, A, h):
+        q, k, v = self.prep_qkv(h)
+        return benchmark(self.forward_dglsp, A, q, k, v)
+
+
+class SparseMHA_hyper(SparseMHA):
+    """gtconv_layer_fused.py:11-39; params = preprocess_Hyper(g)."""
+
+    def forward(self, params, h, fuse=False):
+        N = len(h)
+        if fuse:
+            indptr, indices, rows, val, smem_consume = params
+            out, t = self._fused(GTConvFuse_inference_hyper, h, indptr, indices, rows, val,
+                                 smem_consume)
+        else:
+            out, t = self._nonfused(params, h)
+        return out.reshape(N, -1), t * 1000
+
+
+class SparseMHA_softmax(SparseMHA):
+    """gtconv_layer_fused.py:66-93; params = preprocess_softmax(g)."""
+
+    def forward(self, params, h, fuse=False):
+        N = len(h)
+        if fuse:
+            indptr, indices, rows, val, smem_consume = params
+            out, t = self._fused(GTConvFuse_inference_softmax, h, indptr, indices, rows, val,
+                                 smem_consume)
+        else:
+            out, t = self._nonfused(params, h)
+        return out.reshape(N, -1), t * 1000
+
+
+class SparseMHA_softmax_gm(SparseMHA):
+    """gtconv_layer_softmax_gm.py; params = preprocess_softmax(g)."""
+
+    def forward(self, params, h, fuse=False):
+        N = len(h)
+        if fuse:
+            indptr, indices, rows, val, _ = params
+            out, t = self._fused(GTConvFuse_inference_softmax_gm, h, indptr, indices, rows, val)
+        else:
+            out, t = self._nonfused(params, h)
+        return out.reshape(N, -1), t * 1000
+
+
+class SparseMHA_CSR(SparseMHA):
+    """gtconv_layer_fused.py:42-63; params = preprocess_CSR(g)."""
+
+    def forward(self, params, h, fuse=False):
+        N = len(h)
+        if fuse:
+            indptr, indices, val, smem_consume = params
+            out, t = self._fused(GTConvFuse_inference_csr, h, indptr, indices, val, smem_consume)
+        else:
+            out, t = self._nonfused(params, h)
+        return out.reshape(N, -1), t * 1000
+
+
+class SparseMHA_CSR_GM(SparseMHA):
+    """gtconv_layer_csr_gm.py; params = preprocess_CSR(g)."""
+
+    def forward(self, params, h, fuse=False):
+        N = len(h)
+        if fuse:
+            indptr, indices, val, _ = params
+            out, t = self._fused(GTConvFuse_inference_csr_gm, h, indptr, indices, val)
+        else:
+            out, t = self._nonfused(params, h)
+        return out.reshape(N, -1), t * 1000
+
+
+class SparseMHA_tiling(SparseMHA):
+    """gtconv_layer_tiling.py:7-29; params = preprocess_CSR(g)."""
+
+    def forward(self, params, h, fuse=False):
+        N = len(h)
+        if fuse:
+            indptr, indices, val, smem_consume = params
+            out, t = self._fused(GTConvFuse_inference_tiling, h, indptr, indices, val,
+                                 smem_consume)
+        else:
+            out, t = self._nonfused(params, h)
+        return out.reshape(N, -1), t * 1000
+
+
+class SparseMHA_forward(SparseMHA):
+    """Training module (gtconv_layer_forward.py:7-59); params = preprocess_Hyper_fw_bw(g).
+    The fused branch reshapes straight to [N, heads, head_dim] (l.22-26)."""
+
+    def forward(self, params, h, fuse=False):
+        N = len(h)
+        A, rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx, smem_consume = params
+        if fuse:
+            q = self.q_proj(h).reshape(N, self.num_heads, self.head_dim)
+            q = q * self.scaling
+            k = self.k_proj(h).reshape(N, self.num_heads, self.head_dim)
+            v = self.v_proj(h).reshape(N, self.num_heads, self.head_dim)
+            if self.training:
+                out = GTConvFuse_hyper(rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx,
+                                       smem_consume, q, k, v)
+            else:
+                out = GTConvFuse_inference_hyper(row_ptr, col_ind, rows, val, smem_consume, q, k, v)
+        else:
+            q = self.q_proj(h).reshape(N, self.head_dim, self.num_heads)
+            q = q * self.scaling
+            k = self.k_proj(h).reshape(N, self.head_dim, self.num_heads)
+            v = self.v_proj(h).reshape(N, self.head_dim, self.num_heads)
+            out = self.forward_dglsp(A, q, k, v)
+        return out.reshape(N, -1)
+
+
+class SparseMHA_forward_timing(SparseMHA):
+    """gtconv_layer_forward.py:62-104: the training forward under ``benchmark``."""
+
+    def forward(self, params, h, fuse=False):
+        N = len(h)
+        A, rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx, smem_consume = params
+        if fuse:
+            q = self.q_proj(h).reshape(N, self.num_heads, self.head_dim)
+            q = q * self.scaling
+            k = self.k_proj(h).reshape(N, self.num_heads, self.head_dim)
+            v = self.v_proj(h).reshape(N, self.num_heads, self.head_dim)
+            out, elapsed_time = benchmark(GTConvFuse_hyper, rows, row_ptr, col_ind, val, col_ptr,
+                                          row_ind, val_idx, smem_consume, q, k, v)
+            out = out.transpose(1, 2)
+        else:
+            q, k, v = self.prep_qkv(h)
+            out, elapsed_time = benchmark(self.forward_dglsp, A, q, k, v)
+        return out.reshape(N, -1), elapsed_time * 1000

@@ -1,0 +1,250 @@
+/*
+ * dfgnn_b200.h -- C ABI of the B200-native DF-GNN fused attention-conv library.
+ *
+ * This is the drop-in boundary: one entry point per function the reference's
+ * pybind modules export for the hot path (`fused_gtconv`,
+ * DFGNN/src/fused_gtconv/fused_gtconv.cpp:577-602; `fused_gatconv`,
+ * DFGNN/src/fused_gatconv/fused_gatconv.cpp:355-372), plus the index-format
+ * construction the reference delegates to dgl.sparse
+ * (DFGNN/layers/util.py:52-162).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer valid on the current CUDA device;
+ *     indices are int32, features / edge scalars are float32, contiguous;
+ *   - shapes: Q/K/V/feat/out [m, h, f]; attn_row/attn_col/edge_max/edge_sum [m, h];
+ *     row_ptr/col_ptr [m+1]; col_ind/row_ind/rows/val/val_idx/permute [nnz];
+ *     GT attn_edge / grad_edge [h, nnz]; GAT edge_mask [nnz, h];
+ *   - outputs are CALLER-allocated (the reference's launchers allocate them with
+ *     torch::zeros / torch::empty, e.g. fused_gtconv_hyper.cu:688-691); no entry
+ *     point requires an output to be pre-zeroed;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and
+ *     the call returns without synchronising (the reference launches on the
+ *     legacy default stream, DFGNN/src/util/computeUtil.h:257-265);
+ *   - return value: 0 on success; DFGNN_ERR_* (< 0) for argument errors;
+ *     a positive value is the cudaError_t of a failed launch.
+ *     `dfgnn_last_error()` returns a thread-local message for the last failure
+ *     (the reference raises TORCH_CHECK / glog CHECK failures instead,
+ *     fused_gtconv.cpp:7-13, computeUtil.h:244-265);
+ *   - arguments the reference's signatures carry but the new schedules do not
+ *     need (`rows`, `smem_consume`) stay in the signatures and may be NULL / 0.
+ *   - supported feature widths: any 1 <= f <= 512 (vectorised fast paths for
+ *     f in {16, 32, 64, 128, 256, 512}); any h >= 1; no limit on row degree.
+ */
+#ifndef DFGNN_B200_H_
+#define DFGNN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define DFGNN_OK 0
+#define DFGNN_ERR_INVALID_ARGUMENT (-1)
+#define DFGNN_ERR_UNSUPPORTED_DIM (-2)
+#define DFGNN_ERR_WORKSPACE (-3)
+
+#define DFGNN_ABI_VERSION 1
+
+int dfgnn_abi_version(void);
+const char *dfgnn_last_error(void);
+/* Number of kernels this library has launched in this process (all entry points). */
+uint64_t dfgnn_launch_count(void);
+
+/* ------------------------------------------------------------------------ */
+/* Index-format construction                                                 */
+/* ------------------------------------------------------------------------ */
+
+/* Bytes of scratch the two builders below need for a graph of n nodes / nnz edges. */
+size_t dfgnn_format_workspace_bytes(int64_t n, int64_t nnz);
+
+/*
+ * COO -> CSR (+ the COO half of the hyper format).
+ * Replaces g_to_SPmatrix + A.csr() + torch.sort(A.row) + A.val[val_idx] of
+ * preprocess_CSR / preprocess_Hyper / preprocess_softmax
+ * (DFGNN/layers/util.py:52-57, 66-79, 82-100, 145-162).
+ * Stable by row: inside a row the input edge order is kept.
+ *   row, col : [nnz] int64 (what torch.stack(g.edges()) holds)
+ *   row_ptr  : [n+1]; col_ind, rows : [nnz]
+ *   perm     : [nnz] sorted position -> input edge id (A.csr()'s value_indices), may be NULL
+ *   val      : [nnz] float32, filled with 1.0f (A.val[val_idx] of an unweighted graph), may be NULL
+ */
+int dfgnn_coo_to_csr(int64_t n, int64_t nnz, const int64_t *row, const int64_t *col,
+                     int32_t *row_ptr, int32_t *col_ind, int32_t *rows, int32_t *perm,
+                     float *val, void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * CSR -> CSC with the CSC-position -> CSR-position map.
+ * Replaces dglsp.from_csr(...).csc() of preprocess_Hyper_fw_bw
+ * (DFGNN/layers/util.py:136-141) and the scipy tocsc() `permute` of
+ * DFGNN/script/train/train_gatconv.py:119-136.  Stable by column.
+ */
+int dfgnn_csr_to_csc(int64_t n, int64_t nnz, const int32_t *row_ptr, const int32_t *col_ind,
+                     int32_t *col_ptr, int32_t *row_ind, int32_t *val_idx, void *workspace,
+                     size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------ */
+/* GT / AGNN  (module `fused_gtconv`)                                        */
+/* ------------------------------------------------------------------------ */
+
+/*
+ * Training forward.  Replaces gt_hyper_forward
+ * (fused_gtconv.cpp:79-116 -> fused_gtconv_hyper.cu:727-760, kernel l.31-163).
+ *   out[i] = sum_j softmax_j(<Q_i,K_j> * val_ij) V_j ; attn_edge[h, nnz] = the probabilities.
+ * `val` may be NULL (== all ones).  Rows without edges produce 0.
+ */
+int dfgnn_gt_hyper_forward(int m, int nnz, int h, int f, const int32_t *row_ptr,
+                           const int32_t *col_ind, const int32_t *rows, const float *val,
+                           const int32_t *col_ptr, const int32_t *row_ind,
+                           const int32_t *val_idx, int smem_consume, const float *Q,
+                           const float *K, const float *V, float *out_feat, float *attn_edge,
+                           void *stream);
+
+/*
+ * Backward.  Replaces gt_backward (fused_gtconv.cpp:125-172 ->
+ * fused_gtconv_backward.cu:193-265).  grad_edge [h, nnz] is scratch
+ * (torch::empty in the reference, l.250).
+ */
+int dfgnn_gt_backward(int m, int nnz, int h, int f, const int32_t *row_ptr,
+                      const int32_t *col_ind, const int32_t *rows, const float *val,
+                      const int32_t *col_ptr, const int32_t *row_ind, const int32_t *val_idx,
+                      int smem_consume, const float *Q, const float *K, const float *V,
+                      const float *attn_edge, const float *grad_out, float *grad_Q,
+                      float *grad_K, float *grad_V, float *grad_edge, void *stream);
+
+/*
+ * Inference entry points; all compute the same function, the name selects the
+ * schedule heuristics.  Replace gt_hyper_inference (fused_gtconv.cpp:278-314),
+ * gt_softmax_inference (l.316-352), gt_softmax_gm_inference (l.354-389),
+ * gt_tiling_inference (l.244-276), gt_csr_inference (l.174-207),
+ * gt_csr_gm_inference (l.209-242); export table l.577-602.
+ */
+int dfgnn_gt_hyper_inference(int m, int nnz, int h, int f, const int32_t *indptr,
+                             const int32_t *indices, const int32_t *rows, const float *val,
+                             int smem_consume, const float *Q, const float *K, const float *V,
+                             float *out_feat, void *stream);
+int dfgnn_gt_softmax_inference(int m, int nnz, int h, int f, const int32_t *indptr,
+                               const int32_t *indices, const int32_t *rows, const float *val,
+                               int smem_consume, const float *Q, const float *K, const float *V,
+                               float *out_feat, void *stream);
+int dfgnn_gt_softmax_gm_inference(int m, int nnz, int h, int f, const int32_t *indptr,
+                                  const int32_t *indices, const int32_t *rows, const float *val,
+                                  const float *Q, const float *K, const float *V, float *out_feat,
+                                  void *stream);
+int dfgnn_gt_tiling_inference(int m, int nnz, int h, int f, const int32_t *indptr,
+                              const int32_t *indices, const float *val, int smem_consume,
+                              const float *Q, const float *K, const float *V, float *out_feat,
+                              void *stream);
+int dfgnn_gt_csr_inference(int m, int nnz, int h, int f, const int32_t *indptr,
+                           const int32_t *indices, const float *val, int smem_consume,
+                           const float *Q, const float *K, const float *V, float *out_feat,
+                           void *stream);
+int dfgnn_gt_csr_gm_inference(int m, int nnz, int h, int f, const int32_t *indptr,
+                              const int32_t *indices, const float *val, const float *Q,
+                              const float *K, const float *V, float *out_feat, void *stream);
+
+/*
+ * AGNN fused entry (no reference export; fuses F.normalize of
+ * DFGNN/layers/AGNN/agnn_layer_fused.py:14 into the conv so that one gathered
+ * row of H serves both the score and the aggregation):
+ *   out[i] = sum_j softmax_j(<H_i,H_j> / (max(|H_i|,eps) max(|H_j|,eps))) H_j
+ * inv_norm [m, h] is caller-allocated scratch.  attn_edge may be NULL.
+ */
+int dfgnn_agnn_forward(int m, int nnz, int h, int f, const int32_t *indptr,
+                       const int32_t *indices, const float *H, float *inv_norm, float *out_feat,
+                       float *attn_edge, void *stream);
+
+/* ------------------------------------------------------------------------ */
+/* GAT  (module `fused_gatconv`)                                             */
+/* ------------------------------------------------------------------------ */
+
+/*
+ * Training forward.  Replaces gat_forward (fused_gatconv.cpp:11-32 ->
+ * fused_gatconv_kernel.cu:1062-1129, kernel l.24-125).
+ *   e_ij = leakyrelu(attn_row[i] + attn_col[j]); edge_max/edge_sum = row max / sum exp;
+ *   out[i] = sum_j keep_ij/(1-drop) * softmax_j(e_ij) * feat[j],
+ *   keep_ij = edge_mask[e] > attn_drop, edge_mask ~ U(0,1] written by this call
+ *   from a counter-based generator keyed by `seed` (the reference seeds cuRAND
+ *   with clock(), l.1073, so masks are comparable only at attn_drop == 0).
+ */
+int dfgnn_gat_forward(int m, int nnz, int h, int f, const float *attn_row,
+                      const float *attn_col, const int32_t *row_ptr, const int32_t *col_ind,
+                      float negative_slope, const float *in_feat, float attn_drop,
+                      uint64_t seed, float *out_feat, float *edge_max, float *edge_sum,
+                      float *edge_mask, void *stream);
+
+/*
+ * Backward.  Replaces gat_backward (fused_gatconv.cpp:291-353 ->
+ * fused_gatconv_kernel.cu:1171-1244).  grad_edge [nnz, h] is scratch
+ * (grad_edge_csr, l.1225).  grad_attn_col is produced by a deterministic
+ * column-side sum (the reference uses atomicAdd, l.854).
+ */
+int dfgnn_gat_backward(int m, int nnz, int h, int f, float negative_slope, float attn_drop,
+                       const int32_t *row_ptr, const int32_t *col_ind, const int32_t *col_ptr,
+                       const int32_t *row_ind, const int32_t *permute, const float *edge_max,
+                       const float *edge_sum, const float *edge_mask, const float *in_feat,
+                       const float *attn_row, const float *attn_col, const float *grad_out,
+                       float *grad_feat, float *grad_attn_row, float *grad_attn_col,
+                       float *grad_edge, void *stream);
+
+/*
+ * Inference entry points (one function, several schedule names).  Replace
+ * gat_inference (fused_gatconv.cpp:225-254), gat_inference_hyper (l.99-124),
+ * gat_inference_hyper_recompute (l.126-150), gat_inference_softmax (l.40-68),
+ * gat_inference_softmax_gm (l.70-97), gat_inference_tiling (l.196-223);
+ * export table l.355-372.
+ */
+int dfgnn_gat_inference(int m, int nnz, int h, int f, const float *attn_row,
+                        const float *attn_col, const int32_t *row_ptr, const int32_t *col_ind,
+                        float negative_slope, const float *in_feat, float *out_feat,
+                        void *stream);
+int dfgnn_gat_inference_hyper(int smem_consume, int m, int nnz, int h, int f,
+                              const float *attn_row, const float *attn_col,
+                              const int32_t *indptr, const int32_t *indices,
+                              const int32_t *rows, float negative_slope, const float *in_feat,
+                              float *out_feat, void *stream);
+int dfgnn_gat_inference_hyper_recompute(int m, int nnz, int h, int f, const float *attn_row,
+                                        const float *attn_col, const int32_t *indptr,
+                                        const int32_t *indices, float negative_slope,
+                                        const float *in_feat, float *out_feat, void *stream);
+int dfgnn_gat_inference_softmax(int smem_consume, int m, int nnz, int h, int f,
+                                const float *attn_row, const float *attn_col,
+                                const int32_t *indptr, const int32_t *indices,
+                                const int32_t *rows, float negative_slope,
+                                const float *in_feat, float *out_feat, void *stream);
+int dfgnn_gat_inference_softmax_gm(int m, int nnz, int h, int f, const float *attn_row,
+                                   const float *attn_col, const int32_t *indptr,
+                                   const int32_t *indices, const int32_t *rows,
+                                   float negative_slope, const float *in_feat, float *out_feat,
+                                   void *stream);
+int dfgnn_gat_inference_tiling(int m, int nnz, int h, int f, const float *attn_row,
+                               const float *attn_col, const int32_t *row_ptr,
+                               const int32_t *col_ind, float negative_slope,
+                               const float *in_feat, float *out_feat, void *stream);
+/*
+ * hyper_v2: attention logits computed inside the call from a_l / a_r [h, f].
+ * Replaces gat_inference_hyper_v2 (fused_gatconv.cpp:152-166 ->
+ * fused_gatconv_hyper_v2.cu:212-305).  attn_row / attn_col [m, h] are
+ * caller-allocated scratch (torch::empty in the reference, l.293-294).
+ */
+int dfgnn_gat_inference_hyper_v2(int smem_consume, int m, int nnz, int h, int f,
+                                 const float *a_l, const float *a_r, const int32_t *indptr,
+                                 const int32_t *indices, float negative_slope,
+                                 const float *in_feat, float *attn_row, float *attn_col,
+                                 float *out_feat, void *stream);
+
+/* The attention-logit prologue on its own (fused_gatconv_hyper_v2.cu:212-250). */
+int dfgnn_gat_attn_weight(int m, int h, int f, const float *a_l, const float *a_r,
+                          const float *in_feat, float *attn_row, float *attn_col, void *stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFGNN_B200_H_ */

@@ -1,0 +1,65 @@
+"""Shared helpers for the parity tests."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from dfgnn_b200 import graphs
+from oracle import cpu_oracle as O
+
+# BASELINE.json north_star: fp32 outputs and gradients within 1e-4 relative /
+# 1e-5 absolute of the reference kernels on identical inputs.
+RTOL = 1e-4
+ATOL = 1e-5
+
+
+def assert_close(name, got, want, rtol=RTOL, atol=ATOL):
+    got = got.detach().cpu().numpy() if hasattr(got, "detach") else np.asarray(got)
+    want = want.detach().cpu().numpy() if hasattr(want, "detach") else np.asarray(want)
+    assert got.shape == want.shape, f"{name}: shape {got.shape} vs {want.shape}"
+    err = np.abs(got.astype(np.float64) - want.astype(np.float64))
+    tol = atol + rtol * np.abs(want.astype(np.float64))
+    bad = err > tol
+    if bad.any():
+        i = np.unravel_index(np.argmax(err - tol), err.shape)
+        raise AssertionError(
+            f"{name}: {int(bad.sum())}/{bad.size} elements outside rtol={rtol} atol={atol}; "
+            f"worst at {i}: got {got[i]!r} want {want[i]!r} (max abs err {err.max():.3e})")
+
+
+def make_case(g: graphs.Graph, dim: int, seed: int, heads: int = 1):
+    """CPU-side CSR/CSC (oracle) + seeded operands for a graph."""
+    src, dst = g.edges()
+    n = g.num_nodes()
+    rp, ci, rows, perm = O.coo_to_csr(src, dst, n)
+    cp, ri, vi = O.csr_to_csc(rp, ci, n)
+    X = graphs.conv_inputs(n, dim, seed, heads)
+    return dict(n=n, nnz=len(ci), row_ptr=rp, col_ind=ci, rows=rows, perm=perm, col_ptr=cp,
+                row_ind=ri, val_idx=vi, X=X, src=src, dst=dst)
+
+
+def to_dev(case, dev):
+    """Device copies of the index arrays and operands."""
+    d = {}
+    for k in ("row_ptr", "col_ind", "rows", "col_ptr", "row_ind", "val_idx"):
+        d[k] = torch.from_numpy(case[k]).to(dev)
+    d["val"] = torch.ones(case["nnz"], dtype=torch.float32, device=dev)
+    X = case["X"]
+    for k in ("Q", "K", "V", "dO", "attn_row", "attn_col"):
+        d[k] = getattr(X, k).to(dev).contiguous()
+    return d
+
+
+def random_graph(n, avg_deg, seed, max_deg=None, empty_frac=0.0, name="rand"):
+    """Unsorted-degree random graph with optional empty rows and one super row."""
+    gen = torch.Generator().manual_seed(seed)
+    deg = torch.poisson(torch.full((n,), float(avg_deg)), generator=gen).long()
+    if empty_frac > 0:
+        deg[torch.rand(n, generator=gen) < empty_frac] = 0
+    if max_deg is not None and n > 3:
+        deg[n // 3] = min(max_deg, n)
+    deg = deg.clamp(max=n)
+    row = torch.repeat_interleave(torch.arange(n), deg)
+    col = (torch.rand(row.numel(), generator=gen) * n).long().clamp(max=n - 1)
+    key = torch.unique(row * n + col)
+    return graphs.Graph(torch.div(key, n, rounding_mode="floor"), key % n, n, None, name)
