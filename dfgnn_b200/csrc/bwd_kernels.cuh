@@ -3,7 +3,7 @@
 // GT / AGNN (restating fused_gtconv_backward.cu:40-191):
 //   row side   dA_e = <dO_i, V_j>; t_e = dA_e p_e; s_i = sum_e t_e;
 //              dS_e = t_e - s_i p_e -> grad_edge;  dQ_i = sum_e dS_e K_j
-//              (computed in ONE pass over the row as  sum_e t_e K_j - s_i sum_e p_e K_j)
+//              (computed in ONE pass over the row, see gt_bwd_row_kernel)
 //   col side   dV_j = sum_i p_ij dO_i;  dK_j = sum_i dS_ij Q_i   (deterministic, no atomics)
 // GAT (restating fused_gatconv_kernel.cu:609-660, 711-865):
 //   row side   g_e = keep_e/(1-drop) <dO_i, feat_j>; t_e = p_e g_e; w_i = sum_e t_e;
@@ -73,20 +73,20 @@ __global__ void __launch_bounds__(kNW * 32, 2) gt_bwd_row_kernel(const GtBwdPara
   slots_clear<2 * NR>(s_slot);
   RowBlock b = rowblock_init(s_rp, p.row_ptr, p.m, p.rb);
 
-  // acc2 = [A1 | A2]:  dQ = A1 - s * A2
-  auto finish = [&](int r, float s, float (&acc2)[2 * NR]) {
-    float dq[NR];
-#pragma unroll
-    for (int i = 0; i < NR; ++i) dq[i] = fmaf(-s, acc2[NR + i], acc2[i]);
+  // Per piece: acc2 = [A1c | A2] with A1c = sum_e p_e (dA_e - c) K_e, A2 = sum_e p_e K_e,
+  // c = dA of the piece's first edge.  dQ = A1c + (c - s) * A2, which equals
+  // sum_e (t_e - s p_e) K_e but keeps the subtraction at the scale of the dS terms
+  // (a row with one edge gives exactly 0, like the reference's two-pass form).
+  auto write_dq = [&](int r, float s, const float (&dq)[NR]) {
     if (grp == 0) L::store(p.dQ + ((size_t)(b.seg_lb + r) * h + hid) * f, dq, gl, f);
     if (lane == 0) s_s[r] = s;
   };
 
   for (int r = w; r < b.nseg; r += kNW)
     if (s_rp[r + 1] == s_rp[r]) {
-      float z[2 * NR];
+      float z[NR];
       zero(z);
-      finish(r, 0.f, z);
+      write_dq(r, 0.f, z);
     }
 
   int e = b.e;
@@ -101,7 +101,8 @@ __global__ void __launch_bounds__(kNW * 32, 2) gt_bwd_row_kernel(const GtBwdPara
       float g[NR], acc2[2 * NR];
       L::load(g, p.dO + ((size_t)(b.seg_lb + r) * h + hid) * f, gl, f);
       zero(acc2);
-      float s_part = 0.f;
+      float s_part = 0.f, c_ref = 0.f;
+      bool have_c = false;
 
       for (int base = e; base < seg_end; base += 32) {
         const int cnt = min(32, seg_end - base);
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(kNW * 32, 2) gt_bwd_row_kernel(const GtBwdPara
           my_p = __ldg(attn + base + lane);
         }
         for (int s = 0; s < cnt; s += EPS) {
-          float kk[C][NR], vv[C][NR];
+          float kk[C][NR], vv[C][NR], dA[C];
 #pragma unroll
           for (int c = 0; c < C; ++c) {
             const int idx = s + c * G + grp;
@@ -127,15 +128,22 @@ __global__ void __launch_bounds__(kNW * 32, 2) gt_bwd_row_kernel(const GtBwdPara
             }
           }
 #pragma unroll
+          for (int c = 0; c < C; ++c) dA[c] = group_sum<LPR>(dot<NR>(g, vv[c]));
+          if (!have_c) {  // first edge of the piece sits in lane group 0, slot 0
+            c_ref = __shfl_sync(kFull, dA[0], 0);
+            have_c = true;
+          }
+#pragma unroll
           for (int c = 0; c < C; ++c) {
             const int idx = s + c * G + grp;
             const float pc = __shfl_sync(kFull, my_p, idx);  // 0 beyond cnt
-            const float t = group_sum<LPR>(dot<NR>(g, vv[c])) * pc;
+            const float t = dA[c] * pc;
+            const float u = (dA[c] - c_ref) * pc;
             if (gl == 0 && idx < cnt) gedge[base + idx] = t;
             s_part += t;
 #pragma unroll
             for (int i = 0; i < NR; ++i) {
-              acc2[i] = fmaf(t, kk[c][i], acc2[i]);
+              acc2[i] = fmaf(u, kk[c][i], acc2[i]);
               acc2[NR + i] = fmaf(pc, kk[c][i], acc2[NR + i]);
             }
           }
@@ -148,18 +156,43 @@ __global__ void __launch_bounds__(kNW * 32, 2) gt_bwd_row_kernel(const GtBwdPara
         for (int i = 0; i < 2 * NR; ++i) acc2[i] += __shfl_xor_sync(kFull, acc2[i], off);
       }
       if (starts && ends) {
-        finish(r, s_part, acc2);
+        float dq[NR];
+#pragma unroll
+        for (int i = 0; i < NR; ++i) dq[i] = fmaf(c_ref - s_part, acc2[NR + i], acc2[i]);
+        write_dq(r, s_part, dq);
       } else {
         Slot<2 * NR> sl(s_slot, w, starts ? 1 : 0);
 #pragma unroll
         for (int i = 0; i < 2 * NR; ++i) sl.v(i, lane) = acc2[i];
-        if (lane == 0) { sl.a() = s_part; sl.set_seg(r); }
+        if (lane == 0) { sl.a() = s_part; sl.b() = c_ref; sl.set_seg(r); }
       }
       e = seg_end;
     }
   }
   __syncthreads();
-  sum_merge_slots<2 * NR>(s_slot, finish);
+  {  // rows split over warps: s first, then the re-centred vectors
+    Slot<2 * NR> mine(s_slot, w, 1);
+    const int seg = mine.seg();
+    if (seg >= 0) {
+      float s = mine.a();
+      int w_end = w + 1;
+      for (; w_end < kNW; ++w_end) {
+        Slot<2 * NR> sl(s_slot, w_end, 0);
+        if (sl.seg() != seg) break;
+        s += sl.a();
+      }
+      float dq[NR];
+#pragma unroll
+      for (int i = 0; i < NR; ++i) dq[i] = fmaf(mine.b() - s, mine.v(NR + i, lane), mine.v(i, lane));
+      for (int w2 = w + 1; w2 < w_end; ++w2) {
+        Slot<2 * NR> sl(s_slot, w2, 0);
+        const float dc = sl.b() - s;
+#pragma unroll
+        for (int i = 0; i < NR; ++i) dq[i] += fmaf(dc, sl.v(NR + i, lane), sl.v(i, lane));
+      }
+      write_dq(seg, s, dq);
+    }
+  }
   __syncthreads();
   // t_e -> dS_e = t_e - s_i p_e   (fused_gtconv_backward.cu:171-176)
   for (int i = b.E0 + threadIdx.x; i < b.E1; i += kNW * 32) {
