@@ -119,14 +119,10 @@ class ClockSampler:
         return out
 
 
-def build_graph(name: str, scale_graphs: float = 1.0):
+def build_graph(name: str, seed_offset: int = 0):
     from dfgnn_b200 import graphs
     conv, dim, fn, kw, fmt, cfg = WORKLOADS[name]
-    kw = dict(kw)
-    if "batch" in kw and scale_graphs != 1.0:
-        kw["batch"] = max(1, int(kw["batch"] * scale_graphs))
-    g = getattr(graphs, fn)(**kw)
-    return g
+    return getattr(graphs, fn)(seed=SEEDS[name] + seed_offset, **kw)
 
 
 # ----------------------------------------------------------------------------- #
@@ -226,11 +222,18 @@ def run_ours(args):
 
     name = args.workload
     conv, dim, fn, kw, fmt, cfg = WORKLOADS[name]
-    g_full = build_graph(name)
-    n_total, e_total = g_full.num_nodes(), g_full.num_edges()
-
+    batched = "batch" in kw
+    weak = batched and world > 1 and args.scaling != "strong"
     # ---- partition ------------------------------------------------
-    part = ddist.make_partition(g_full, world, rank)
+    if weak:
+        # data-parallel: every rank owns its own batch of graphs, no collective in the conv
+        g_full = build_graph(name, seed_offset=1000 * rank)
+        part = ddist.make_partition(g_full, 1, 0)
+        part.describe = f"{kw['batch']} graphs per GPU on {world} GPUs (weak scaling), no collective"
+    else:
+        g_full = build_graph(name)
+        part = ddist.make_partition(g_full, world, rank)
+    n_total, e_total = g_full.num_nodes(), g_full.num_edges()
     g = part.local_graph.to(dev)
     n_rows, n_cols, e_local = part.n_rows, part.n_cols, part.local_graph.num_edges()
 
@@ -364,7 +367,11 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
     ms, e2e_t, fwd_t, ag_t, rs_t = (float(x) for x in stats.cpu())
-    units = float(e_total) * dim  # edges*dim processed by all ranks per step
+    tot = torch.tensor([float(e_local), float(n_rows)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    e_all, n_all = (float(x) for x in tot.cpu())
+    units = e_all * dim  # edges*dim processed by all ranks per step
 
     line = None
     if rank == 0:
@@ -375,10 +382,10 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": units / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
-            "higher_is_better": True, "scaling": part.scaling, "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "weak" if (weak or world == 1) else "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": name, "conv": conv, "dim": dim, "heads": 1, "format": fmt,
-                       "nodes": n_total, "edges": e_total, "baseline_config_index": cfg,
+                       "nodes": int(n_all), "edges": int(e_all), "baseline_config_index": cfg,
                        "partition": part.describe, "l2": "flushed between timed steps (256 MB fill)",
                        "graph_sha256": g_full.sha256()[:16]},
             "e2e": {"value": units / (e2e_t * 1e-3), "unit": UNIT, "ms_per_step": e2e_t,
@@ -496,6 +503,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="arxiv-gat", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--scaling", default="auto", choices=["auto", "weak", "strong"],
+                    help="batched workloads at N>1: weak (own batch per GPU, default) or strong "
+                         "(one global batch sharded by graph); full graphs are always row-partitioned")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

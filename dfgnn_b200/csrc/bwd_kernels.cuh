@@ -19,7 +19,7 @@
 namespace dfgnn {
 
 struct GtBwdParams {
-  int m, nnz, h, f, rb;
+  int m, n, nnz, h, f, rb, rb_col;  // m rows, n columns
   const int* row_ptr;
   const int* col_ind;
   const int* col_ptr;
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(kNW * 32, 2) gt_bwd_col_kernel(const GtBwdPara
   const float* gedge = p.grad_edge + (size_t)hid * p.nnz;
 
   slots_clear<2 * NR>(s_slot);
-  RowBlock b = rowblock_init(s_cp, p.col_ptr, p.m, p.rb);
+  RowBlock b = rowblock_init(s_cp, p.col_ptr, p.n, p.rb_col);
 
   // acc2 = [dV | dK]
   auto finish = [&](int c, float, float (&acc2)[2 * NR]) {
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(kNW * 32, 2) gt_bwd_col_kernel(const GtBwdPara
 // ------------------------------------------------------------------------- //
 
 struct GatBwdParams {
-  int m, nnz, h, f, rb;
+  int m, n, nnz, h, f, rb, rb_col;  // m rows, n columns
   float slope, drop;
   const int* row_ptr;
   const int* col_ind;
@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(kNW * 32, 3) gat_bwd_col_kernel(const GatBwdPa
   const float keep_scale = 1.f / (1.f - p.drop);
 
   slots_clear<NR>(s_slot);
-  RowBlock b = rowblock_init(s_cp, p.col_ptr, p.m, p.rb);
+  RowBlock b = rowblock_init(s_cp, p.col_ptr, p.n, p.rb_col);
 
   auto finish = [&](int c, float dac, float (&acc)[NR]) {
     const size_t node = (size_t)(b.seg_lb + c) * h + hid;

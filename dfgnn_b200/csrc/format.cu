@@ -18,13 +18,13 @@ static inline int key_bits(int64_t n) {
   return b;
 }
 
-__global__ void coo_keys_kernel(int64_t nnz, int64_t n, const int64_t* __restrict__ row,
+__global__ void coo_keys_kernel(int64_t nnz, int64_t n, int64_t n_cols, const int64_t* __restrict__ row,
                                 const int64_t* __restrict__ col, int32_t* __restrict__ keys,
                                 int32_t* __restrict__ ids, int* __restrict__ bad) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nnz) return;
   const int64_t r = row[i], c = col[i];
-  if (r < 0 || r >= n || c < 0 || c >= n) { *bad = 1; keys[i] = 0; }
+  if (r < 0 || r >= n || c < 0 || c >= n_cols) { *bad = 1; keys[i] = 0; }
   else keys[i] = (int32_t)r;
   ids[i] = (int32_t)i;
 }
@@ -89,12 +89,13 @@ size_t dfgnn_format_workspace_bytes(int64_t n, int64_t nnz) {
   return 3 * e + 256 + align_up(sort_temp_bytes(nnz > 0 ? nnz : 1, key_bits(n))) + 256;
 }
 
-int dfgnn_coo_to_csr(int64_t n, int64_t nnz, const int64_t* row, const int64_t* col,
+int dfgnn_coo_to_csr(int64_t n, int64_t n_cols, int64_t nnz, const int64_t* row, const int64_t* col,
                      int32_t* row_ptr, int32_t* col_ind, int32_t* rows, int32_t* perm, float* val,
                      void* workspace, size_t workspace_bytes, void* stream) {
   const char* fn = "dfgnn_coo_to_csr";
-  if (n < 0 || nnz < 0 || n > INT32_MAX || nnz > INT32_MAX) {
-    set_error("%s: n=%lld nnz=%lld out of int32 range", fn, (long long)n, (long long)nnz);
+  if (n < 0 || n_cols < 0 || nnz < 0 || n > INT32_MAX || n_cols > INT32_MAX || nnz > INT32_MAX) {
+    set_error("%s: n_rows=%lld n_cols=%lld nnz=%lld out of int32 range", fn, (long long)n,
+              (long long)n_cols, (long long)nnz);
     return DFGNN_ERR_INVALID_ARGUMENT;
   }
   DFGNN_REQUIRE(row_ptr, fn);
@@ -108,9 +109,10 @@ int dfgnn_coo_to_csr(int64_t n, int64_t nnz, const int64_t* row, const int64_t* 
   }
   DFGNN_REQUIRE(row, fn); DFGNN_REQUIRE(col, fn); DFGNN_REQUIRE(col_ind, fn); DFGNN_REQUIRE(rows, fn);
   DFGNN_REQUIRE(workspace, fn);
-  if (workspace_bytes < dfgnn_format_workspace_bytes(n, nnz)) {
+  const int64_t n_max = n > n_cols ? n : n_cols;
+  if (workspace_bytes < dfgnn_format_workspace_bytes(n_max, nnz)) {
     set_error("%s: workspace too small (%zu < %zu)", fn, workspace_bytes,
-              dfgnn_format_workspace_bytes(n, nnz));
+              dfgnn_format_workspace_bytes(n_max, nnz));
     return DFGNN_ERR_WORKSPACE;
   }
   const int bits = key_bits(n);
@@ -124,7 +126,7 @@ int dfgnn_coo_to_csr(int64_t n, int64_t nnz, const int64_t* row, const int64_t* 
   size_t temp_bytes = workspace_bytes - (3 * e + 256);
 
   cudaMemsetAsync(bad, 0, sizeof(int), st);
-  coo_keys_kernel<<<blocks(nnz), 256, 0, st>>>(nnz, n, row, col, keys_in, ids_in, bad);
+  coo_keys_kernel<<<blocks(nnz), 256, 0, st>>>(nnz, n, n_cols, row, col, keys_in, ids_in, bad);
   if (int rc = check_launch(fn)) return rc;
   cudaError_t err = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, rows, ids_in,
                                                     perm_buf, (int)nnz, 0, bits, st);
@@ -138,16 +140,20 @@ int dfgnn_coo_to_csr(int64_t n, int64_t nnz, const int64_t* row, const int64_t* 
   err = cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, st);
   if (err == cudaSuccess) err = cudaStreamSynchronize(st);
   if (err != cudaSuccess) { set_error("%s: %s", fn, cudaGetErrorString(err)); return (int)err; }
-  if (h_bad) { set_error("%s: edge endpoint outside [0, %lld)", fn, (long long)n); return DFGNN_ERR_INVALID_ARGUMENT; }
+  if (h_bad) {
+    set_error("%s: edge endpoint outside [0, %lld) x [0, %lld)", fn, (long long)n, (long long)n_cols);
+    return DFGNN_ERR_INVALID_ARGUMENT;
+  }
   return DFGNN_OK;
 }
 
-int dfgnn_csr_to_csc(int64_t n, int64_t nnz, const int32_t* row_ptr, const int32_t* col_ind,
+int dfgnn_csr_to_csc(int64_t n_rows, int64_t n, int64_t nnz, const int32_t* row_ptr, const int32_t* col_ind,
                      int32_t* col_ptr, int32_t* row_ind, int32_t* val_idx, void* workspace,
                      size_t workspace_bytes, void* stream) {
   const char* fn = "dfgnn_csr_to_csc";
-  if (n < 0 || nnz < 0 || n > INT32_MAX || nnz > INT32_MAX) {
-    set_error("%s: n=%lld nnz=%lld out of int32 range", fn, (long long)n, (long long)nnz);
+  if (n < 0 || n_rows < 0 || nnz < 0 || n > INT32_MAX || n_rows > INT32_MAX || nnz > INT32_MAX) {
+    set_error("%s: n_rows=%lld n_cols=%lld nnz=%lld out of int32 range", fn, (long long)n_rows,
+              (long long)n, (long long)nnz);
     return DFGNN_ERR_INVALID_ARGUMENT;
   }
   DFGNN_REQUIRE(col_ptr, fn);
@@ -158,9 +164,10 @@ int dfgnn_csr_to_csc(int64_t n, int64_t nnz, const int32_t* row_ptr, const int32
   }
   DFGNN_REQUIRE(row_ptr, fn); DFGNN_REQUIRE(col_ind, fn); DFGNN_REQUIRE(row_ind, fn);
   DFGNN_REQUIRE(val_idx, fn); DFGNN_REQUIRE(workspace, fn);
-  if (workspace_bytes < dfgnn_format_workspace_bytes(n, nnz)) {
+  const int64_t n_max = n > n_rows ? n : n_rows;
+  if (workspace_bytes < dfgnn_format_workspace_bytes(n_max, nnz)) {
     set_error("%s: workspace too small (%zu < %zu)", fn, workspace_bytes,
-              dfgnn_format_workspace_bytes(n, nnz));
+              dfgnn_format_workspace_bytes(n_max, nnz));
     return DFGNN_ERR_WORKSPACE;
   }
   const int bits = key_bits(n);
@@ -179,7 +186,7 @@ int dfgnn_csr_to_csc(int64_t n, int64_t nnz, const int32_t* row_ptr, const int32
   if (err != cudaSuccess) { set_error("%s: radix sort: %s", fn, cudaGetErrorString(err)); return (int)err; }
   seg_ptr_kernel<<<blocks(nnz + 1), 256, 0, st>>>(nnz, n, keys_out, col_ptr);
   if (int rc = check_launch(fn)) return rc;
-  row_of_kernel<<<blocks(nnz), 256, 0, st>>>(nnz, n, row_ptr, val_idx, row_ind);
+  row_of_kernel<<<blocks(nnz), 256, 0, st>>>(nnz, n_rows, row_ptr, val_idx, row_ind);
   return check_launch(fn);
 }
 

@@ -4,7 +4,7 @@
 
 using namespace dfgnn;
 
-extern "C" int dfgnn_gat_backward(int m, int nnz, int h, int f, float negative_slope,
+extern "C" int dfgnn_gat_backward(int m, int n, int nnz, int h, int f, float negative_slope,
                                   float attn_drop, const int32_t* row_ptr, const int32_t* col_ind,
                                   const int32_t* col_ptr, const int32_t* row_ind,
                                   const int32_t* permute, const float* edge_max,
@@ -15,6 +15,7 @@ extern "C" int dfgnn_gat_backward(int m, int nnz, int h, int f, float negative_s
                                   void* stream) {
   const char* fn = "dfgnn_gat_backward";
   if (int rc = check_common(fn, m, nnz, h, f)) return rc;
+  if (n < 0) { set_error("%s: invalid n=%d", fn, n); return DFGNN_ERR_INVALID_ARGUMENT; }
   DFGNN_REQUIRE(row_ptr, fn); DFGNN_REQUIRE(col_ptr, fn);
   if (nnz > 0) {
     DFGNN_REQUIRE(col_ind, fn); DFGNN_REQUIRE(row_ind, fn); DFGNN_REQUIRE(permute, fn);
@@ -28,23 +29,28 @@ extern "C" int dfgnn_gat_backward(int m, int nnz, int h, int f, float negative_s
     set_error("%s: attn_drop=%g must be in [0, 1)", fn, (double)attn_drop);
     return DFGNN_ERR_INVALID_ARGUMENT;
   }
-  if (m == 0) return DFGNN_OK;
+  if (m == 0 && n == 0) return DFGNN_OK;
   cudaStream_t st = (cudaStream_t)stream;
   // with attn_drop == 0 every edge is kept: skip the mask reads entirely
   const float* mask = attn_drop > 0.f ? edge_mask : nullptr;
-  GatBwdParams p{m, nnz, h, f, pick_rb(m, nnz), negative_slope, attn_drop, row_ptr, col_ind,
+  GatBwdParams p{m, n, nnz, h, f, pick_rb(m, nnz), pick_rb(n, nnz), negative_slope, attn_drop, row_ptr, col_ind,
                  col_ptr, row_ind, permute, edge_max, edge_sum, mask, in_feat, attn_row,
                  attn_col, grad_out, grad_feat, grad_attn_row, grad_attn_col, grad_edge};
   const dim3 grid((m + p.rb - 1) / p.rb, h);
+  const dim3 grid_c((n + p.rb_col - 1) / p.rb_col, h);
   int rc = DFGNN_OK;
   dispatch_layout(f, [&](auto tag) {
     using L = typename decltype(tag)::type;
     constexpr int C = ChunkOf<L>::C;
-    gat_bwd_row_kernel<L, C><<<grid, kNW * 32, slot_bytes<1>(), st>>>(p);
-    rc = check_launch(fn);
-    if (rc) return;
-    gat_bwd_col_kernel<L, C><<<grid, kNW * 32, slot_bytes<L::NR>(), st>>>(p);
-    rc = check_launch(fn);
+    if (m > 0) {
+      gat_bwd_row_kernel<L, C><<<grid, kNW * 32, slot_bytes<1>(), st>>>(p);
+      rc = check_launch(fn);
+      if (rc) return;
+    }
+    if (n > 0) {
+      gat_bwd_col_kernel<L, C><<<grid_c, kNW * 32, slot_bytes<L::NR>(), st>>>(p);
+      rc = check_launch(fn);
+    }
   });
   return rc;
 }

@@ -4,7 +4,7 @@
 
 using namespace dfgnn;
 
-extern "C" int dfgnn_gt_backward(int m, int nnz, int h, int f, const int32_t* row_ptr,
+extern "C" int dfgnn_gt_backward(int m, int n, int nnz, int h, int f, const int32_t* row_ptr,
                                  const int32_t* col_ind, const int32_t* /*rows*/,
                                  const float* /*val*/, const int32_t* col_ptr,
                                  const int32_t* row_ind, const int32_t* val_idx,
@@ -14,6 +14,7 @@ extern "C" int dfgnn_gt_backward(int m, int nnz, int h, int f, const int32_t* ro
                                  void* stream) {
   const char* fn = "dfgnn_gt_backward";
   if (int rc = check_common(fn, m, nnz, h, f)) return rc;
+  if (n < 0) { set_error("%s: invalid n=%d", fn, n); return DFGNN_ERR_INVALID_ARGUMENT; }
   DFGNN_REQUIRE(row_ptr, fn); DFGNN_REQUIRE(col_ptr, fn);
   if (nnz > 0) {
     DFGNN_REQUIRE(col_ind, fn); DFGNN_REQUIRE(row_ind, fn); DFGNN_REQUIRE(val_idx, fn);
@@ -21,11 +22,12 @@ extern "C" int dfgnn_gt_backward(int m, int nnz, int h, int f, const int32_t* ro
   }
   DFGNN_REQUIRE(Q, fn); DFGNN_REQUIRE(K, fn); DFGNN_REQUIRE(V, fn); DFGNN_REQUIRE(grad_out, fn);
   DFGNN_REQUIRE(grad_Q, fn); DFGNN_REQUIRE(grad_K, fn); DFGNN_REQUIRE(grad_V, fn);
-  if (m == 0) return DFGNN_OK;
+  if (m == 0 && n == 0) return DFGNN_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  GtBwdParams p{m, nnz, h, f, pick_rb(m, nnz), row_ptr, col_ind, col_ptr, row_ind, val_idx,
+  GtBwdParams p{m, n, nnz, h, f, pick_rb(m, nnz), pick_rb(n, nnz), row_ptr, col_ind, col_ptr, row_ind, val_idx,
                 Q, K, V, attn_edge, grad_out, grad_Q, grad_K, grad_V, grad_edge};
   const dim3 grid((m + p.rb - 1) / p.rb, h);
+  const dim3 grid_c((n + p.rb_col - 1) / p.rb_col, h);
   int rc = DFGNN_OK;
   dispatch_layout(f, [&](auto tag) {
     using L = typename decltype(tag)::type;
@@ -33,11 +35,15 @@ extern "C" int dfgnn_gt_backward(int m, int nnz, int h, int f, const int32_t* ro
     const size_t smem = slot_bytes<2 * L::NR>();
     ensure_smem(gt_bwd_row_kernel<L, C>, smem);
     ensure_smem(gt_bwd_col_kernel<L, C>, smem);
-    gt_bwd_row_kernel<L, C><<<grid, kNW * 32, smem, st>>>(p);
-    rc = check_launch(fn);
-    if (rc) return;
-    gt_bwd_col_kernel<L, C><<<grid, kNW * 32, smem, st>>>(p);
-    rc = check_launch(fn);
+    if (m > 0) {
+      gt_bwd_row_kernel<L, C><<<grid, kNW * 32, smem, st>>>(p);
+      rc = check_launch(fn);
+      if (rc) return;
+    }
+    if (n > 0) {
+      gt_bwd_col_kernel<L, C><<<grid_c, kNW * 32, smem, st>>>(p);
+      rc = check_launch(fn);
+    }
   });
   return rc;
 }

@@ -35,7 +35,7 @@ class SparseMatrix:
 
     def csr(self):
         """-> (indptr, indices, value_indices) like dgl.sparse (int64, as DGL returns)."""
-        row_ptr, col_ind, _, perm, _ = coo_to_csr(self.row, self.col, self.shape[0])
+        row_ptr, col_ind, _, perm, _ = coo_to_csr(self.row, self.col, self.shape[0], self.shape[1])
         return row_ptr.long(), col_ind.long(), perm.long()
 
 
@@ -44,8 +44,10 @@ def _require_cuda(t: torch.Tensor, name: str):
         raise RuntimeError(f"{name} must be on CUDA: format construction runs on the GPU only")
 
 
-def coo_to_csr(row: torch.Tensor, col: torch.Tensor, n: int):
-    """-> row_ptr[n+1] i32, col_ind[E] i32, rows[E] i32, perm[E] i32, val[E] f32 (ones)."""
+def coo_to_csr(row: torch.Tensor, col: torch.Tensor, n: int, n_cols: int = None):
+    """-> row_ptr[n+1] i32, col_ind[E] i32, rows[E] i32, perm[E] i32, val[E] f32 (ones).
+    n rows; n_cols columns (default n: the reference's square adjacency)."""
+    n_cols = n if n_cols is None else int(n_cols)
     _require_cuda(row, "row")
     _require_cuda(col, "col")
     row = row.contiguous().to(torch.int64)
@@ -61,9 +63,9 @@ def coo_to_csr(row: torch.Tensor, col: torch.Tensor, n: int):
         rows = torch.empty(nnz, dtype=torch.int32, device=dev)
         perm = torch.empty(nnz, dtype=torch.int32, device=dev)
         val = torch.empty(nnz, dtype=torch.float32, device=dev)
-        ws_bytes = int(L.dfgnn_format_workspace_bytes(n, nnz))
+        ws_bytes = int(L.dfgnn_format_workspace_bytes(max(n, n_cols), nnz))
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
-        rc = L.dfgnn_coo_to_csr(n, nnz, row.data_ptr() if nnz else None,
+        rc = L.dfgnn_coo_to_csr(n, n_cols, nnz, row.data_ptr() if nnz else None,
                                 col.data_ptr() if nnz else None, row_ptr.data_ptr(),
                                 col_ind.data_ptr() if nnz else None,
                                 rows.data_ptr() if nnz else None,
@@ -74,15 +76,17 @@ def coo_to_csr(row: torch.Tensor, col: torch.Tensor, n: int):
     return row_ptr, col_ind, rows, perm, val
 
 
-def csr_to_csc(row_ptr: torch.Tensor, col_ind: torch.Tensor):
-    """-> col_ptr[n+1], row_ind[E], val_idx[E] (all int32); val_idx = CSC pos -> CSR pos."""
+def csr_to_csc(row_ptr: torch.Tensor, col_ind: torch.Tensor, n_cols: int = None):
+    """-> col_ptr[n_cols+1], row_ind[E], val_idx[E] (all int32); val_idx = CSC pos -> CSR pos.
+    n_cols defaults to the number of rows (square adjacency)."""
     _require_cuda(row_ptr, "row_ptr")
     _require_cuda(col_ind, "col_ind")
     if row_ptr.dtype != torch.int32 or col_ind.dtype != torch.int32:
         raise RuntimeError("row_ptr and col_ind must be int32")
     row_ptr = row_ptr.contiguous()
     col_ind = col_ind.contiguous()
-    n = row_ptr.numel() - 1
+    n_rows = row_ptr.numel() - 1
+    n = n_rows if n_cols is None else int(n_cols)
     nnz = col_ind.numel()
     dev = row_ptr.device
     L = _lib.lib()
@@ -90,9 +94,9 @@ def csr_to_csc(row_ptr: torch.Tensor, col_ind: torch.Tensor):
         col_ptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
         row_ind = torch.empty(nnz, dtype=torch.int32, device=dev)
         val_idx = torch.empty(nnz, dtype=torch.int32, device=dev)
-        ws_bytes = int(L.dfgnn_format_workspace_bytes(n, nnz))
+        ws_bytes = int(L.dfgnn_format_workspace_bytes(max(n, n_rows), nnz))
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
-        rc = L.dfgnn_csr_to_csc(n, nnz, row_ptr.data_ptr(), col_ind.data_ptr() if nnz else None,
+        rc = L.dfgnn_csr_to_csc(n_rows, n, nnz, row_ptr.data_ptr(), col_ind.data_ptr() if nnz else None,
                                 col_ptr.data_ptr(), row_ind.data_ptr() if nnz else None,
                                 val_idx.data_ptr() if nnz else None, ws.data_ptr(), ws_bytes,
                                 torch.cuda.current_stream(dev).cuda_stream)

@@ -29,13 +29,16 @@ class Graph:
     """Minimal COO graph container (the subset of DGLGraph used by preprocessing)."""
 
     def __init__(self, src: torch.Tensor, dst: torch.Tensor, num_nodes: int,
-                 batch_num_nodes: Optional[torch.Tensor] = None, name: str = "graph"):
+                 batch_num_nodes: Optional[torch.Tensor] = None, name: str = "graph",
+                 num_cols: Optional[int] = None):
         assert src.shape == dst.shape and src.dim() == 1
         self._src = src
         self._dst = dst
         self._n = int(num_nodes)
         self._bnn = batch_num_nodes
         self.name = name
+        # a row-partitioned shard is rectangular: num_nodes() local rows x num_cols columns
+        self.num_cols = self._n if num_cols is None else int(num_cols)
 
     def edges(self) -> Tuple[torch.Tensor, torch.Tensor]:
         return self._src, self._dst
@@ -61,7 +64,8 @@ class Graph:
 
     def to(self, device) -> "Graph":
         bnn = None if self._bnn is None else self._bnn.to(device)
-        return Graph(self._src.to(device), self._dst.to(device), self._n, bnn, self.name)
+        return Graph(self._src.to(device), self._dst.to(device), self._n, bnn, self.name,
+                     self.num_cols)
 
     def sha256(self) -> str:
         """Fingerprint of the edge list (recorded in BASELINE.md once frozen)."""

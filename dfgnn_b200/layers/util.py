@@ -15,7 +15,7 @@ def g_to_SPmatrix(g):
     """layers/util.py:52-57: COO of the graph + the hard-coded max_neigh = 128."""
     row, col = g.edges()
     N = g.num_nodes()
-    return SparseMatrix(row, col, (N, N)), 128
+    return SparseMatrix(row, col, (N, getattr(g, "num_cols", N))), 128
 
 
 def preprocess_dglsp(g, **args):
@@ -30,21 +30,21 @@ def _smem(max_neigh: int, mult: int) -> int:
 def preprocess_CSR(g, **args):
     """layers/util.py:66-79 -> (row_ptr, col_ind, val, smem_consume=128)."""
     A, max_neigh = g_to_SPmatrix(g)
-    row_ptr, col_ind, _, _, val = coo_to_csr(A.row, A.col, A.shape[0])
+    row_ptr, col_ind, _, _, val = coo_to_csr(A.row, A.col, A.shape[0], A.shape[1])
     return row_ptr, col_ind, val, _smem(max_neigh, 1)
 
 
 def preprocess_Hyper(g, **args):
     """layers/util.py:82-100 -> (row_ptr, col_ind, rows, val, smem_consume=1024)."""
     A, max_neigh = g_to_SPmatrix(g)
-    row_ptr, col_ind, rows, _, val = coo_to_csr(A.row, A.col, A.shape[0])
+    row_ptr, col_ind, rows, _, val = coo_to_csr(A.row, A.col, A.shape[0], A.shape[1])
     return row_ptr, col_ind, rows, val, _smem(max_neigh, 8)
 
 
 def preprocess_softmax(g, **args):
     """layers/util.py:145-162 -> (row_ptr, col_ind, rows, val, smem_consume=128)."""
     A, max_neigh = g_to_SPmatrix(g)
-    row_ptr, col_ind, rows, _, val = coo_to_csr(A.row, A.col, A.shape[0])
+    row_ptr, col_ind, rows, _, val = coo_to_csr(A.row, A.col, A.shape[0], A.shape[1])
     return row_ptr, col_ind, rows, val, _smem(max_neigh, 1)
 
 
@@ -54,8 +54,8 @@ def preprocess_Hyper_fw_bw(g, fused=True):
     A, max_neigh = g_to_SPmatrix(g)
     if not fused:
         return A, None, None, None, None, None, None, None, None
-    row_ptr, col_ind, rows, _, val = coo_to_csr(A.row, A.col, A.shape[0])
-    col_ptr, row_ind, val_idx = csr_to_csc(row_ptr, col_ind)
+    row_ptr, col_ind, rows, _, val = coo_to_csr(A.row, A.col, A.shape[0], A.shape[1])
+    col_ptr, row_ind, val_idx = csr_to_csc(row_ptr, col_ind, A.shape[1])
     return A, rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx, _smem(max_neigh, 8)
 
 
@@ -64,8 +64,8 @@ def preprocess_gat_fw_bw(g):
     DFGNN/script/train/train_gatconv.py:119-136 builds with scipy).
     -> (row_ptr, col_ind, col_ptr, row_ind, permute)."""
     A, _ = g_to_SPmatrix(g)
-    row_ptr, col_ind, _, _, _ = coo_to_csr(A.row, A.col, A.shape[0])
-    col_ptr, row_ind, permute = csr_to_csc(row_ptr, col_ind)
+    row_ptr, col_ind, _, _, _ = coo_to_csr(A.row, A.col, A.shape[0], A.shape[1])
+    col_ptr, row_ind, permute = csr_to_csc(row_ptr, col_ind, A.shape[1])
     return row_ptr, col_ind, col_ptr, row_ind, permute
 
 

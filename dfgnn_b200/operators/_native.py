@@ -41,11 +41,11 @@ def _stream(ref: torch.Tensor):
     return torch.cuda.current_stream(ref.device).cuda_stream
 
 
-def _csr_dims(indptr, indices, X, fn):
+def _csr_dims(indptr, indices, X, fn, row_side=True):
     if X.dim() != 3:
         raise RuntimeError(f"{fn}: features must be [N, heads, dim], got {tuple(X.shape)}")
     m = indptr.numel() - 1
-    if X.shape[0] != m:
+    if row_side and X.shape[0] != m:
         raise RuntimeError(f"{fn}: {X.shape[0]} feature rows for {m} graph rows")
     return m, indices.numel(), X.shape[1], X.shape[2]
 
@@ -57,7 +57,8 @@ def _check_gt(fn, indptr, indices, Q, K, V, rows=None, val=None):
     _chk("val", val, torch.float32, allow_none=True)
     for n, t in (("Q", Q), ("K", K), ("V", V)):
         _chk(n, t, torch.float32)
-    if Q.shape != K.shape or Q.shape != V.shape:
+    # square adjacency: identical shapes; a row-partitioned shard has fewer Q rows than K/V rows
+    if K.shape != V.shape or Q.dim() != 3 or Q.shape[1:] != K.shape[1:]:
         raise RuntimeError(f"{fn}: Q, K, V must have the same shape")
     if val is not None and val.numel() != indices.numel():
         raise RuntimeError(f"{fn}: val and indices differ in length")
@@ -98,13 +99,14 @@ def gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem_con
         raise RuntimeError(f"{fn}: grad must have the shape of Q")
     if attn_edge.numel() != h * nnz or row_ind.numel() != nnz or val_idx.numel() != nnz:
         raise RuntimeError(f"{fn}: attn_edge / row_ind / val_idx do not match nnz={nnz}")
-    if col_ptr.numel() != m + 1:
-        raise RuntimeError(f"{fn}: col_ptr must have m+1 entries")
+    n = col_ptr.numel() - 1
+    if K.shape[0] != n:
+        raise RuntimeError(f"{fn}: col_ptr describes {n} columns but K has {K.shape[0]} rows")
     with torch.cuda.device(Q.device):
-        gq, gk, gv = torch.empty_like(Q), torch.empty_like(Q), torch.empty_like(Q)
+        gq, gk, gv = torch.empty_like(Q), torch.empty_like(K), torch.empty_like(V)
         ge = torch.empty((h, nnz), dtype=torch.float32, device=Q.device)
         rc = _lib.lib().dfgnn_gt_backward(
-            m, nnz, h, f, _ptr(row_ptr), _ptr(col_ind), _ptr(rows), _ptr(val), _ptr(col_ptr),
+            m, n, nnz, h, f, _ptr(row_ptr), _ptr(col_ind), _ptr(rows), _ptr(val), _ptr(col_ptr),
             _ptr(row_ind), _ptr(val_idx), int(smem_consume), _ptr(Q), _ptr(K), _ptr(V),
             _ptr(attn_edge), _ptr(grad), _ptr(gq), _ptr(gk), _ptr(gv), _ptr(ge), _stream(Q))
     _lib.check(rc, fn)
@@ -192,9 +194,10 @@ def _check_gat(fn, attn_row, attn_col, indptr, indices, in_feat, rows=None):
     _chk("indices", indices, torch.int32)
     _chk("rows", rows, torch.int32, allow_none=True)
     _chk("in_feat", in_feat, torch.float32)
-    m, nnz, h, f = _csr_dims(indptr, indices, in_feat, fn)
-    if attn_row.numel() != m * h or attn_col.numel() != m * h:
-        raise RuntimeError(f"{fn}: attn_row / attn_col must be [N, heads]")
+    # in_feat / attn_col are column-side (n rows), attn_row / out are row-side (m rows)
+    m, nnz, h, f = _csr_dims(indptr, indices, in_feat, fn, row_side=False)
+    if attn_row.numel() != m * h or attn_col.numel() != in_feat.shape[0] * h:
+        raise RuntimeError(f"{fn}: attn_row must be [rows, heads] and attn_col [cols, heads]")
     return m, nnz, h, f
 
 
@@ -214,7 +217,7 @@ def gat_forward(attn_row, attn_col, row_ptr, col_ind, negative_slope, in_feat, a
     m, nnz, h, f = _check_gat(fn, attn_row, attn_col, row_ptr, col_ind, in_feat)
     dev = in_feat.device
     with torch.cuda.device(dev):
-        out = torch.empty_like(in_feat)
+        out = torch.empty((m, h, f), dtype=torch.float32, device=dev)
         emax = torch.empty((m, h), dtype=torch.float32, device=dev)
         esum = torch.empty((m, h), dtype=torch.float32, device=dev)
         emask = torch.empty((nnz, h), dtype=torch.float32, device=dev)
@@ -237,18 +240,19 @@ def gat_backward(negative_slope, attn_drop, row_ptr, col_ind, col_ptr, row_ind, 
     for n, t in (("edge_max", edge_max), ("edge_sum", edge_sum), ("edge_mask", edge_mask),
                  ("grad", grad)):
         _chk(n, t, torch.float32)
-    if grad.shape != in_feat.shape:
-        raise RuntimeError(f"{fn}: grad must have the shape of in_feat")
-    if row_ind.numel() != nnz or permute.numel() != nnz or col_ptr.numel() != m + 1:
+    n = col_ptr.numel() - 1
+    if tuple(grad.shape) != (m, h, f):
+        raise RuntimeError(f"{fn}: grad must be [rows, heads, dim]")
+    if row_ind.numel() != nnz or permute.numel() != nnz or in_feat.shape[0] != n:
         raise RuntimeError(f"{fn}: CSC arrays do not match the CSR")
     dev = in_feat.device
     with torch.cuda.device(dev):
         gf = torch.empty_like(in_feat)
         gr = torch.empty((m, h), dtype=torch.float32, device=dev)
-        gc = torch.empty((m, h), dtype=torch.float32, device=dev)
+        gc = torch.empty((n, h), dtype=torch.float32, device=dev)
         ge = torch.empty((nnz, h), dtype=torch.float32, device=dev)
         rc = _lib.lib().dfgnn_gat_backward(
-            m, nnz, h, f, float(negative_slope), float(attn_drop), _ptr(row_ptr), _ptr(col_ind),
+            m, n, nnz, h, f, float(negative_slope), float(attn_drop), _ptr(row_ptr), _ptr(col_ind),
             _ptr(col_ptr), _ptr(row_ind), _ptr(permute), _ptr(edge_max), _ptr(edge_sum),
             _ptr(edge_mask), _ptr(in_feat), _ptr(attn_row), _ptr(attn_col), _ptr(grad), _ptr(gf),
             _ptr(gr), _ptr(gc), _ptr(ge), _stream(in_feat))
@@ -260,7 +264,7 @@ def _gat_inference(cname, fn, smem_consume, attn_row, attn_col, indptr, indices,
                    negative_slope, in_feat, has_smem, has_rows):
     m, nnz, h, f = _check_gat(fn, attn_row, attn_col, indptr, indices, in_feat, rows)
     with torch.cuda.device(in_feat.device):
-        out = torch.empty_like(in_feat)
+        out = torch.empty((m, h, f), dtype=torch.float32, device=in_feat.device)
         args = [int(smem_consume)] if has_smem else []
         args += [m, nnz, h, f, _ptr(attn_row), _ptr(attn_col), _ptr(indptr), _ptr(indices)]
         if has_rows:

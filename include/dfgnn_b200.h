@@ -60,7 +60,7 @@ uint64_t dfgnn_launch_count(void);
 /* ------------------------------------------------------------------------ */
 
 /* Bytes of scratch the two builders below need for a graph of n nodes / nnz edges. */
-size_t dfgnn_format_workspace_bytes(int64_t n, int64_t nnz);
+size_t dfgnn_format_workspace_bytes(int64_t n, int64_t nnz); /* n = max(n_rows, n_cols) */
 
 /*
  * COO -> CSR (+ the COO half of the hyper format).
@@ -68,12 +68,15 @@ size_t dfgnn_format_workspace_bytes(int64_t n, int64_t nnz);
  * preprocess_CSR / preprocess_Hyper / preprocess_softmax
  * (DFGNN/layers/util.py:52-57, 66-79, 82-100, 145-162).
  * Stable by row: inside a row the input edge order is kept.
- *   row, col : [nnz] int64 (what torch.stack(g.edges()) holds)
- *   row_ptr  : [n+1]; col_ind, rows : [nnz]
+ *   row, col : [nnz] int64 (what torch.stack(g.edges()) holds); row < n_rows, col < n_cols
+ *              (n_rows == n_cols for the reference's square adjacency; a row-partitioned
+ *              shard of a full graph is n_rows_local x n_cols_global)
+ *   row_ptr  : [n_rows+1]; col_ind, rows : [nnz]
  *   perm     : [nnz] sorted position -> input edge id (A.csr()'s value_indices), may be NULL
  *   val      : [nnz] float32, filled with 1.0f (A.val[val_idx] of an unweighted graph), may be NULL
  */
-int dfgnn_coo_to_csr(int64_t n, int64_t nnz, const int64_t *row, const int64_t *col,
+int dfgnn_coo_to_csr(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t *row,
+                     const int64_t *col,
                      int32_t *row_ptr, int32_t *col_ind, int32_t *rows, int32_t *perm,
                      float *val, void *workspace, size_t workspace_bytes, void *stream);
 
@@ -83,7 +86,8 @@ int dfgnn_coo_to_csr(int64_t n, int64_t nnz, const int64_t *row, const int64_t *
  * (DFGNN/layers/util.py:136-141) and the scipy tocsc() `permute` of
  * DFGNN/script/train/train_gatconv.py:119-136.  Stable by column.
  */
-int dfgnn_csr_to_csc(int64_t n, int64_t nnz, const int32_t *row_ptr, const int32_t *col_ind,
+int dfgnn_csr_to_csc(int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t *row_ptr,
+                     const int32_t *col_ind,
                      int32_t *col_ptr, int32_t *row_ind, int32_t *val_idx, void *workspace,
                      size_t workspace_bytes, void *stream);
 
@@ -107,9 +111,11 @@ int dfgnn_gt_hyper_forward(int m, int nnz, int h, int f, const int32_t *row_ptr,
 /*
  * Backward.  Replaces gt_backward (fused_gtconv.cpp:125-172 ->
  * fused_gtconv_backward.cu:193-265).  grad_edge [h, nnz] is scratch
- * (torch::empty in the reference, l.250).
+ * (torch::empty in the reference, l.250).  m = rows (row_ptr, Q, grad_out, grad_Q),
+ * n = columns (col_ptr, K, V, grad_K, grad_V); the reference reads both sizes too
+ * (fused_gtconv_backward.cu:238-239) and they are equal for a square adjacency.
  */
-int dfgnn_gt_backward(int m, int nnz, int h, int f, const int32_t *row_ptr,
+int dfgnn_gt_backward(int m, int n, int nnz, int h, int f, const int32_t *row_ptr,
                       const int32_t *col_ind, const int32_t *rows, const float *val,
                       const int32_t *col_ptr, const int32_t *row_ind, const int32_t *val_idx,
                       int smem_consume, const float *Q, const float *K, const float *V,
@@ -181,9 +187,11 @@ int dfgnn_gat_forward(int m, int nnz, int h, int f, const float *attn_row,
  * Backward.  Replaces gat_backward (fused_gatconv.cpp:291-353 ->
  * fused_gatconv_kernel.cu:1171-1244).  grad_edge [nnz, h] is scratch
  * (grad_edge_csr, l.1225).  grad_attn_col is produced by a deterministic
- * column-side sum (the reference uses atomicAdd, l.854).
+ * column-side sum (the reference uses atomicAdd, l.854).  m = rows, n = columns
+ * (grad_feat, grad_attn_col, attn_col, in_feat have n rows; the rest m).
  */
-int dfgnn_gat_backward(int m, int nnz, int h, int f, float negative_slope, float attn_drop,
+int dfgnn_gat_backward(int m, int n, int nnz, int h, int f, float negative_slope,
+                       float attn_drop,
                        const int32_t *row_ptr, const int32_t *col_ind, const int32_t *col_ptr,
                        const int32_t *row_ind, const int32_t *permute, const float *edge_max,
                        const float *edge_sum, const float *edge_mask, const float *in_feat,
