@@ -405,12 +405,12 @@ def run_ours(args):
         }
 
     # ---- GPU reference (the reference's own kernels, sm_100a) + CPU baseline, N = 1 ---
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.no_ref:
         line["gpu_reference"] = time_gpu_reference(name, conv, dim, dict(
             row_ptr=row_ptr, col_ind=col_ind, rows=rows, val=val, col_ptr=col_ptr, row_ind=row_ind,
             val_idx=val_idx), d_in, flush, args.steps, e_total)
-        if not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline(name, g_full)
+    if rank == 0 and world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(name, g_full)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -503,6 +503,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="arxiv-gat", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-ref", action="store_true", help="skip the reference-CUDA-kernel timing leg")
     ap.add_argument("--scaling", default="auto", choices=["auto", "weak", "strong"],
                     help="batched workloads at N>1: weak (own batch per GPU, default) or strong "
                          "(one global batch sharded by graph); full graphs are always row-partitioned")

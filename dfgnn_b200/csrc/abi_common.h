@@ -50,11 +50,12 @@ inline bool dispatch_layout(int f, Fn&& fn) {
   return true;
 }
 
-// Segments (rows / columns) per CTA: aim at ~64 entries per warp, within [8, kMaxRB].
+// Segments (rows / columns) per CTA: aim at ~64 entries per warp, but keep at least
+// ~4 CTAs per SM in the grid (148 SMs) so that small graphs still fill the chip; [8, kMaxRB].
 inline int pick_rb(int m, int nnz) {
   const double avg = m > 0 ? (double)nnz / (double)m : 0.0;
   int rb = 8;
-  while (rb < kMaxRB && avg * rb < 64.0 * kNW) rb <<= 1;
+  while (rb < kMaxRB && avg * rb < 64.0 * kNW && (m / (2 * rb)) >= 4 * 148) rb <<= 1;
   return rb;
 }
 
