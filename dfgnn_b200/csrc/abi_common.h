@@ -32,14 +32,17 @@ inline int check_launch(const char* what) {
 template <class T>
 struct Tag { using type = T; };
 
-// Picks the register layout for a feature width.  Returns false for f > 512.
+// Picks the lane-group layout for a feature width.  Returns false for f > 512.
+// 8 lanes per row wherever the row is at least 8 float4 wide: 4 rows per warp
+// instruction stream, 3-stage group reductions.
 template <class Fn>
 inline bool dispatch_layout(int f, Fn&& fn) {
-  if (f == 32) fn(Tag<VecLayout<8>>{});
-  else if (f == 64) fn(Tag<VecLayout<16>>{});
-  else if (f == 128) fn(Tag<VecLayout<32>>{});
-  else if (f == 256) fn(Tag<VecLayout<64>>{});
-  else if (f == 512) fn(Tag<VecLayout<128>>{});
+  if (f == 16) fn(Tag<VecLayout<4, 4>>{});
+  else if (f == 32) fn(Tag<VecLayout<8, 8>>{});
+  else if (f == 64) fn(Tag<VecLayout<16, 8>>{});
+  else if (f == 128) fn(Tag<VecLayout<32, 8>>{});
+  else if (f == 256) fn(Tag<VecLayout<64, 16>>{});
+  else if (f == 512) fn(Tag<VecLayout<128, 32>>{});
   else if (f <= 32) fn(Tag<ScalarLayout<1>>{});
   else if (f <= 64) fn(Tag<ScalarLayout<2>>{});
   else if (f <= 96) fn(Tag<ScalarLayout<3>>{});
@@ -50,12 +53,13 @@ inline bool dispatch_layout(int f, Fn&& fn) {
   return true;
 }
 
-// Segments (rows / columns) per CTA: aim at ~64 entries per warp, but keep at least
-// ~4 CTAs per SM in the grid (148 SMs) so that small graphs still fill the chip; [8, kMaxRB].
-inline int pick_rb(int m, int nnz) {
+// Segments (rows / columns) per CTA: aim at ~48 entries per lane group (kNW * G groups
+// per CTA), but keep at least ~4 CTAs per SM in the grid (148 SMs) so that small graphs
+// still fill the chip; [8, kMaxRB].
+inline int pick_rb(int m, int nnz, int G) {
   const double avg = m > 0 ? (double)nnz / (double)m : 0.0;
   int rb = 8;
-  while (rb < kMaxRB && avg * rb < 64.0 * kNW && (m / (2 * rb)) >= 4 * 148) rb <<= 1;
+  while (rb < kMaxRB && avg * rb < 48.0 * kNW * G && (m / (2 * rb)) >= 4 * 148) rb <<= 1;
   return rb;
 }
 
@@ -83,8 +87,10 @@ inline int check_common(const char* fn, int m, int nnz, int h, int f) {
     }                                                                 \
   } while (0)
 
-template <int NV>
-constexpr size_t slot_bytes() { return (size_t)kNW * 2 * Slot<NV>::kFloats * sizeof(float); }
+template <int NV, class L>
+constexpr size_t slot_bytes() {
+  return (size_t)kNW * L::G * 2 * Slot<NV, L::LPR>::kFloats * sizeof(float);
+}
 
 // kernels whose partial-result slots exceed the 48 KB default need the opt-in
 template <class K>

@@ -12,6 +12,7 @@
 //   col side   grad_feat_j = sum_i keep/(1-drop) p_ij dO_i;  grad_attn_col_j = sum_i de_ij
 //              (the reference scatters grad_attn_col with atomicAdd, l.854; here it is
 //               a column-side sum through `permute`, bit-reproducible)
+// Schedule: rowblock.cuh (lane groups in lockstep).
 #pragma once
 
 #include "rowblock.cuh"
@@ -36,53 +37,53 @@ struct GtBwdParams {
   float* grad_edge;    // [h, nnz]
 };
 
-// Sum-merge of split segments: NV floats per lane + one scalar (slot.a).
-template <int NV, class Fin>
-__device__ __forceinline__ void sum_merge_slots(float* s_slot, Fin fin) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  Slot<NV> mine(s_slot, w, 1);
+// Sum-merge of split segments: NV floats per lane + one scalar (slot.a).  Group-local.
+template <int NV, int LPR, int G, class Fin>
+__device__ __forceinline__ void sum_merge_slots(float* s_slot, int vw, int gl, Fin fin) {
+  Slot<NV, LPR> mine(s_slot, vw, 1);
   const int seg = mine.seg();
   if (seg < 0) return;
   float a = mine.a(), acc[NV];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) acc[i] = mine.v(i, lane);
-  for (int w2 = w + 1; w2 < kNW; ++w2) {
-    Slot<NV> s(s_slot, w2, 0);
+  for (int i = 0; i < NV; ++i) acc[i] = mine.v(i, gl);
+  for (int v2 = vw + 1; v2 < kNW * G; ++v2) {
+    Slot<NV, LPR> s(s_slot, v2, 0);
     if (s.seg() != seg) break;
     a += s.a();
 #pragma unroll
-    for (int i = 0; i < NV; ++i) acc[i] += s.v(i, lane);
+    for (int i = 0; i < NV; ++i) acc[i] += s.v(i, gl);
   }
   fin(seg, a, acc);
 }
 
 template <class L, int C>
 __global__ void __launch_bounds__(kNW * 32, 2) gt_bwd_row_kernel(const GtBwdParams p) {
-  constexpr int NR = L::NR, LPR = L::LPR, G = L::G, EPS = G * C;
-  static_assert(32 % EPS == 0, "edges per step must divide 32");
+  constexpr int NR = L::NR, LPR = L::LPR, G = L::G, VW = kNW * G;
+  constexpr int CH = ChunkOf<L>::kChunk;
+  static_assert(CH % C == 0 && CH <= LPR, "chunking");
   __shared__ int s_rp[kMaxRB + 1];
   __shared__ float s_s[kMaxRB];
   extern __shared__ float s_slot[];
 
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int grp = lane / LPR, gl = lane % LPR;
+  const int grp = lane / LPR, gl = lane % LPR, vw = w * G + grp;
   const int hid = blockIdx.y, h = p.h, f = p.f;
   const float* attn = p.attn + (size_t)hid * p.nnz;
   float* gedge = p.grad_edge + (size_t)hid * p.nnz;
 
-  slots_clear<2 * NR>(s_slot);
-  RowBlock b = rowblock_init(s_rp, p.row_ptr, p.m, p.rb);
+  slots_clear<2 * NR, LPR>(s_slot, vw, gl);
+  const RowBlock b = rowblock_init<G>(s_rp, p.row_ptr, p.m, p.rb, vw);
 
   // Per piece: acc2 = [A1c | A2] with A1c = sum_e p_e (dA_e - c) K_e, A2 = sum_e p_e K_e,
   // c = dA of the piece's first edge.  dQ = A1c + (c - s) * A2, which equals
   // sum_e (t_e - s p_e) K_e but keeps the subtraction at the scale of the dS terms
   // (a row with one edge gives exactly 0, like the reference's two-pass form).
   auto write_dq = [&](int r, float s, const float (&dq)[NR]) {
-    if (grp == 0) L::store(p.dQ + ((size_t)(b.seg_lb + r) * h + hid) * f, dq, gl, f);
-    if (lane == 0) s_s[r] = s;
+    L::store(p.dQ + ((size_t)(b.seg_lb + r) * h + hid) * f, dq, gl, f);
+    if (gl == 0) s_s[r] = s;
   };
 
-  for (int r = w; r < b.nseg; r += kNW)
+  for (int r = vw; r < b.nseg; r += VW)
     if (s_rp[r + 1] == s_rp[r]) {
       float z[NR];
       zero(z);
@@ -90,105 +91,103 @@ __global__ void __launch_bounds__(kNW * 32, 2) gt_bwd_row_kernel(const GtBwdPara
     }
 
   int e = b.e;
-  if (e < b.e_end) {
-    int r = find_row(s_rp, b.nseg, e);
-    while (e < b.e_end) {
+  int r = e < b.e_end ? find_row(s_rp, b.nseg, e) : 0;
+  while (__any_sync(kFull, e < b.e_end)) {
+    const bool act = e < b.e_end;
+    int rs = 0, re = 0, pend = e;
+    if (act) {
       while (s_rp[r + 1] <= e) ++r;
-      const int rs = s_rp[r], re = s_rp[r + 1];
-      const int seg_end = min(re, b.e_end);
-      const bool starts = (e == rs), ends = (seg_end == re);
+      rs = s_rp[r];
+      re = s_rp[r + 1];
+      pend = min(re, b.e_end);
+    }
+    float g[NR], acc2[2 * NR];
+    L::load(g, p.dO + ((size_t)(b.seg_lb + (act ? r : 0)) * h + hid) * f, gl, f);
+    zero(acc2);
+    float s_part = 0.f, c_ref = 0.f;
+    bool have_c = false;
 
-      float g[NR], acc2[2 * NR];
-      L::load(g, p.dO + ((size_t)(b.seg_lb + r) * h + hid) * f, gl, f);
-      zero(acc2);
-      float s_part = 0.f, c_ref = 0.f;
-      bool have_c = false;
-
-      for (int base = e; base < seg_end; base += 32) {
-        const int cnt = min(32, seg_end - base);
-        int my_col = 0;
-        float my_p = 0.f;
-        if (lane < cnt) {
-          my_col = __ldg(p.col_ind + base + lane);
-          my_p = __ldg(attn + base + lane);
+    for (int base = e; __any_sync(kFull, base < pend); base += CH) {
+      const int cnt = pend - base;
+      int my_col = 0;
+      float my_p = 0.f, my_t = 0.f;
+      if (gl < CH && gl < cnt) {
+        my_col = __ldg(p.col_ind + base + gl);
+        my_p = __ldg(attn + base + gl);
+      }
+#pragma unroll
+      for (int s = 0; s < CH; s += C) {
+        if (s > 0 && !__any_sync(kFull, s < cnt)) break;
+        float kk[C][NR], vv[C][NR], dA[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const int col = group_bcast<LPR>(my_col, s + c);
+          const size_t off = ((size_t)col * h + hid) * f;
+          if (s + c < cnt) {
+            L::load(vv[c], p.V + off, gl, f);
+            L::load(kk[c], p.K + off, gl, f);
+          } else {
+            zero(vv[c]);
+            zero(kk[c]);
+          }
         }
-        for (int s = 0; s < cnt; s += EPS) {
-          float kk[C][NR], vv[C][NR], dA[C];
 #pragma unroll
-          for (int c = 0; c < C; ++c) {
-            const int idx = s + c * G + grp;
-            const int col = __shfl_sync(kFull, my_col, idx);
-            const size_t off = ((size_t)col * h + hid) * f;
-            if (idx < cnt) {
-              L::load(vv[c], p.V + off, gl, f);
-              L::load(kk[c], p.K + off, gl, f);
-            } else {
-              zero(vv[c]);
-              zero(kk[c]);
-            }
-          }
+        for (int c = 0; c < C; ++c) dA[c] = group_sum<LPR>(dot<NR>(g, vv[c]));
+        if (!have_c) {  // the piece's first edge is slot 0 of its first step
+          c_ref = dA[0];
+          have_c = true;
+        }
 #pragma unroll
-          for (int c = 0; c < C; ++c) dA[c] = group_sum<LPR>(dot<NR>(g, vv[c]));
-          if (!have_c) {  // first edge of the piece sits in lane group 0, slot 0
-            c_ref = __shfl_sync(kFull, dA[0], 0);
-            have_c = true;
-          }
+        for (int c = 0; c < C; ++c) {
+          const float pc = group_bcast<LPR>(my_p, s + c);  // 0 beyond cnt
+          const float t = dA[c] * pc;
+          const float u = (dA[c] - c_ref) * pc;
+          if (gl == s + c) my_t = t;
+          s_part += t;
 #pragma unroll
-          for (int c = 0; c < C; ++c) {
-            const int idx = s + c * G + grp;
-            const float pc = __shfl_sync(kFull, my_p, idx);  // 0 beyond cnt
-            const float t = dA[c] * pc;
-            const float u = (dA[c] - c_ref) * pc;
-            if (gl == 0 && idx < cnt) gedge[base + idx] = t;
-            s_part += t;
-#pragma unroll
-            for (int i = 0; i < NR; ++i) {
-              acc2[i] = fmaf(u, kk[c][i], acc2[i]);
-              acc2[NR + i] = fmaf(pc, kk[c][i], acc2[NR + i]);
-            }
+          for (int i = 0; i < NR; ++i) {
+            acc2[i] = fmaf(u, kk[c][i], acc2[i]);
+            acc2[NR + i] = fmaf(pc, kk[c][i], acc2[NR + i]);
           }
         }
       }
-#pragma unroll
-      for (int off = LPR; off < 32; off <<= 1) {
-        s_part += __shfl_xor_sync(kFull, s_part, off);
-#pragma unroll
-        for (int i = 0; i < 2 * NR; ++i) acc2[i] += __shfl_xor_sync(kFull, acc2[i], off);
-      }
-      if (starts && ends) {
+      if (gl < CH && gl < cnt) gedge[base + gl] = my_t;
+    }
+    if (act) {
+      if (e == rs && pend == re) {
         float dq[NR];
 #pragma unroll
         for (int i = 0; i < NR; ++i) dq[i] = fmaf(c_ref - s_part, acc2[NR + i], acc2[i]);
         write_dq(r, s_part, dq);
       } else {
-        Slot<2 * NR> sl(s_slot, w, starts ? 1 : 0);
+        Slot<2 * NR, LPR> sl(s_slot, vw, e == rs ? 1 : 0);
 #pragma unroll
-        for (int i = 0; i < 2 * NR; ++i) sl.v(i, lane) = acc2[i];
-        if (lane == 0) { sl.a() = s_part; sl.b() = c_ref; sl.set_seg(r); }
+        for (int i = 0; i < 2 * NR; ++i) sl.v(i, gl) = acc2[i];
+        if (gl == 0) { sl.a() = s_part; sl.b() = c_ref; sl.set_seg(r); }
       }
-      e = seg_end;
     }
+    e = pend;
   }
   __syncthreads();
-  {  // rows split over warps: s first, then the re-centred vectors
-    Slot<2 * NR> mine(s_slot, w, 1);
+  {  // rows split over groups: s first, then the re-centred vectors
+    Slot<2 * NR, LPR> mine(s_slot, vw, 1);
     const int seg = mine.seg();
     if (seg >= 0) {
       float s = mine.a();
-      int w_end = w + 1;
-      for (; w_end < kNW; ++w_end) {
-        Slot<2 * NR> sl(s_slot, w_end, 0);
+      int v_end = vw + 1;
+      for (; v_end < VW; ++v_end) {
+        Slot<2 * NR, LPR> sl(s_slot, v_end, 0);
         if (sl.seg() != seg) break;
         s += sl.a();
       }
       float dq[NR];
 #pragma unroll
-      for (int i = 0; i < NR; ++i) dq[i] = fmaf(mine.b() - s, mine.v(NR + i, lane), mine.v(i, lane));
-      for (int w2 = w + 1; w2 < w_end; ++w2) {
-        Slot<2 * NR> sl(s_slot, w2, 0);
+      for (int i = 0; i < NR; ++i) dq[i] = fmaf(mine.b() - s, mine.v(NR + i, gl), mine.v(i, gl));
+      for (int v2 = vw + 1; v2 < v_end; ++v2) {
+        Slot<2 * NR, LPR> sl(s_slot, v2, 0);
         const float dc = sl.b() - s;
 #pragma unroll
-        for (int i = 0; i < NR; ++i) dq[i] += fmaf(dc, sl.v(NR + i, lane), sl.v(i, lane));
+        for (int i = 0; i < NR; ++i) dq[i] += fmaf(dc, sl.v(NR + i, gl), sl.v(i, gl));
       }
       write_dq(seg, s, dq);
     }
@@ -196,43 +195,42 @@ __global__ void __launch_bounds__(kNW * 32, 2) gt_bwd_row_kernel(const GtBwdPara
   __syncthreads();
   // t_e -> dS_e = t_e - s_i p_e   (fused_gtconv_backward.cu:171-176)
   for (int i = b.E0 + threadIdx.x; i < b.E1; i += kNW * 32) {
-    const int r = find_row(s_rp, b.nseg, i);
-    gedge[i] = fmaf(-s_s[r], __ldg(attn + i), gedge[i]);
+    const int rr = find_row(s_rp, b.nseg, i);
+    gedge[i] = fmaf(-s_s[rr], __ldg(attn + i), gedge[i]);
   }
 }
 
 // Column side: segments are CSC columns.  dV_j = sum p dO_i, dK_j = sum dS Q_i.
 template <class L, int C>
 __global__ void __launch_bounds__(kNW * 32, 2) gt_bwd_col_kernel(const GtBwdParams p) {
-  constexpr int NR = L::NR, LPR = L::LPR, G = L::G, EPS = G * C;
-  static_assert(32 % EPS == 0, "edges per step must divide 32");
+  constexpr int NR = L::NR, LPR = L::LPR, G = L::G, VW = kNW * G;
+  constexpr int CH = ChunkOf<L>::kChunk;
+  static_assert(CH % C == 0 && CH <= LPR, "chunking");
   __shared__ int s_cp[kMaxRB + 1];
   extern __shared__ float s_slot[];
 
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int grp = lane / LPR, gl = lane % LPR;
+  const int grp = lane / LPR, gl = lane % LPR, vw = w * G + grp;
   const int hid = blockIdx.y, h = p.h, f = p.f;
   const float* attn = p.attn + (size_t)hid * p.nnz;
   const float* gedge = p.grad_edge + (size_t)hid * p.nnz;
 
-  slots_clear<2 * NR>(s_slot);
-  RowBlock b = rowblock_init(s_cp, p.col_ptr, p.n, p.rb_col);
+  slots_clear<2 * NR, LPR>(s_slot, vw, gl);
+  const RowBlock b = rowblock_init<G>(s_cp, p.col_ptr, p.n, p.rb_col, vw);
 
   // acc2 = [dV | dK]
   auto finish = [&](int c, float, float (&acc2)[2 * NR]) {
-    if (grp == 0) {
-      float t[NR];
-      const size_t off = ((size_t)(b.seg_lb + c) * h + hid) * f;
+    float t[NR];
+    const size_t off = ((size_t)(b.seg_lb + c) * h + hid) * f;
 #pragma unroll
-      for (int i = 0; i < NR; ++i) t[i] = acc2[i];
-      L::store(p.dV + off, t, gl, f);
+    for (int i = 0; i < NR; ++i) t[i] = acc2[i];
+    L::store(p.dV + off, t, gl, f);
 #pragma unroll
-      for (int i = 0; i < NR; ++i) t[i] = acc2[NR + i];
-      L::store(p.dK + off, t, gl, f);
-    }
+    for (int i = 0; i < NR; ++i) t[i] = acc2[NR + i];
+    L::store(p.dK + off, t, gl, f);
   };
 
-  for (int c = w; c < b.nseg; c += kNW)
+  for (int c = vw; c < b.nseg; c += VW)
     if (s_cp[c + 1] == s_cp[c]) {
       float z[2 * NR];
       zero(z);
@@ -240,71 +238,70 @@ __global__ void __launch_bounds__(kNW * 32, 2) gt_bwd_col_kernel(const GtBwdPara
     }
 
   int e = b.e;
-  if (e < b.e_end) {
-    int c0 = find_row(s_cp, b.nseg, e);
-    while (e < b.e_end) {
+  int c0 = e < b.e_end ? find_row(s_cp, b.nseg, e) : 0;
+  while (__any_sync(kFull, e < b.e_end)) {
+    const bool act = e < b.e_end;
+    int rs = 0, re = 0, pend = e;
+    if (act) {
       while (s_cp[c0 + 1] <= e) ++c0;
-      const int rs = s_cp[c0], re = s_cp[c0 + 1];
-      const int seg_end = min(re, b.e_end);
-      const bool starts = (e == rs), ends = (seg_end == re);
-
-      float acc2[2 * NR];
-      zero(acc2);
-      for (int base = e; base < seg_end; base += 32) {
-        const int cnt = min(32, seg_end - base);
-        int my_rid = 0;
-        float my_p = 0.f, my_ds = 0.f;
-        if (lane < cnt) {
-          my_rid = __ldg(p.row_ind + base + lane);
-          const int eid = __ldg(p.val_idx + base + lane);
-          my_p = __ldg(attn + eid);
-          my_ds = __ldg(gedge + eid);
-        }
-        for (int s = 0; s < cnt; s += EPS) {
-          float go[C][NR], qq[C][NR];
+      rs = s_cp[c0];
+      re = s_cp[c0 + 1];
+      pend = min(re, b.e_end);
+    }
+    float acc2[2 * NR];
+    zero(acc2);
+    for (int base = e; __any_sync(kFull, base < pend); base += CH) {
+      const int cnt = pend - base;
+      int my_rid = 0;
+      float my_p = 0.f, my_ds = 0.f;
+      if (gl < CH && gl < cnt) {
+        my_rid = __ldg(p.row_ind + base + gl);
+        const int eid = __ldg(p.val_idx + base + gl);
+        my_p = __ldg(attn + eid);
+        my_ds = __ldg(gedge + eid);
+      }
 #pragma unroll
-          for (int c = 0; c < C; ++c) {
-            const int idx = s + c * G + grp;
-            const int rid = __shfl_sync(kFull, my_rid, idx);
-            const size_t off = ((size_t)rid * h + hid) * f;
-            if (idx < cnt) {
-              L::load(go[c], p.dO + off, gl, f);
-              L::load(qq[c], p.Q + off, gl, f);
-            } else {
-              zero(go[c]);
-              zero(qq[c]);
-            }
+      for (int s = 0; s < CH; s += C) {
+        if (s > 0 && !__any_sync(kFull, s < cnt)) break;
+        float go[C][NR], qq[C][NR];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const int rid = group_bcast<LPR>(my_rid, s + c);
+          const size_t off = ((size_t)rid * h + hid) * f;
+          if (s + c < cnt) {
+            L::load(go[c], p.dO + off, gl, f);
+            L::load(qq[c], p.Q + off, gl, f);
+          } else {
+            zero(go[c]);
+            zero(qq[c]);
           }
+        }
 #pragma unroll
-          for (int c = 0; c < C; ++c) {
-            const int idx = s + c * G + grp;
-            const float pc = __shfl_sync(kFull, my_p, idx);
-            const float ds = __shfl_sync(kFull, my_ds, idx);
+        for (int c = 0; c < C; ++c) {
+          const float pc = group_bcast<LPR>(my_p, s + c);
+          const float ds = group_bcast<LPR>(my_ds, s + c);
 #pragma unroll
-            for (int i = 0; i < NR; ++i) {
-              acc2[i] = fmaf(pc, go[c][i], acc2[i]);
-              acc2[NR + i] = fmaf(ds, qq[c][i], acc2[NR + i]);
-            }
+          for (int i = 0; i < NR; ++i) {
+            acc2[i] = fmaf(pc, go[c][i], acc2[i]);
+            acc2[NR + i] = fmaf(ds, qq[c][i], acc2[NR + i]);
           }
         }
       }
-#pragma unroll
-      for (int off = LPR; off < 32; off <<= 1)
-#pragma unroll
-        for (int i = 0; i < 2 * NR; ++i) acc2[i] += __shfl_xor_sync(kFull, acc2[i], off);
-      if (starts && ends) {
+    }
+    if (act) {
+      if (e == rs && pend == re) {
         finish(c0, 0.f, acc2);
       } else {
-        Slot<2 * NR> sl(s_slot, w, starts ? 1 : 0);
+        Slot<2 * NR, LPR> sl(s_slot, vw, e == rs ? 1 : 0);
 #pragma unroll
-        for (int i = 0; i < 2 * NR; ++i) sl.v(i, lane) = acc2[i];
-        if (lane == 0) { sl.a() = 0.f; sl.set_seg(c0); }
+        for (int i = 0; i < 2 * NR; ++i) sl.v(i, gl) = acc2[i];
+        if (gl == 0) { sl.a() = 0.f; sl.set_seg(c0); }
       }
-      e = seg_end;
     }
+    e = pend;
   }
   __syncthreads();
-  sum_merge_slots<2 * NR>(s_slot, finish);
+  sum_merge_slots<2 * NR, LPR, G>(s_slot, vw, gl, finish);
 }
 
 // ------------------------------------------------------------------------- //
@@ -331,136 +328,141 @@ struct GatBwdParams {
 };
 
 template <class L, int C>
-__global__ void __launch_bounds__(kNW * 32, 3) gat_bwd_row_kernel(const GatBwdParams p) {
-  constexpr int NR = L::NR, LPR = L::LPR, G = L::G, EPS = G * C;
-  static_assert(32 % EPS == 0, "edges per step must divide 32");
+__global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 3 : 2)) gat_bwd_row_kernel(const GatBwdParams p) {
+  constexpr int NR = L::NR, LPR = L::LPR, G = L::G, VW = kNW * G;
+  static_assert(LPR % C == 0, "chunking");
   __shared__ int s_rp[kMaxRB + 1];
   __shared__ float s_w[kMaxRB];
   extern __shared__ float s_slot[];
 
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int grp = lane / LPR, gl = lane % LPR;
+  const int grp = lane / LPR, gl = lane % LPR, vw = w * G + grp;
   const int hid = blockIdx.y, h = p.h, f = p.f;
   const float keep_scale = 1.f / (1.f - p.drop);
 
-  slots_clear<1>(s_slot);
-  RowBlock b = rowblock_init(s_rp, p.row_ptr, p.m, p.rb);
+  slots_clear<1, LPR>(s_slot, vw, gl);
+  const RowBlock b = rowblock_init<G>(s_rp, p.row_ptr, p.m, p.rb, vw);
 
-  for (int r = w; r < b.nseg; r += kNW)
-    if (s_rp[r + 1] == s_rp[r] && lane == 0) s_w[r] = 0.f;
+  for (int r = vw; r < b.nseg; r += VW)
+    if (s_rp[r + 1] == s_rp[r] && gl == 0) s_w[r] = 0.f;
 
   int e = b.e;
-  if (e < b.e_end) {
-    int r = find_row(s_rp, b.nseg, e);
-    while (e < b.e_end) {
+  int r = e < b.e_end ? find_row(s_rp, b.nseg, e) : 0;
+  while (__any_sync(kFull, e < b.e_end)) {
+    const bool act = e < b.e_end;
+    int rs = 0, re = 0, pend = e;
+    if (act) {
       while (s_rp[r + 1] <= e) ++r;
-      const int rs = s_rp[r], re = s_rp[r + 1];
-      const int seg_end = min(re, b.e_end);
-      const bool starts = (e == rs), ends = (seg_end == re);
-      const size_t node = (size_t)(b.seg_lb + r) * h + hid;
-
-      float g[NR];
-      L::load(g, p.dO + node * f, gl, f);
-      const float ar_i = __ldg(p.ar + node);
-      const float mx = __ldg(p.emax + node);
-      const float inv = 1.f / __ldg(p.esum + node);
-      float w_part = 0.f;
-
-      for (int base = e; base < seg_end; base += 32) {
-        const int cnt = min(32, seg_end - base);
-        int my_col = 0;
-        float my_p = 0.f;  // p_e * keep_e / (1 - drop)
-        if (lane < cnt) {
-          my_col = __ldg(p.col_ind + base + lane);
-          const float sc = leaky(ar_i + __ldg(p.ac + (size_t)my_col * h + hid), p.slope);
-          my_p = __expf(sc - mx) * inv;
-          if (p.emask)
-            my_p = (__ldg(p.emask + (size_t)(base + lane) * h + hid) > p.drop) ? my_p * keep_scale : 0.f;
-        }
-        for (int s = 0; s < cnt; s += EPS) {
-          float ff[C][NR];
-#pragma unroll
-          for (int c = 0; c < C; ++c) {
-            const int idx = s + c * G + grp;
-            const int col = __shfl_sync(kFull, my_col, idx);
-            if (idx < cnt) L::load(ff[c], p.feat + ((size_t)col * h + hid) * f, gl, f);
-            else zero(ff[c]);
-          }
-#pragma unroll
-          for (int c = 0; c < C; ++c) {
-            const int idx = s + c * G + grp;
-            const float pc = __shfl_sync(kFull, my_p, idx);
-            const float t = group_sum<LPR>(dot<NR>(g, ff[c])) * pc;
-            if (gl == 0 && idx < cnt) p.grad_edge[(size_t)(base + idx) * h + hid] = t;
-            w_part += t;
-          }
-        }
-      }
-#pragma unroll
-      for (int off = LPR; off < 32; off <<= 1) w_part += __shfl_xor_sync(kFull, w_part, off);
-      if (starts && ends) {
-        if (lane == 0) s_w[r] = w_part;
-      } else {
-        Slot<1> sl(s_slot, w, starts ? 1 : 0);
-        if (lane == 0) { sl.a() = w_part; sl.set_seg(r); }
-      }
-      e = seg_end;
+      rs = s_rp[r];
+      re = s_rp[r + 1];
+      pend = min(re, b.e_end);
     }
+    const size_t node = (size_t)(b.seg_lb + (act ? r : 0)) * h + hid;
+    float g[NR];
+    L::load(g, p.dO + node * f, gl, f);
+    const float ar_i = __ldg(p.ar + node);
+    const float mx = __ldg(p.emax + node);
+    const float inv = 1.f / __ldg(p.esum + node);
+    float w_lane = 0.f;
+
+    for (int base = e; __any_sync(kFull, base < pend); base += LPR) {
+      const int cnt = pend - base;
+      int my_col = 0;
+      float my_p = 0.f, my_t = 0.f;  // my_p = p_e * keep_e / (1 - drop)
+      if (gl < cnt) {
+        my_col = __ldg(p.col_ind + base + gl);
+        const float sc = leaky(ar_i + __ldg(p.ac + (size_t)my_col * h + hid), p.slope);
+        my_p = __expf(sc - mx) * inv;
+        if (p.emask)
+          my_p = (__ldg(p.emask + (size_t)(base + gl) * h + hid) > p.drop) ? my_p * keep_scale : 0.f;
+      }
+#pragma unroll
+      for (int s = 0; s < LPR; s += C) {
+        if (s > 0 && !__any_sync(kFull, s < cnt)) break;
+        float ff[C][NR];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const int col = group_bcast<LPR>(my_col, s + c);
+          if (s + c < cnt) L::load(ff[c], p.feat + ((size_t)col * h + hid) * f, gl, f);
+          else zero(ff[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float ge = group_sum<LPR>(dot<NR>(g, ff[c]));
+          if (gl == s + c) my_t = ge * my_p;  // lane s+c owns this edge
+        }
+      }
+      if (gl < cnt) p.grad_edge[(size_t)(base + gl) * h + hid] = my_t;
+      w_lane += my_t;
+    }
+    const float w_part = group_sum<LPR>(w_lane);
+    if (act) {
+      if (e == rs && pend == re) {
+        if (gl == 0) s_w[r] = w_part;
+      } else {
+        Slot<1, LPR> sl(s_slot, vw, e == rs ? 1 : 0);
+        if (gl == 0) { sl.a() = w_part; sl.set_seg(r); }
+      }
+    }
+    e = pend;
   }
   __syncthreads();
   {
-    auto fin = [&](int r, float a, float (&)[1]) { if (lane == 0) s_w[r] = a; };
-    sum_merge_slots<1>(s_slot, fin);
+    auto fin = [&](int rr, float a, float (&)[1]) { if (gl == 0) s_w[rr] = a; };
+    sum_merge_slots<1, LPR, G>(s_slot, vw, gl, fin);
   }
   __syncthreads();
-  // de_e and grad_attn_row, row-wise (fused_gatconv_kernel.cu:830-864)
-  for (int r = w; r < b.nseg; r += kNW) {
-    const size_t node = (size_t)(b.seg_lb + r) * h + hid;
-    const int rs = s_rp[r], re = s_rp[r + 1];
+  // de_e and grad_attn_row, one row per group, groups of a warp in lockstep
+  // (fused_gatconv_kernel.cu:830-864)
+  for (int r0 = w * G; r0 < b.nseg; r0 += VW) {
+    const int rr = r0 + grp;
+    const bool valid = rr < b.nseg;
+    const int rs = valid ? s_rp[rr] : 0, re = valid ? s_rp[rr + 1] : 0;
+    const size_t node = (size_t)(b.seg_lb + (valid ? rr : 0)) * h + hid;
+    const float ar_i = __ldg(p.ar + node);
+    const float mx = __ldg(p.emax + node);
+    const float inv = re > rs ? 1.f / __ldg(p.esum + node) : 0.f;
+    const float wr = valid ? s_w[rr] : 0.f;
     float rsum = 0.f;
-    if (re > rs) {
-      const float ar_i = __ldg(p.ar + node);
-      const float mx = __ldg(p.emax + node);
-      const float inv = 1.f / __ldg(p.esum + node);
-      const float wr = s_w[r];
-      for (int i = rs + lane; i < re; i += 32) {
+    for (int i = rs + gl; __any_sync(kFull, i < re); i += LPR) {
+      if (i < re) {
         const int col = __ldg(p.col_ind + i);
-        const float x = ar_i + __ldg(p.ac + (size_t)col * h + hid);
-        const float pe = __expf(leaky(x, p.slope) - mx) * inv;
+        const float x = leaky(ar_i + __ldg(p.ac + (size_t)col * h + hid), p.slope);
+        const float pe = __expf(x - mx) * inv;
         const size_t eid = (size_t)i * h + hid;
         float de = fmaf(-wr, pe, p.grad_edge[eid]);
-        if (leaky(x, p.slope) < 0.f) de *= p.slope;
+        if (x < 0.f) de *= p.slope;
         p.grad_edge[eid] = de;
         rsum += de;
       }
-      rsum = warp_sum(rsum);
     }
-    if (lane == 0) p.grad_ar[node] = rsum;
+    rsum = group_sum<LPR>(rsum);
+    if (valid && gl == 0) p.grad_ar[node] = rsum;
   }
 }
 
 template <class L, int C>
-__global__ void __launch_bounds__(kNW * 32, 3) gat_bwd_col_kernel(const GatBwdParams p) {
-  constexpr int NR = L::NR, LPR = L::LPR, G = L::G, EPS = G * C;
-  static_assert(32 % EPS == 0, "edges per step must divide 32");
+__global__ void __launch_bounds__(kNW * 32, (L::NR * C <= 32 ? 3 : 2)) gat_bwd_col_kernel(const GatBwdParams p) {
+  constexpr int NR = L::NR, LPR = L::LPR, G = L::G, VW = kNW * G;
+  static_assert(LPR % C == 0, "chunking");
   __shared__ int s_cp[kMaxRB + 1];
   extern __shared__ float s_slot[];
 
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int grp = lane / LPR, gl = lane % LPR;
+  const int grp = lane / LPR, gl = lane % LPR, vw = w * G + grp;
   const int hid = blockIdx.y, h = p.h, f = p.f;
   const float keep_scale = 1.f / (1.f - p.drop);
 
-  slots_clear<NR>(s_slot);
-  RowBlock b = rowblock_init(s_cp, p.col_ptr, p.n, p.rb_col);
+  slots_clear<NR, LPR>(s_slot, vw, gl);
+  const RowBlock b = rowblock_init<G>(s_cp, p.col_ptr, p.n, p.rb_col, vw);
 
   auto finish = [&](int c, float dac, float (&acc)[NR]) {
     const size_t node = (size_t)(b.seg_lb + c) * h + hid;
-    if (grp == 0) L::store(p.grad_feat + node * f, acc, gl, f);
-    if (lane == 0) p.grad_ac[node] = dac;
+    L::store(p.grad_feat + node * f, acc, gl, f);
+    if (gl == 0) p.grad_ac[node] = dac;
   };
 
-  for (int c = w; c < b.nseg; c += kNW)
+  for (int c = vw; c < b.nseg; c += VW)
     if (s_cp[c + 1] == s_cp[c]) {
       float z[NR];
       zero(z);
@@ -468,65 +470,65 @@ __global__ void __launch_bounds__(kNW * 32, 3) gat_bwd_col_kernel(const GatBwdPa
     }
 
   int e = b.e;
-  if (e < b.e_end) {
-    int c0 = find_row(s_cp, b.nseg, e);
-    while (e < b.e_end) {
+  int c0 = e < b.e_end ? find_row(s_cp, b.nseg, e) : 0;
+  while (__any_sync(kFull, e < b.e_end)) {
+    const bool act = e < b.e_end;
+    int rs = 0, re = 0, pend = e;
+    if (act) {
       while (s_cp[c0 + 1] <= e) ++c0;
-      const int rs = s_cp[c0], re = s_cp[c0 + 1];
-      const int seg_end = min(re, b.e_end);
-      const bool starts = (e == rs), ends = (seg_end == re);
-      const float ac_j = __ldg(p.ac + (size_t)(b.seg_lb + c0) * h + hid);
-
-      float acc[NR];
-      zero(acc);
-      float dac = 0.f;
-      for (int base = e; base < seg_end; base += 32) {
-        const int cnt = min(32, seg_end - base);
-        int my_rid = 0;
-        float my_p = 0.f;
-        if (lane < cnt) {
-          my_rid = __ldg(p.row_ind + base + lane);
-          const size_t eid = (size_t)__ldg(p.permute + base + lane) * h + hid;
-          const size_t rn = (size_t)my_rid * h + hid;
-          const float sc = leaky(__ldg(p.ar + rn) + ac_j, p.slope);
-          my_p = __expf(sc - __ldg(p.emax + rn)) / __ldg(p.esum + rn);
-          if (p.emask) my_p = (__ldg(p.emask + eid) > p.drop) ? my_p * keep_scale : 0.f;
-          dac += __ldg(p.grad_edge + eid);
-        }
-        for (int s = 0; s < cnt; s += EPS) {
-          float go[C][NR], pc[C];
-#pragma unroll
-          for (int c = 0; c < C; ++c) {
-            const int idx = s + c * G + grp;
-            const int rid = __shfl_sync(kFull, my_rid, idx);
-            pc[c] = __shfl_sync(kFull, my_p, idx);
-            if (idx < cnt) L::load(go[c], p.dO + ((size_t)rid * h + hid) * f, gl, f);
-            else zero(go[c]);
-          }
-#pragma unroll
-          for (int c = 0; c < C; ++c)
-#pragma unroll
-            for (int i = 0; i < NR; ++i) acc[i] = fmaf(pc[c], go[c][i], acc[i]);
-        }
+      rs = s_cp[c0];
+      re = s_cp[c0 + 1];
+      pend = min(re, b.e_end);
+    }
+    const float ac_j = __ldg(p.ac + (size_t)(b.seg_lb + (act ? c0 : 0)) * h + hid);
+    float acc[NR];
+    zero(acc);
+    float dac_lane = 0.f;
+    for (int base = e; __any_sync(kFull, base < pend); base += LPR) {
+      const int cnt = pend - base;
+      int my_rid = 0;
+      float my_p = 0.f;
+      if (gl < cnt) {
+        my_rid = __ldg(p.row_ind + base + gl);
+        const size_t eid = (size_t)__ldg(p.permute + base + gl) * h + hid;
+        const size_t rn = (size_t)my_rid * h + hid;
+        const float sc = leaky(__ldg(p.ar + rn) + ac_j, p.slope);
+        my_p = __expf(sc - __ldg(p.emax + rn)) / __ldg(p.esum + rn);
+        if (p.emask) my_p = (__ldg(p.emask + eid) > p.drop) ? my_p * keep_scale : 0.f;
+        dac_lane += __ldg(p.grad_edge + eid);
       }
-      dac = warp_sum(dac);
 #pragma unroll
-      for (int off = LPR; off < 32; off <<= 1)
+      for (int s = 0; s < LPR; s += C) {
+        if (s > 0 && !__any_sync(kFull, s < cnt)) break;
+        float go[C][NR], pc[C];
 #pragma unroll
-        for (int i = 0; i < NR; ++i) acc[i] += __shfl_xor_sync(kFull, acc[i], off);
-      if (starts && ends) {
+        for (int c = 0; c < C; ++c) {
+          const int rid = group_bcast<LPR>(my_rid, s + c);
+          pc[c] = group_bcast<LPR>(my_p, s + c);
+          if (s + c < cnt) L::load(go[c], p.dO + ((size_t)rid * h + hid) * f, gl, f);
+          else zero(go[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+          for (int i = 0; i < NR; ++i) acc[i] = fmaf(pc[c], go[c][i], acc[i]);
+      }
+    }
+    const float dac = group_sum<LPR>(dac_lane);
+    if (act) {
+      if (e == rs && pend == re) {
         finish(c0, dac, acc);
       } else {
-        Slot<NR> sl(s_slot, w, starts ? 1 : 0);
+        Slot<NR, LPR> sl(s_slot, vw, e == rs ? 1 : 0);
 #pragma unroll
-        for (int i = 0; i < NR; ++i) sl.v(i, lane) = acc[i];
-        if (lane == 0) { sl.a() = dac; sl.set_seg(c0); }
+        for (int i = 0; i < NR; ++i) sl.v(i, gl) = acc[i];
+        if (gl == 0) { sl.a() = dac; sl.set_seg(c0); }
       }
-      e = seg_end;
     }
+    e = pend;
   }
   __syncthreads();
-  sum_merge_slots<NR>(s_slot, finish);
+  sum_merge_slots<NR, LPR, G>(s_slot, vw, gl, finish);
 }
 
 }  // namespace dfgnn

@@ -19,42 +19,45 @@ namespace dfgnn {
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr float kNeg = -1e30f;  // "minus infinity" that survives subtraction
+constexpr float kLog2e = 1.4426950408889634f;
 
 // ------------------------------------------------------------------------- //
 // Feature-row layouts: how the f floats of one node row are spread over a    //
-// warp.  LPR lanes cooperate on one row, G = 32/LPR rows are in flight per   //
-// load instruction, every lane keeps NR floats of the row in registers.      //
+// lane group.  LPR lanes cooperate on one row and form a "virtual warp" that //
+// walks its own slice of edges; a warp holds G = 32/LPR such groups running  //
+// in lockstep.  Every lane keeps NR floats of the row in registers.          //
 // ------------------------------------------------------------------------- //
 
-// f = 4*F4 with F4 a power of two <= 32, or a multiple of 32: 16-byte loads.
-template <int F4_>
+// f = 4*F4: 16-byte loads; lane gl of the group owns float4 number v*LPR + gl
+// (one load instruction covers LPR*16 contiguous bytes per group).
+template <int F4_, int LPR_>
 struct VecLayout {
-  static_assert(F4_ >= 1 && ((F4_ < 32 && (F4_ & (F4_ - 1)) == 0) || F4_ % 32 == 0), "bad F4");
+  static_assert(LPR_ >= 1 && LPR_ <= 32 && (LPR_ & (LPR_ - 1)) == 0 && F4_ % LPR_ == 0, "bad layout");
   static constexpr int F4 = F4_;
-  static constexpr int LPR = F4 < 32 ? F4 : 32;
+  static constexpr int LPR = LPR_;
   static constexpr int VPL = F4 / LPR;
   static constexpr int G = 32 / LPR;
   static constexpr int NR = 4 * VPL;
 
   __device__ __forceinline__ static void load(float (&r)[NR], const float* __restrict__ row,
                                               int gl, int /*f*/) {
-    const float4* p = reinterpret_cast<const float4*>(row);
+    const float4* p = reinterpret_cast<const float4*>(row) + gl;
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
-      const float4 t = __ldg(p + v * LPR + gl);
+      const float4 t = __ldg(p + v * LPR);
       r[4 * v + 0] = t.x; r[4 * v + 1] = t.y; r[4 * v + 2] = t.z; r[4 * v + 3] = t.w;
     }
   }
   __device__ __forceinline__ static void store(float* __restrict__ row, const float (&r)[NR],
                                                int gl, int /*f*/) {
-    float4* p = reinterpret_cast<float4*>(row);
+    float4* p = reinterpret_cast<float4*>(row) + gl;
 #pragma unroll
     for (int v = 0; v < VPL; ++v)
-      p[v * LPR + gl] = make_float4(r[4 * v + 0], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+      p[v * LPR] = make_float4(r[4 * v + 0], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
   }
 };
 
-// any f <= 32*NT: scalar loads, lane l owns features l, l+32, ...
+// any f <= 32*NT: scalar loads, the whole warp is one group, lane l owns features l, l+32, ...
 template <int NT_>
 struct ScalarLayout {
   static constexpr int LPR = 32;
@@ -79,13 +82,16 @@ struct ScalarLayout {
   }
 };
 
-// edges a lane group keeps in flight per step: bounded by registers (2 rows of
-// NR floats per edge in the forward) and by the requirement G*C | 32.
+// edges a lane group keeps in flight per step: bounded by registers (two rows of
+// NR floats per edge in the GT kernels) and by the group's chunk of LPR edges.
 template <class L>
 struct ChunkOf {
-  static constexpr int kMax = L::NR <= 4 ? 8 : (L::NR <= 8 ? 4 : (L::NR <= 16 ? 2 : 1));
-  static constexpr int kByG = 32 / L::G;
-  static constexpr int C = kMax < kByG ? kMax : kByG;
+  static constexpr int kByReg = L::NR <= 4 ? 8 : (L::NR <= 8 ? 4 : (L::NR <= 16 ? 2 : 1));
+  static constexpr int kChunk = L::LPR < 8 ? L::LPR : 8;  // edges whose indices a group prefetches
+  static constexpr int C = kByReg < kChunk ? kByReg : kChunk;
+  // kernels that gather ONE row per edge (GAT) can keep twice as many edges in flight
+  static constexpr int kByReg1 = L::NR <= 8 ? 8 : (L::NR <= 16 ? 4 : 2);
+  static constexpr int C1 = kByReg1 < L::LPR ? kByReg1 : L::LPR;
 };
 
 template <int N>
@@ -102,12 +108,23 @@ __device__ __forceinline__ float dot(const float (&a)[N], const float (&b)[N]) {
   return s;
 }
 
-// all-reduce (sum) inside an aligned group of LPR lanes
+// all-reduce inside an aligned group of LPR lanes (the warp must be converged)
 template <int LPR>
 __device__ __forceinline__ float group_sum(float v) {
 #pragma unroll
   for (int off = LPR / 2; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off);
   return v;
+}
+template <int LPR>
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+  for (int off = LPR / 2; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, off));
+  return v;
+}
+// value held by lane `src` (0..LPR-1) of the caller's own group
+template <int LPR, class T>
+__device__ __forceinline__ T group_bcast(T v, int src) {
+  return __shfl_sync(kFull, v, src, LPR);
 }
 
 __device__ __forceinline__ float warp_sum(float v) { return group_sum<32>(v); }
@@ -130,6 +147,13 @@ __device__ __forceinline__ int find_row(const int* a, int n, int e) {
 }
 
 __device__ __forceinline__ float leaky(float x, float slope) { return x > 0.f ? x : x * slope; }
+
+// 2^x as one MUFU.EX2 (x <= 0 here; results below the normal range flush to 0)
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // counter-based uniform in (0, 1]: two rounds of a 64-bit mix (splitmix64
 // finaliser) over (seed, edge index).  Replaces the cuRAND stream the reference

@@ -33,22 +33,25 @@ extern "C" int dfgnn_gat_backward(int m, int n, int nnz, int h, int f, float neg
   cudaStream_t st = (cudaStream_t)stream;
   // with attn_drop == 0 every edge is kept: skip the mask reads entirely
   const float* mask = attn_drop > 0.f ? edge_mask : nullptr;
-  GatBwdParams p{m, n, nnz, h, f, pick_rb(m, nnz), pick_rb(n, nnz), negative_slope, attn_drop, row_ptr, col_ind,
+  GatBwdParams p{m, n, nnz, h, f, 8, 8, negative_slope, attn_drop, row_ptr, col_ind,
                  col_ptr, row_ind, permute, edge_max, edge_sum, mask, in_feat, attn_row,
                  attn_col, grad_out, grad_feat, grad_attn_row, grad_attn_col, grad_edge};
-  const dim3 grid((m + p.rb - 1) / p.rb, h);
-  const dim3 grid_c((n + p.rb_col - 1) / p.rb_col, h);
   int rc = DFGNN_OK;
   dispatch_layout(f, [&](auto tag) {
     using L = typename decltype(tag)::type;
-    constexpr int C = ChunkOf<L>::C;
+    constexpr int C = ChunkOf<L>::C1;
+    p.rb = pick_rb(m, nnz, L::G);
+    p.rb_col = pick_rb(n, nnz, L::G);
+    const dim3 grid((m + p.rb - 1) / p.rb, h);
+    const dim3 grid_c((n + p.rb_col - 1) / p.rb_col, h);
+    ensure_smem(gat_bwd_col_kernel<L, C>, slot_bytes<L::NR, L>());
     if (m > 0) {
-      gat_bwd_row_kernel<L, C><<<grid, kNW * 32, slot_bytes<1>(), st>>>(p);
+      gat_bwd_row_kernel<L, C><<<grid, kNW * 32, slot_bytes<1, L>(), st>>>(p);
       rc = check_launch(fn);
       if (rc) return;
     }
     if (n > 0) {
-      gat_bwd_col_kernel<L, C><<<grid_c, kNW * 32, slot_bytes<L::NR>(), st>>>(p);
+      gat_bwd_col_kernel<L, C><<<grid_c, kNW * 32, slot_bytes<L::NR, L>(), st>>>(p);
       rc = check_launch(fn);
     }
   });

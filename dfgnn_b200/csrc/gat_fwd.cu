@@ -21,14 +21,17 @@ int launch_gat_fwd(int m, int nnz, int h, int f, const float* ar, const float* a
     return DFGNN_ERR_INVALID_ARGUMENT;
   }
   if (m == 0) return DFGNN_OK;
-  GatFwdParams p{m, nnz, h, f, pick_rb(m, nnz), row_ptr, col_ind, ar, ac, feat,
+  GatFwdParams p{m, nnz, h, f, 8, row_ptr, col_ind, ar, ac, feat,
                  slope, drop, seed, out, emax, esum, emask};
-  const dim3 grid((m + p.rb - 1) / p.rb, h);
   int rc = DFGNN_OK;
   dispatch_layout(f, [&](auto tag) {
     using L = typename decltype(tag)::type;
-    constexpr int C = ChunkOf<L>::C;
-    gat_fwd_kernel<L, C><<<grid, kNW * 32, slot_bytes<L::NR>(), st>>>(p);
+    constexpr int C = ChunkOf<L>::C1;
+    p.rb = pick_rb(m, nnz, L::G);
+    const dim3 grid((m + p.rb - 1) / p.rb, h);
+    const size_t smem = slot_bytes<L::NR, L>();
+    ensure_smem(gat_fwd_kernel<L, C>, smem);
+    gat_fwd_kernel<L, C><<<grid, kNW * 32, smem, st>>>(p);
     rc = check_launch(fn);
   });
   return rc;

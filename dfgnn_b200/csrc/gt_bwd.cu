@@ -24,15 +24,17 @@ extern "C" int dfgnn_gt_backward(int m, int n, int nnz, int h, int f, const int3
   DFGNN_REQUIRE(grad_Q, fn); DFGNN_REQUIRE(grad_K, fn); DFGNN_REQUIRE(grad_V, fn);
   if (m == 0 && n == 0) return DFGNN_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  GtBwdParams p{m, n, nnz, h, f, pick_rb(m, nnz), pick_rb(n, nnz), row_ptr, col_ind, col_ptr, row_ind, val_idx,
+  GtBwdParams p{m, n, nnz, h, f, 8, 8, row_ptr, col_ind, col_ptr, row_ind, val_idx,
                 Q, K, V, attn_edge, grad_out, grad_Q, grad_K, grad_V, grad_edge};
-  const dim3 grid((m + p.rb - 1) / p.rb, h);
-  const dim3 grid_c((n + p.rb_col - 1) / p.rb_col, h);
   int rc = DFGNN_OK;
   dispatch_layout(f, [&](auto tag) {
     using L = typename decltype(tag)::type;
     constexpr int C = ChunkOf<L>::C;
-    const size_t smem = slot_bytes<2 * L::NR>();
+    p.rb = pick_rb(m, nnz, L::G);
+    p.rb_col = pick_rb(n, nnz, L::G);
+    const dim3 grid((m + p.rb - 1) / p.rb, h);
+    const dim3 grid_c((n + p.rb_col - 1) / p.rb_col, h);
+    const size_t smem = slot_bytes<2 * L::NR, L>();
     ensure_smem(gt_bwd_row_kernel<L, C>, smem);
     ensure_smem(gt_bwd_col_kernel<L, C>, smem);
     if (m > 0) {

@@ -9,13 +9,14 @@ int launch_dot_fwd(bool agnn, int m, int nnz, int h, int f, const int* row_ptr, 
                    const float* rn, float* out, float* attn, cudaStream_t st, const char* fn) {
   if (int rc = check_common(fn, m, nnz, h, f)) return rc;
   if (m == 0) return DFGNN_OK;
-  DotFwdParams p{m, nnz, h, f, pick_rb(m, nnz), row_ptr, col_ind, val, Q, K, V, rn, out, attn};
-  const dim3 grid((m + p.rb - 1) / p.rb, h);
+  DotFwdParams p{m, nnz, h, f, 8, row_ptr, col_ind, val, Q, K, V, rn, out, attn};
   int rc = DFGNN_OK;
   dispatch_layout(f, [&](auto tag) {
     using L = typename decltype(tag)::type;
     constexpr int C = ChunkOf<L>::C;
-    const size_t smem = slot_bytes<L::NR>();
+    p.rb = pick_rb(m, nnz, L::G);
+    const dim3 grid((m + p.rb - 1) / p.rb, h);
+    const size_t smem = slot_bytes<L::NR, L>();
     if (agnn) {
       ensure_smem(dot_fwd_kernel<L, C, true>, smem);
       dot_fwd_kernel<L, C, true><<<grid, kNW * 32, smem, st>>>(p);

@@ -1,39 +1,42 @@
 // rowblock.cuh -- the segmented row-block scaffolding shared by all conv kernels.
 //
 // A CTA of kNW warps owns `rb` consecutive segments (rows of a CSR or columns of
-// a CSC) and their contiguous range of entries [E0, E1).  That range is cut
-// into kNW equal slices, one per warp; a warp walks the *pieces* of segments
-// that intersect its slice.  A piece that covers a whole segment is finished by
-// the warp on its own; a segment cut by a slice boundary leaves partial results
-// in shared-memory slots (at most two per warp: a head piece that continues a
-// segment begun by an earlier warp, and a tail piece that begins a segment some
-// later warp finishes) which the warp that holds the segment's FIRST piece
-// folds together after one __syncthreads().
+// a CSC) and their contiguous range of entries [E0, E1).  Every warp is split
+// into G lane groups of LPR lanes ("virtual warps", VW = kNW*G per CTA); the
+// entry range is cut into VW equal slices, one per group, and a group walks the
+// *pieces* of segments that intersect its slice.  The groups of a warp advance
+// in lockstep, one piece at a time, so every shuffle runs with the warp converged.
+// A piece that covers a whole segment is finished by its group alone; a segment
+// cut by a slice boundary leaves partial results in shared-memory slots (at most
+// two per group: a head piece continuing a segment begun by an earlier group,
+// and a tail piece beginning a segment a later group finishes), which the group
+// holding the segment's FIRST piece folds together after one __syncthreads().
 //
 // This is the CSR+COO "hyper" idea of the reference (edge-balanced phase +
 // row-parallel phase, fused_gtconv_hyper.cu:63-161) restated so that no
-// per-edge score is ever staged in shared memory (no degree limit) and so that
-// a super-node row is spread over all warps of the CTA.
+// per-edge score is staged in shared memory (no degree limit), a super-node row
+// is spread over all groups of the CTA, and short rows run G per warp.
 #pragma once
 
 #include "common.cuh"
 
 namespace dfgnn {
 
-constexpr int kNW = 8;       // warps per CTA
-constexpr int kMaxRB = 64;   // max segments per CTA
+constexpr int kNW = 8;        // warps per CTA
+constexpr int kMaxRB = 128;   // max segments per CTA
 
 struct RowBlock {
   int seg_lb;   // first segment of this CTA
   int nseg;     // segments in this CTA
   int E0, E1;   // entry range of the CTA
-  int e, e_end; // entry range of this warp
+  int e, e_end; // entry range of this lane group
 };
 
-// Loads seg_ptr[seg_lb .. seg_lb+nseg] into s_ptr and computes the warp's slice.
+// Loads seg_ptr[seg_lb .. seg_lb+nseg] into s_ptr and computes the group's slice.
 // Contains a __syncthreads().
+template <int G>
 __device__ __forceinline__ RowBlock rowblock_init(int* s_ptr, const int* __restrict__ seg_ptr,
-                                                  int n_seg_total, int rb) {
+                                                  int n_seg_total, int rb, int vw) {
   RowBlock b;
   b.seg_lb = blockIdx.x * rb;
   b.nseg = min(rb, n_seg_total - b.seg_lb);
@@ -41,32 +44,31 @@ __device__ __forceinline__ RowBlock rowblock_init(int* s_ptr, const int* __restr
   __syncthreads();
   b.E0 = s_ptr[0];
   b.E1 = s_ptr[b.nseg];
-  const int w = threadIdx.x >> 5;
-  const int per = (b.E1 - b.E0 + kNW - 1) / kNW;
-  b.e = min(b.E1, b.E0 + w * per);
+  constexpr int VW = kNW * G;
+  const int per = (b.E1 - b.E0 + VW - 1) / VW;
+  b.e = min(b.E1, b.E0 + vw * per);
   b.e_end = min(b.E1, b.e + per);
   return b;
 }
 
-// A partial-result slot: NV floats per lane (stored [NV][32], conflict free)
+// A partial-result slot of one lane group: NV floats per lane (stored [NV][LPR])
 // followed by 4 scalars: {a, b, seg (int), unused}.
-template <int NV>
+template <int NV, int LPR>
 struct Slot {
-  static constexpr int kFloats = NV * 32 + 4;
+  static constexpr int kFloats = NV * LPR + 4;
   float* base;
-  __device__ __forceinline__ Slot(float* smem, int warp, int which)
-      : base(smem + (size_t)(warp * 2 + which) * kFloats) {}
-  __device__ __forceinline__ int seg() const { return reinterpret_cast<const int*>(base)[NV * 32 + 2]; }
-  __device__ __forceinline__ void set_seg(int s) { reinterpret_cast<int*>(base)[NV * 32 + 2] = s; }
-  __device__ __forceinline__ float& a() { return base[NV * 32 + 0]; }
-  __device__ __forceinline__ float& b() { return base[NV * 32 + 1]; }
-  __device__ __forceinline__ float& v(int i, int lane) { return base[i * 32 + lane]; }
+  __device__ __forceinline__ Slot(float* smem, int vw, int which)
+      : base(smem + (size_t)(vw * 2 + which) * kFloats) {}
+  __device__ __forceinline__ int seg() const { return reinterpret_cast<const int*>(base)[NV * LPR + 2]; }
+  __device__ __forceinline__ void set_seg(int s) { reinterpret_cast<int*>(base)[NV * LPR + 2] = s; }
+  __device__ __forceinline__ float& a() { return base[NV * LPR + 0]; }
+  __device__ __forceinline__ float& b() { return base[NV * LPR + 1]; }
+  __device__ __forceinline__ float& v(int i, int gl) { return base[i * LPR + gl]; }
 };
 
-template <int NV>
-__device__ __forceinline__ void slots_clear(float* smem) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (lane < 2) Slot<NV>(smem, w, lane).set_seg(-1);
+template <int NV, int LPR>
+__device__ __forceinline__ void slots_clear(float* smem, int vw, int gl) {
+  if (gl < 2) Slot<NV, LPR>(smem, vw, gl).set_seg(-1);
 }
 
 }  // namespace dfgnn
