@@ -12,7 +12,8 @@ import subprocess
 from ctypes import c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdfgnn_b200.so")
+# DFGNN_B200_LIB selects another build of the same ABI (developer variants, tools/kbench.py)
+LIB_PATH = os.environ.get("DFGNN_B200_LIB") or os.path.join(_HERE, "libdfgnn_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 _lib = None

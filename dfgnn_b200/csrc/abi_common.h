@@ -14,6 +14,13 @@
 #include "common.cuh"
 #include "rowblock.cuh"
 
+#ifndef DFGNN_LPR64
+#define DFGNN_LPR64 8
+#endif
+#ifndef DFGNN_LPR128
+#define DFGNN_LPR128 8
+#endif
+
 namespace dfgnn {
 
 void set_error(const char* fmt, ...);
@@ -39,8 +46,8 @@ template <class Fn>
 inline bool dispatch_layout(int f, Fn&& fn) {
   if (f == 16) fn(Tag<VecLayout<4, 4>>{});
   else if (f == 32) fn(Tag<VecLayout<8, 8>>{});
-  else if (f == 64) fn(Tag<VecLayout<16, 8>>{});
-  else if (f == 128) fn(Tag<VecLayout<32, 8>>{});
+  else if (f == 64) fn(Tag<VecLayout<16, DFGNN_LPR64>>{});
+  else if (f == 128) fn(Tag<VecLayout<32, DFGNN_LPR128>>{});
   else if (f == 256) fn(Tag<VecLayout<64, 16>>{});
   else if (f == 512) fn(Tag<VecLayout<128, 32>>{});
   else if (f <= 32) fn(Tag<ScalarLayout<1>>{});

@@ -12,7 +12,7 @@
 //   col side   grad_feat_j = sum_i keep/(1-drop) p_ij dO_i;  grad_attn_col_j = sum_i de_ij
 //              (the reference scatters grad_attn_col with atomicAdd, l.854; here it is
 //               a column-side sum through `permute`, bit-reproducible)
-// Schedule: rowblock.cuh (lane groups in lockstep).
+// Schedule: rowblock.cuh (walk_pieces).
 #pragma once
 
 #include "rowblock.cuh"
@@ -57,7 +57,7 @@ __device__ __forceinline__ void sum_merge_slots(float* s_slot, int vw, int gl, F
 }
 
 template <class L, int C>
-__global__ void __launch_bounds__(kNW * 32, 2) gt_bwd_row_kernel(const GtBwdParams p) {
+__global__ void __launch_bounds__(kNW * 32, 16 / kNW) gt_bwd_row_kernel(const GtBwdParams p) {
   constexpr int NR = L::NR, LPR = L::LPR, G = L::G, VW = kNW * G;
   constexpr int CH = ChunkOf<L>::kChunk;
   static_assert(CH % C == 0 && CH <= LPR, "chunking");
@@ -70,6 +70,11 @@ __global__ void __launch_bounds__(kNW * 32, 2) gt_bwd_row_kernel(const GtBwdPara
   const int hid = blockIdx.y, h = p.h, f = p.f;
   const float* attn = p.attn + (size_t)hid * p.nnz;
   float* gedge = p.grad_edge + (size_t)hid * p.nnz;
+  const RowAddr<L> ra(h, f, hid, gl);
+  const char* Gb = ra.base(p.dO);
+  const char* Kb = ra.base(p.K);
+  const char* Vb = ra.base(p.V);
+  char* DQb = ra.base(p.dQ);
 
   slots_clear<2 * NR, LPR>(s_slot, vw, gl);
   const RowBlock b = rowblock_init<G>(s_rp, p.row_ptr, p.m, p.rb, vw);
@@ -79,7 +84,7 @@ __global__ void __launch_bounds__(kNW * 32, 2) gt_bwd_row_kernel(const GtBwdPara
   // sum_e (t_e - s p_e) K_e but keeps the subtraction at the scale of the dS terms
   // (a row with one edge gives exactly 0, like the reference's two-pass form).
   auto write_dq = [&](int r, float s, const float (&dq)[NR]) {
-    L::store(p.dQ + ((size_t)(b.seg_lb + r) * h + hid) * f, dq, gl, f);
+    L::store(ra.at(DQb, b.seg_lb + r), dq, gl, f);
     if (gl == 0) s_s[r] = s;
   };
 
@@ -90,84 +95,77 @@ __global__ void __launch_bounds__(kNW * 32, 2) gt_bwd_row_kernel(const GtBwdPara
       write_dq(r, 0.f, z);
     }
 
-  int e = b.e;
-  int r = e < b.e_end ? find_row(s_rp, b.nseg, e) : 0;
-  while (__any_sync(kFull, e < b.e_end)) {
-    const bool act = e < b.e_end;
-    int rs = 0, re = 0, pend = e;
-    if (act) {
-      while (s_rp[r + 1] <= e) ++r;
-      rs = s_rp[r];
-      re = s_rp[r + 1];
-      pend = min(re, b.e_end);
-    }
-    float g[NR], acc2[2 * NR];
-    L::load(g, p.dO + ((size_t)(b.seg_lb + (act ? r : 0)) * h + hid) * f, gl, f);
-    zero(acc2);
-    float s_part = 0.f, c_ref = 0.f;
-    bool have_c = false;
-
-    for (int base = e; __any_sync(kFull, base < pend); base += CH) {
-      const int cnt = pend - base;
-      int my_col = 0;
-      float my_p = 0.f, my_t = 0.f;
-      if (gl < CH && gl < cnt) {
-        my_col = __ldg(p.col_ind + base + gl);
-        my_p = __ldg(attn + base + gl);
-      }
+  float g[NR], acc2[2 * NR];
+  zero(g);
+  zero(acc2);
+  float s_part = 0.f, c_ref = 0.f;
+  bool have_c = false;
+  walk_pieces<CH>(
+      b, s_rp,
+      [&](int r) {
+        L::load(g, ra.at(Gb, b.seg_lb + r), gl, f);
+        zero(acc2);
+        s_part = 0.f;
+        c_ref = 0.f;
+        have_c = false;
+      },
+      [&](int base, int cnt) {
+        int my_col = 0;
+        float my_p = 0.f, my_t = 0.f;
+        if (gl < cnt) {
+          my_col = __ldg(p.col_ind + base + gl);
+          my_p = __ldg(attn + base + gl);
+        }
 #pragma unroll
-      for (int s = 0; s < CH; s += C) {
-        if (s > 0 && !__any_sync(kFull, s < cnt)) break;
-        float kk[C][NR], vv[C][NR], dA[C];
+        for (int s = 0; s < CH; s += C) {
+          if (s > 0 && !__any_sync(kFull, s < cnt)) break;
+          float kk[C][NR], vv[C][NR], dA[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const int col = group_bcast<LPR>(my_col, s + c);
-          const size_t off = ((size_t)col * h + hid) * f;
-          if (s + c < cnt) {
-            L::load(vv[c], p.V + off, gl, f);
-            L::load(kk[c], p.K + off, gl, f);
-          } else {
-            zero(vv[c]);
-            zero(kk[c]);
+          for (int c = 0; c < C; ++c) {
+            const int col = group_bcast<LPR>(my_col, s + c);
+            if (s + c < cnt) {
+              L::load(vv[c], ra.at(Vb, col), gl, f);
+              L::load(kk[c], ra.at(Kb, col), gl, f);
+            } else {
+              zero(vv[c]);
+              zero(kk[c]);
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < C; ++c) dA[c] = group_sum<LPR>(dot<NR>(g, vv[c]));
+          if (!have_c && cnt > 0) {  // the piece's first edge is slot 0 of its first step
+            c_ref = dA[0];
+            have_c = true;
+          }
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const float pc = group_bcast<LPR>(my_p, s + c);  // 0 beyond cnt
+            const float t = dA[c] * pc;
+            const float u = (dA[c] - c_ref) * pc;
+            if (gl == s + c) my_t = t;
+            s_part += t;
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+              acc2[i] = fmaf(u, kk[c][i], acc2[i]);
+              acc2[NR + i] = fmaf(pc, kk[c][i], acc2[NR + i]);
+            }
           }
         }
+        if (gl < cnt) gedge[base + gl] = my_t;
+      },
+      [&](int r, bool first, bool last) {
+        if (first && last) {
+          float dq[NR];
 #pragma unroll
-        for (int c = 0; c < C; ++c) dA[c] = group_sum<LPR>(dot<NR>(g, vv[c]));
-        if (!have_c) {  // the piece's first edge is slot 0 of its first step
-          c_ref = dA[0];
-          have_c = true;
+          for (int i = 0; i < NR; ++i) dq[i] = fmaf(c_ref - s_part, acc2[NR + i], acc2[i]);
+          write_dq(r, s_part, dq);
+        } else {
+          Slot<2 * NR, LPR> sl(s_slot, vw, first ? 1 : 0);
+#pragma unroll
+          for (int i = 0; i < 2 * NR; ++i) sl.v(i, gl) = acc2[i];
+          if (gl == 0) { sl.a() = s_part; sl.b() = c_ref; sl.set_seg(r); }
         }
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const float pc = group_bcast<LPR>(my_p, s + c);  // 0 beyond cnt
-          const float t = dA[c] * pc;
-          const float u = (dA[c] - c_ref) * pc;
-          if (gl == s + c) my_t = t;
-          s_part += t;
-#pragma unroll
-          for (int i = 0; i < NR; ++i) {
-            acc2[i] = fmaf(u, kk[c][i], acc2[i]);
-            acc2[NR + i] = fmaf(pc, kk[c][i], acc2[NR + i]);
-          }
-        }
-      }
-      if (gl < CH && gl < cnt) gedge[base + gl] = my_t;
-    }
-    if (act) {
-      if (e == rs && pend == re) {
-        float dq[NR];
-#pragma unroll
-        for (int i = 0; i < NR; ++i) dq[i] = fmaf(c_ref - s_part, acc2[NR + i], acc2[i]);
-        write_dq(r, s_part, dq);
-      } else {
-        Slot<2 * NR, LPR> sl(s_slot, vw, e == rs ? 1 : 0);
-#pragma unroll
-        for (int i = 0; i < 2 * NR; ++i) sl.v(i, gl) = acc2[i];
-        if (gl == 0) { sl.a() = s_part; sl.b() = c_ref; sl.set_seg(r); }
-      }
-    }
-    e = pend;
-  }
+      });
   __syncthreads();
   {  // rows split over groups: s first, then the re-centred vectors
     Slot<2 * NR, LPR> mine(s_slot, vw, 1);
@@ -202,7 +200,7 @@ __global__ void __launch_bounds__(kNW * 32, 2) gt_bwd_row_kernel(const GtBwdPara
 
 // Column side: segments are CSC columns.  dV_j = sum p dO_i, dK_j = sum dS Q_i.
 template <class L, int C>
-__global__ void __launch_bounds__(kNW * 32, 2) gt_bwd_col_kernel(const GtBwdParams p) {
+__global__ void __launch_bounds__(kNW * 32, 16 / kNW) gt_bwd_col_kernel(const GtBwdParams p) {
   constexpr int NR = L::NR, LPR = L::LPR, G = L::G, VW = kNW * G;
   constexpr int CH = ChunkOf<L>::kChunk;
   static_assert(CH % C == 0 && CH <= LPR, "chunking");
@@ -214,6 +212,11 @@ __global__ void __launch_bounds__(kNW * 32, 2) gt_bwd_col_kernel(const GtBwdPara
   const int hid = blockIdx.y, h = p.h, f = p.f;
   const float* attn = p.attn + (size_t)hid * p.nnz;
   const float* gedge = p.grad_edge + (size_t)hid * p.nnz;
+  const RowAddr<L> ra(h, f, hid, gl);
+  const char* Gb = ra.base(p.dO);
+  const char* Qb = ra.base(p.Q);
+  char* DVb = ra.base(p.dV);
+  char* DKb = ra.base(p.dK);
 
   slots_clear<2 * NR, LPR>(s_slot, vw, gl);
   const RowBlock b = rowblock_init<G>(s_cp, p.col_ptr, p.n, p.rb_col, vw);
@@ -221,13 +224,12 @@ __global__ void __launch_bounds__(kNW * 32, 2) gt_bwd_col_kernel(const GtBwdPara
   // acc2 = [dV | dK]
   auto finish = [&](int c, float, float (&acc2)[2 * NR]) {
     float t[NR];
-    const size_t off = ((size_t)(b.seg_lb + c) * h + hid) * f;
 #pragma unroll
     for (int i = 0; i < NR; ++i) t[i] = acc2[i];
-    L::store(p.dV + off, t, gl, f);
+    L::store(ra.at(DVb, b.seg_lb + c), t, gl, f);
 #pragma unroll
     for (int i = 0; i < NR; ++i) t[i] = acc2[NR + i];
-    L::store(p.dK + off, t, gl, f);
+    L::store(ra.at(DKb, b.seg_lb + c), t, gl, f);
   };
 
   for (int c = vw; c < b.nseg; c += VW)
@@ -237,69 +239,56 @@ __global__ void __launch_bounds__(kNW * 32, 2) gt_bwd_col_kernel(const GtBwdPara
       finish(c, 0.f, z);
     }
 
-  int e = b.e;
-  int c0 = e < b.e_end ? find_row(s_cp, b.nseg, e) : 0;
-  while (__any_sync(kFull, e < b.e_end)) {
-    const bool act = e < b.e_end;
-    int rs = 0, re = 0, pend = e;
-    if (act) {
-      while (s_cp[c0 + 1] <= e) ++c0;
-      rs = s_cp[c0];
-      re = s_cp[c0 + 1];
-      pend = min(re, b.e_end);
-    }
-    float acc2[2 * NR];
-    zero(acc2);
-    for (int base = e; __any_sync(kFull, base < pend); base += CH) {
-      const int cnt = pend - base;
-      int my_rid = 0;
-      float my_p = 0.f, my_ds = 0.f;
-      if (gl < CH && gl < cnt) {
-        my_rid = __ldg(p.row_ind + base + gl);
-        const int eid = __ldg(p.val_idx + base + gl);
-        my_p = __ldg(attn + eid);
-        my_ds = __ldg(gedge + eid);
-      }
-#pragma unroll
-      for (int s = 0; s < CH; s += C) {
-        if (s > 0 && !__any_sync(kFull, s < cnt)) break;
-        float go[C][NR], qq[C][NR];
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const int rid = group_bcast<LPR>(my_rid, s + c);
-          const size_t off = ((size_t)rid * h + hid) * f;
-          if (s + c < cnt) {
-            L::load(go[c], p.dO + off, gl, f);
-            L::load(qq[c], p.Q + off, gl, f);
-          } else {
-            zero(go[c]);
-            zero(qq[c]);
-          }
+  float acc2[2 * NR];
+  zero(acc2);
+  walk_pieces<CH>(
+      b, s_cp, [&](int) { zero(acc2); },
+      [&](int base, int cnt) {
+        int my_rid = 0;
+        float my_p = 0.f, my_ds = 0.f;
+        if (gl < cnt) {
+          my_rid = __ldg(p.row_ind + base + gl);
+          const int eid = __ldg(p.val_idx + base + gl);
+          my_p = __ldg(attn + eid);
+          my_ds = __ldg(gedge + eid);
         }
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const float pc = group_bcast<LPR>(my_p, s + c);
-          const float ds = group_bcast<LPR>(my_ds, s + c);
+        for (int s = 0; s < CH; s += C) {
+          if (s > 0 && !__any_sync(kFull, s < cnt)) break;
+          float go[C][NR], qq[C][NR];
 #pragma unroll
-          for (int i = 0; i < NR; ++i) {
-            acc2[i] = fmaf(pc, go[c][i], acc2[i]);
-            acc2[NR + i] = fmaf(ds, qq[c][i], acc2[NR + i]);
+          for (int c = 0; c < C; ++c) {
+            const int rid = group_bcast<LPR>(my_rid, s + c);
+            if (s + c < cnt) {
+              L::load(go[c], ra.at(Gb, rid), gl, f);
+              L::load(qq[c], ra.at(Qb, rid), gl, f);
+            } else {
+              zero(go[c]);
+              zero(qq[c]);
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const float pc = group_bcast<LPR>(my_p, s + c);
+            const float ds = group_bcast<LPR>(my_ds, s + c);
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+              acc2[i] = fmaf(pc, go[c][i], acc2[i]);
+              acc2[NR + i] = fmaf(ds, qq[c][i], acc2[NR + i]);
+            }
           }
         }
-      }
-    }
-    if (act) {
-      if (e == rs && pend == re) {
-        finish(c0, 0.f, acc2);
-      } else {
-        Slot<2 * NR, LPR> sl(s_slot, vw, e == rs ? 1 : 0);
+      },
+      [&](int c0, bool first, bool last) {
+        if (first && last) {
+          finish(c0, 0.f, acc2);
+        } else {
+          Slot<2 * NR, LPR> sl(s_slot, vw, first ? 1 : 0);
 #pragma unroll
-        for (int i = 0; i < 2 * NR; ++i) sl.v(i, gl) = acc2[i];
-        if (gl == 0) { sl.a() = 0.f; sl.set_seg(c0); }
-      }
-    }
-    e = pend;
-  }
+          for (int i = 0; i < 2 * NR; ++i) sl.v(i, gl) = acc2[i];
+          if (gl == 0) { sl.a() = 0.f; sl.set_seg(c0); }
+        }
+      });
   __syncthreads();
   sum_merge_slots<2 * NR, LPR, G>(s_slot, vw, gl, finish);
 }
@@ -328,7 +317,7 @@ struct GatBwdParams {
 };
 
 template <class L, int C>
-__global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 3 : 2)) gat_bwd_row_kernel(const GatBwdParams p) {
+__global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : 16) / kNW) gat_bwd_row_kernel(const GatBwdParams p) {
   constexpr int NR = L::NR, LPR = L::LPR, G = L::G, VW = kNW * G;
   static_assert(LPR % C == 0, "chunking");
   __shared__ int s_rp[kMaxRB + 1];
@@ -339,6 +328,10 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 3 : 2)) gat_bwd_row_ke
   const int grp = lane / LPR, gl = lane % LPR, vw = w * G + grp;
   const int hid = blockIdx.y, h = p.h, f = p.f;
   const float keep_scale = 1.f / (1.f - p.drop);
+  const RowAddr<L> ra(h, f, hid, gl);
+  const char* Gb = ra.base(p.dO);
+  const char* Fb = ra.base(p.feat);
+  const float* acb = p.ac + hid;
 
   slots_clear<1, LPR>(s_slot, vw, gl);
   const RowBlock b = rowblock_init<G>(s_rp, p.row_ptr, p.m, p.rb, vw);
@@ -346,66 +339,56 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 3 : 2)) gat_bwd_row_ke
   for (int r = vw; r < b.nseg; r += VW)
     if (s_rp[r + 1] == s_rp[r] && gl == 0) s_w[r] = 0.f;
 
-  int e = b.e;
-  int r = e < b.e_end ? find_row(s_rp, b.nseg, e) : 0;
-  while (__any_sync(kFull, e < b.e_end)) {
-    const bool act = e < b.e_end;
-    int rs = 0, re = 0, pend = e;
-    if (act) {
-      while (s_rp[r + 1] <= e) ++r;
-      rs = s_rp[r];
-      re = s_rp[r + 1];
-      pend = min(re, b.e_end);
-    }
-    const size_t node = (size_t)(b.seg_lb + (act ? r : 0)) * h + hid;
-    float g[NR];
-    L::load(g, p.dO + node * f, gl, f);
-    const float ar_i = __ldg(p.ar + node);
-    const float mx = __ldg(p.emax + node);
-    const float inv = 1.f / __ldg(p.esum + node);
-    float w_lane = 0.f;
-
-    for (int base = e; __any_sync(kFull, base < pend); base += LPR) {
-      const int cnt = pend - base;
-      int my_col = 0;
-      float my_p = 0.f, my_t = 0.f;  // my_p = p_e * keep_e / (1 - drop)
-      if (gl < cnt) {
-        my_col = __ldg(p.col_ind + base + gl);
-        const float sc = leaky(ar_i + __ldg(p.ac + (size_t)my_col * h + hid), p.slope);
-        my_p = __expf(sc - mx) * inv;
-        if (p.emask)
-          my_p = (__ldg(p.emask + (size_t)(base + gl) * h + hid) > p.drop) ? my_p * keep_scale : 0.f;
-      }
-#pragma unroll
-      for (int s = 0; s < LPR; s += C) {
-        if (s > 0 && !__any_sync(kFull, s < cnt)) break;
-        float ff[C][NR];
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const int col = group_bcast<LPR>(my_col, s + c);
-          if (s + c < cnt) L::load(ff[c], p.feat + ((size_t)col * h + hid) * f, gl, f);
-          else zero(ff[c]);
+  float g[NR], ar_i = 0.f, mx = 0.f, inv = 0.f, w_lane = 0.f;
+  zero(g);
+  walk_pieces<LPR>(
+      b, s_rp,
+      [&](int r) {
+        const size_t node = (size_t)(b.seg_lb + r) * h + hid;
+        L::load(g, ra.at(Gb, b.seg_lb + r), gl, f);
+        ar_i = __ldg(p.ar + node);
+        mx = __ldg(p.emax + node);
+        inv = 1.f / __ldg(p.esum + node);
+        w_lane = 0.f;
+      },
+      [&](int base, int cnt) {
+        int my_col = 0;
+        float my_p = 0.f, my_t = 0.f;  // my_p = p_e * keep_e / (1 - drop)
+        if (gl < cnt) {
+          my_col = __ldg(p.col_ind + base + gl);
+          const float sc = leaky(ar_i + __ldg(acb + (size_t)(unsigned)my_col * (unsigned)h), p.slope);
+          my_p = fast_exp(sc - mx) * inv;
+          if (p.emask)
+            my_p = (__ldg(p.emask + (size_t)(base + gl) * h + hid) > p.drop) ? my_p * keep_scale : 0.f;
         }
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const float ge = group_sum<LPR>(dot<NR>(g, ff[c]));
-          if (gl == s + c) my_t = ge * my_p;  // lane s+c owns this edge
+        for (int s = 0; s < LPR; s += C) {
+          if (s > 0 && !__any_sync(kFull, s < cnt)) break;
+          float ff[C][NR];
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const int col = group_bcast<LPR>(my_col, s + c);
+            if (s + c < cnt) L::load(ff[c], ra.at(Fb, col), gl, f);
+            else zero(ff[c]);
+          }
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const float ge = group_sum<LPR>(dot<NR>(g, ff[c]));
+            if (gl == s + c) my_t = ge * my_p;  // lane s+c owns this edge
+          }
         }
-      }
-      if (gl < cnt) p.grad_edge[(size_t)(base + gl) * h + hid] = my_t;
-      w_lane += my_t;
-    }
-    const float w_part = group_sum<LPR>(w_lane);
-    if (act) {
-      if (e == rs && pend == re) {
-        if (gl == 0) s_w[r] = w_part;
-      } else {
-        Slot<1, LPR> sl(s_slot, vw, e == rs ? 1 : 0);
-        if (gl == 0) { sl.a() = w_part; sl.set_seg(r); }
-      }
-    }
-    e = pend;
-  }
+        if (gl < cnt) p.grad_edge[(size_t)(base + gl) * h + hid] = my_t;
+        w_lane += my_t;
+      },
+      [&](int r, bool first, bool last) {
+        const float w_part = group_sum_local<LPR>(w_lane, lane);
+        if (first && last) {
+          if (gl == 0) s_w[r] = w_part;
+        } else {
+          Slot<1, LPR> sl(s_slot, vw, first ? 1 : 0);
+          if (gl == 0) { sl.a() = w_part; sl.set_seg(r); }
+        }
+      });
   __syncthreads();
   {
     auto fin = [&](int rr, float a, float (&)[1]) { if (gl == 0) s_w[rr] = a; };
@@ -427,8 +410,8 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 3 : 2)) gat_bwd_row_ke
     for (int i = rs + gl; __any_sync(kFull, i < re); i += LPR) {
       if (i < re) {
         const int col = __ldg(p.col_ind + i);
-        const float x = leaky(ar_i + __ldg(p.ac + (size_t)col * h + hid), p.slope);
-        const float pe = __expf(x - mx) * inv;
+        const float x = leaky(ar_i + __ldg(acb + (size_t)(unsigned)col * (unsigned)h), p.slope);
+        const float pe = fast_exp(x - mx) * inv;
         const size_t eid = (size_t)i * h + hid;
         float de = fmaf(-wr, pe, p.grad_edge[eid]);
         if (x < 0.f) de *= p.slope;
@@ -442,7 +425,7 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 3 : 2)) gat_bwd_row_ke
 }
 
 template <class L, int C>
-__global__ void __launch_bounds__(kNW * 32, (L::NR * C <= 32 ? 3 : 2)) gat_bwd_col_kernel(const GatBwdParams p) {
+__global__ void __launch_bounds__(kNW * 32, (L::NR * C <= 32 ? 24 : 16) / kNW) gat_bwd_col_kernel(const GatBwdParams p) {
   constexpr int NR = L::NR, LPR = L::LPR, G = L::G, VW = kNW * G;
   static_assert(LPR % C == 0, "chunking");
   __shared__ int s_cp[kMaxRB + 1];
@@ -452,13 +435,16 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR * C <= 32 ? 3 : 2)) gat_bwd_c
   const int grp = lane / LPR, gl = lane % LPR, vw = w * G + grp;
   const int hid = blockIdx.y, h = p.h, f = p.f;
   const float keep_scale = 1.f / (1.f - p.drop);
+  const RowAddr<L> ra(h, f, hid, gl);
+  const char* Gb = ra.base(p.dO);
+  char* GFb = ra.base(p.grad_feat);
 
   slots_clear<NR, LPR>(s_slot, vw, gl);
   const RowBlock b = rowblock_init<G>(s_cp, p.col_ptr, p.n, p.rb_col, vw);
 
   auto finish = [&](int c, float dac, float (&acc)[NR]) {
     const size_t node = (size_t)(b.seg_lb + c) * h + hid;
-    L::store(p.grad_feat + node * f, acc, gl, f);
+    L::store(ra.at(GFb, b.seg_lb + c), acc, gl, f);
     if (gl == 0) p.grad_ac[node] = dac;
   };
 
@@ -469,64 +455,55 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR * C <= 32 ? 3 : 2)) gat_bwd_c
       finish(c, 0.f, z);
     }
 
-  int e = b.e;
-  int c0 = e < b.e_end ? find_row(s_cp, b.nseg, e) : 0;
-  while (__any_sync(kFull, e < b.e_end)) {
-    const bool act = e < b.e_end;
-    int rs = 0, re = 0, pend = e;
-    if (act) {
-      while (s_cp[c0 + 1] <= e) ++c0;
-      rs = s_cp[c0];
-      re = s_cp[c0 + 1];
-      pend = min(re, b.e_end);
-    }
-    const float ac_j = __ldg(p.ac + (size_t)(b.seg_lb + (act ? c0 : 0)) * h + hid);
-    float acc[NR];
-    zero(acc);
-    float dac_lane = 0.f;
-    for (int base = e; __any_sync(kFull, base < pend); base += LPR) {
-      const int cnt = pend - base;
-      int my_rid = 0;
-      float my_p = 0.f;
-      if (gl < cnt) {
-        my_rid = __ldg(p.row_ind + base + gl);
-        const size_t eid = (size_t)__ldg(p.permute + base + gl) * h + hid;
-        const size_t rn = (size_t)my_rid * h + hid;
-        const float sc = leaky(__ldg(p.ar + rn) + ac_j, p.slope);
-        my_p = __expf(sc - __ldg(p.emax + rn)) / __ldg(p.esum + rn);
-        if (p.emask) my_p = (__ldg(p.emask + eid) > p.drop) ? my_p * keep_scale : 0.f;
-        dac_lane += __ldg(p.grad_edge + eid);
-      }
-#pragma unroll
-      for (int s = 0; s < LPR; s += C) {
-        if (s > 0 && !__any_sync(kFull, s < cnt)) break;
-        float go[C][NR], pc[C];
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const int rid = group_bcast<LPR>(my_rid, s + c);
-          pc[c] = group_bcast<LPR>(my_p, s + c);
-          if (s + c < cnt) L::load(go[c], p.dO + ((size_t)rid * h + hid) * f, gl, f);
-          else zero(go[c]);
+  float ac_j = 0.f, acc[NR], dac_lane = 0.f;
+  zero(acc);
+  walk_pieces<LPR>(
+      b, s_cp,
+      [&](int c0) {
+        ac_j = __ldg(p.ac + (size_t)(b.seg_lb + c0) * h + hid);
+        zero(acc);
+        dac_lane = 0.f;
+      },
+      [&](int base, int cnt) {
+        int my_rid = 0;
+        float my_p = 0.f;
+        if (gl < cnt) {
+          my_rid = __ldg(p.row_ind + base + gl);
+          const size_t eid = (size_t)__ldg(p.permute + base + gl) * h + hid;
+          const size_t rn = (size_t)my_rid * h + hid;
+          const float sc = leaky(__ldg(p.ar + rn) + ac_j, p.slope);
+          my_p = fast_exp(sc - __ldg(p.emax + rn)) / __ldg(p.esum + rn);
+          if (p.emask) my_p = (__ldg(p.emask + eid) > p.drop) ? my_p * keep_scale : 0.f;
+          dac_lane += __ldg(p.grad_edge + eid);
         }
 #pragma unroll
-        for (int c = 0; c < C; ++c)
+        for (int s = 0; s < LPR; s += C) {
+          if (s > 0 && !__any_sync(kFull, s < cnt)) break;
+          float go[C][NR], pc[C];
 #pragma unroll
-          for (int i = 0; i < NR; ++i) acc[i] = fmaf(pc[c], go[c][i], acc[i]);
-      }
-    }
-    const float dac = group_sum<LPR>(dac_lane);
-    if (act) {
-      if (e == rs && pend == re) {
-        finish(c0, dac, acc);
-      } else {
-        Slot<NR, LPR> sl(s_slot, vw, e == rs ? 1 : 0);
+          for (int c = 0; c < C; ++c) {
+            const int rid = group_bcast<LPR>(my_rid, s + c);
+            pc[c] = group_bcast<LPR>(my_p, s + c);
+            if (s + c < cnt) L::load(go[c], ra.at(Gb, rid), gl, f);
+            else zero(go[c]);
+          }
 #pragma unroll
-        for (int i = 0; i < NR; ++i) sl.v(i, gl) = acc[i];
-        if (gl == 0) { sl.a() = dac; sl.set_seg(c0); }
-      }
-    }
-    e = pend;
-  }
+          for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int i = 0; i < NR; ++i) acc[i] = fmaf(pc[c], go[c][i], acc[i]);
+        }
+      },
+      [&](int c0, bool first, bool last) {
+        const float dac = group_sum_local<LPR>(dac_lane, lane);
+        if (first && last) {
+          finish(c0, dac, acc);
+        } else {
+          Slot<NR, LPR> sl(s_slot, vw, first ? 1 : 0);
+#pragma unroll
+          for (int i = 0; i < NR; ++i) sl.v(i, gl) = acc[i];
+          if (gl == 0) { sl.a() = dac; sl.set_seg(c0); }
+        }
+      });
   __syncthreads();
   sum_merge_slots<NR, LPR, G>(s_slot, vw, gl, finish);
 }

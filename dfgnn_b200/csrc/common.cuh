@@ -39,9 +39,11 @@ struct VecLayout {
   static constexpr int G = 32 / LPR;
   static constexpr int NR = 4 * VPL;
 
+  // `row` = row start + lane_off(gl) bytes (see RowAddr)
+  __device__ __forceinline__ static int lane_off(int gl) { return gl * 16; }
   __device__ __forceinline__ static void load(float (&r)[NR], const float* __restrict__ row,
-                                              int gl, int /*f*/) {
-    const float4* p = reinterpret_cast<const float4*>(row) + gl;
+                                              int /*gl*/, int /*f*/) {
+    const float4* p = reinterpret_cast<const float4*>(row);
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
       const float4 t = __ldg(p + v * LPR);
@@ -49,8 +51,8 @@ struct VecLayout {
     }
   }
   __device__ __forceinline__ static void store(float* __restrict__ row, const float (&r)[NR],
-                                               int gl, int /*f*/) {
-    float4* p = reinterpret_cast<float4*>(row) + gl;
+                                               int /*gl*/, int /*f*/) {
+    float4* p = reinterpret_cast<float4*>(row);
 #pragma unroll
     for (int v = 0; v < VPL; ++v)
       p[v * LPR] = make_float4(r[4 * v + 0], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
@@ -64,21 +66,39 @@ struct ScalarLayout {
   static constexpr int G = 1;
   static constexpr int NR = NT_;
 
+  __device__ __forceinline__ static int lane_off(int gl) { return gl * 4; }
   __device__ __forceinline__ static void load(float (&r)[NR], const float* __restrict__ row,
                                               int gl, int f) {
 #pragma unroll
-    for (int t = 0; t < NR; ++t) {
-      const int d = t * 32 + gl;
-      r[t] = d < f ? __ldg(row + d) : 0.f;
-    }
+    for (int t = 0; t < NR; ++t) r[t] = (t * 32 + gl) < f ? __ldg(row + t * 32) : 0.f;
   }
   __device__ __forceinline__ static void store(float* __restrict__ row, const float (&r)[NR],
                                                int gl, int f) {
 #pragma unroll
-    for (int t = 0; t < NR; ++t) {
-      const int d = t * 32 + gl;
-      if (d < f) row[d] = r[t];
-    }
+    for (int t = 0; t < NR; ++t)
+      if ((t * 32 + gl) < f) row[t * 32] = r[t];
+  }
+};
+
+// Row addressing with ONE 32x32+64 multiply-add per gathered row: every thread keeps
+// byte pointers that already contain its head and lane offsets.
+template <class L>
+struct RowAddr {
+  uint32_t stride_b;  // bytes between consecutive node rows = h * f * 4
+  int hid, f, gl;
+  __device__ __forceinline__ RowAddr(int h, int f_, int hid_, int gl_)
+      : stride_b((uint32_t)h * (uint32_t)f_ * 4u), hid(hid_), f(f_), gl(gl_) {}
+  __device__ __forceinline__ const char* base(const float* t) const {
+    return reinterpret_cast<const char*>(t + (size_t)hid * f) + L::lane_off(gl);
+  }
+  __device__ __forceinline__ char* base(float* t) const {
+    return reinterpret_cast<char*>(t + (size_t)hid * f) + L::lane_off(gl);
+  }
+  __device__ __forceinline__ const float* at(const char* b, int row) const {
+    return reinterpret_cast<const float*>(b + (uint64_t)(uint32_t)row * stride_b);
+  }
+  __device__ __forceinline__ float* at(char* b, int row) const {
+    return reinterpret_cast<float*>(b + (uint64_t)(uint32_t)row * stride_b);
   }
 };
 
@@ -90,7 +110,7 @@ struct ChunkOf {
   static constexpr int kChunk = L::LPR < 8 ? L::LPR : 8;  // edges whose indices a group prefetches
   static constexpr int C = kByReg < kChunk ? kByReg : kChunk;
   // kernels that gather ONE row per edge (GAT) can keep twice as many edges in flight
-  static constexpr int kByReg1 = L::NR <= 8 ? 8 : (L::NR <= 16 ? 4 : 2);
+  static constexpr int kByReg1 = L::NR <= 4 ? 8 : (L::NR <= 8 ? 4 : (L::NR <= 16 ? 4 : 2));
   static constexpr int C1 = kByReg1 < L::LPR ? kByReg1 : L::LPR;
 };
 
@@ -121,6 +141,15 @@ __device__ __forceinline__ float group_max(float v) {
   for (int off = LPR / 2; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, off));
   return v;
 }
+// group all-reduce that is legal in group-divergent code: only the caller's own group
+// takes part (every lane of the group must be there)
+template <int LPR>
+__device__ __forceinline__ float group_sum_local(float v, int lane) {
+  const unsigned mask = LPR == 32 ? kFull : (((1u << (LPR & 31)) - 1u) << (lane & ~(LPR - 1)));
+#pragma unroll
+  for (int off = LPR / 2; off > 0; off >>= 1) v += __shfl_xor_sync(mask, v, off);
+  return v;
+}
 // value held by lane `src` (0..LPR-1) of the caller's own group
 template <int LPR, class T>
 __device__ __forceinline__ T group_bcast(T v, int src) {
@@ -148,12 +177,13 @@ __device__ __forceinline__ int find_row(const int* a, int n, int e) {
 
 __device__ __forceinline__ float leaky(float x, float slope) { return x > 0.f ? x : x * slope; }
 
-// 2^x as one MUFU.EX2 (x <= 0 here; results below the normal range flush to 0)
+// e^x and 2^x as one MUFU.EX2 (x <= 0 here; results below the normal range flush to 0)
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float fast_exp(float x) { return fast_exp2(x * kLog2e); }
 
 // counter-based uniform in (0, 1]: two rounds of a 64-bit mix (splitmix64
 // finaliser) over (seed, edge index).  Replaces the cuRAND stream the reference

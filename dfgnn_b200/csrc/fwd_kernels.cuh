@@ -6,7 +6,7 @@
 //   gat_fwd_kernel<L, C>         GAT  : s_ij = leakyrelu(ar_i + ac_j), O_i = sum_j keep_ij p_ij feat_j
 //
 // Maths spec: SURVEY.md section 8 (restating fused_gtconv_hyper.cu:31-163 and
-// fused_gatconv_kernel.cu:24-125).  Schedule: rowblock.cuh (lane groups in lockstep).
+// fused_gatconv_kernel.cu:24-125).  Schedule: rowblock.cuh (walk_pieces).
 #pragma once
 
 #include "rowblock.cuh"
@@ -63,7 +63,7 @@ __device__ __forceinline__ void softmax_merge_slots(float* s_slot, int vw, int g
 // Scores are kept in the base-2 exponent domain (Q is pre-multiplied by log2 e),
 // so every exponential is one ex2.approx.
 template <class L, int C, bool AGNN>
-__global__ void __launch_bounds__(kNW * 32, 2) dot_fwd_kernel(const DotFwdParams p) {
+__global__ void __launch_bounds__(kNW * 32, 16 / kNW) dot_fwd_kernel(const DotFwdParams p) {
   constexpr int NR = L::NR, LPR = L::LPR, G = L::G, VW = kNW * G;
   constexpr int CH = ChunkOf<L>::kChunk;  // edges per index prefetch (<= LPR)
   static_assert(CH % C == 0 && CH <= LPR, "chunking");
@@ -77,6 +77,11 @@ __global__ void __launch_bounds__(kNW * 32, 2) dot_fwd_kernel(const DotFwdParams
   const bool train = p.attn != nullptr;
   const bool use_w = AGNN || p.val != nullptr;
   float* attn = train ? p.attn + (size_t)hid * p.nnz : nullptr;
+  const RowAddr<L> ra(h, f, hid, gl);
+  const char* Qb = ra.base(p.Q);
+  const char* Kb = ra.base(p.K);
+  const char* Vb = ra.base(p.V);
+  char* Ob = ra.base(p.out);
 
   slots_clear<NR, LPR>(s_slot, vw, gl);
   const RowBlock b = rowblock_init<G>(s_rp, p.row_ptr, p.m, p.rb, vw);
@@ -85,7 +90,7 @@ __global__ void __launch_bounds__(kNW * 32, 2) dot_fwd_kernel(const DotFwdParams
     const float inv = l > 0.f ? 1.f / l : 0.f;
 #pragma unroll
     for (int i = 0; i < NR; ++i) acc[i] *= inv;
-    L::store(p.out + ((size_t)(b.seg_lb + r) * h + hid) * f, acc, gl, f);
+    L::store(ra.at(Ob, b.seg_lb + r), acc, gl, f);
     if (gl == 0) { s_m[r] = m; s_inv[r] = inv; }
   };
 
@@ -97,92 +102,83 @@ __global__ void __launch_bounds__(kNW * 32, 2) dot_fwd_kernel(const DotFwdParams
       finish(r, kNeg, 0.f, z);
     }
 
-  int e = b.e;
-  int r = e < b.e_end ? find_row(s_rp, b.nseg, e) : 0;
-  while (__any_sync(kFull, e < b.e_end)) {  // one piece per group per iteration
-    const bool act = e < b.e_end;
-    int rs = 0, re = 0, pend = e;
-    if (act) {
-      while (s_rp[r + 1] <= e) ++r;
-      rs = s_rp[r];
-      re = s_rp[r + 1];
-      pend = min(re, b.e_end);
-    }
-    const size_t node = (size_t)(b.seg_lb + (act ? r : 0)) * h + hid;
-    float q[NR], acc[NR];
-    L::load(q, p.Q + node * f, gl, f);
+  float q[NR], acc[NR];
+  zero(q);
+  zero(acc);
+  float rn_i = 1.f, m_run = kNeg, l_run = 0.f;
+  walk_pieces<CH>(
+      b, s_rp,
+      [&](int r) {
+        L::load(q, ra.at(Qb, b.seg_lb + r), gl, f);
 #pragma unroll
-    for (int i = 0; i < NR; ++i) q[i] *= kLog2e;
-    zero(acc);
-    const float rn_i = AGNN ? __ldg(p.rn + node) : 1.f;
-    float m_run = kNeg, l_run = 0.f;
-
-    for (int base = e; __any_sync(kFull, base < pend); base += CH) {
-      const int cnt = pend - base;  // edges of this group's piece left (<= 0: group idles)
-      int my_col = 0;
-      float my_w = 1.f, my_sc = 0.f;
-      if (gl < CH && gl < cnt) {
-        my_col = __ldg(p.col_ind + base + gl);
-        if (AGNN) my_w = __ldg(p.rn + (size_t)my_col * h + hid) * rn_i;
-        else if (p.val) my_w = __ldg(p.val + base + gl);
-      }
+        for (int i = 0; i < NR; ++i) q[i] *= kLog2e;
+        if (AGNN) rn_i = __ldg(p.rn + (size_t)(b.seg_lb + r) * h + hid);
+        zero(acc);
+        m_run = kNeg;
+        l_run = 0.f;
+      },
+      [&](int base, int cnt) {
+        int my_col = 0;
+        float my_w = 1.f, my_sc = 0.f;
+        if (gl < cnt) {
+          my_col = __ldg(p.col_ind + base + gl);
+          if (AGNN) my_w = __ldg(p.rn + (size_t)my_col * h + hid) * rn_i;
+          else if (p.val) my_w = __ldg(p.val + base + gl);
+        }
 #pragma unroll
-      for (int s = 0; s < CH; s += C) {
-        if (s > 0 && !__any_sync(kFull, s < cnt)) break;
-        float kk[AGNN ? 1 : C][NR], vv[C][NR], d[C];
-        bool ok[C];
+        for (int s = 0; s < CH; s += C) {
+          if (s > 0 && !__any_sync(kFull, s < cnt)) break;
+          float kk[AGNN ? 1 : C][NR], vv[C][NR], d[C];
+          bool ok[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-          ok[c] = s + c < cnt;
-          const int col = group_bcast<LPR>(my_col, s + c);
-          const size_t off = ((size_t)col * h + hid) * f;
-          if (ok[c]) {
-            if (!AGNN) L::load(kk[c], p.K + off, gl, f);
-            L::load(vv[c], p.V + off, gl, f);
-          } else {
-            if (!AGNN) zero(kk[c]);
-            zero(vv[c]);
+          for (int c = 0; c < C; ++c) {
+            ok[c] = s + c < cnt;
+            const int col = group_bcast<LPR>(my_col, s + c);
+            if (ok[c]) {
+              if (!AGNN) L::load(kk[c], ra.at(Kb, col), gl, f);
+              L::load(vv[c], ra.at(Vb, col), gl, f);
+            } else {
+              if (!AGNN) zero(kk[c]);
+              zero(vv[c]);
+            }
           }
+          float cm = kNeg;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            float dc = AGNN ? dot<NR>(q, vv[c]) : dot<NR>(q, kk[AGNN ? 0 : c]);
+            dc = group_sum<LPR>(dc);
+            if (use_w) dc *= group_bcast<LPR>(my_w, s + c);
+            if (gl == s + c) my_sc = dc;
+            d[c] = dc;
+            cm = ok[c] ? fmaxf(cm, dc) : cm;
+          }
+          const float m_new = fmaxf(m_run, cm);
+          const float scale = fast_exp2(m_run - m_new);
+#pragma unroll
+          for (int i = 0; i < NR; ++i) acc[i] *= scale;
+          float ps = 0.f;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const float pc = ok[c] ? fast_exp2(d[c] - m_new) : 0.f;
+            ps += pc;
+#pragma unroll
+            for (int i = 0; i < NR; ++i) acc[i] = fmaf(pc, vv[c][i], acc[i]);
+          }
+          l_run = fmaf(l_run, scale, ps);
+          m_run = m_new;
         }
-        float cm = kNeg;
+        if (train && gl < cnt) attn[base + gl] = my_sc;  // raw score, normalised below
+      },
+      [&](int r, bool first, bool last) {
+        if (first && last) {
+          finish(r, m_run, l_run, acc);
+        } else {
+          Slot<NR, LPR> sl(s_slot, vw, first ? 1 : 0);
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-          float dc = AGNN ? dot<NR>(q, vv[c]) : dot<NR>(q, kk[AGNN ? 0 : c]);
-          dc = group_sum<LPR>(dc);
-          if (use_w) dc *= group_bcast<LPR>(my_w, s + c);
-          if (gl == s + c) my_sc = dc;
-          d[c] = dc;
-          cm = ok[c] ? fmaxf(cm, dc) : cm;
+          for (int i = 0; i < NR; ++i) sl.v(i, gl) = acc[i];
+          if (gl == 0) { sl.a() = m_run; sl.b() = l_run; sl.set_seg(r); }
         }
-        const float m_new = fmaxf(m_run, cm);
-        const float scale = fast_exp2(m_run - m_new);
-#pragma unroll
-        for (int i = 0; i < NR; ++i) acc[i] *= scale;
-        float ps = 0.f;
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const float pc = ok[c] ? fast_exp2(d[c] - m_new) : 0.f;
-          ps += pc;
-#pragma unroll
-          for (int i = 0; i < NR; ++i) acc[i] = fmaf(pc, vv[c][i], acc[i]);
-        }
-        l_run = fmaf(l_run, scale, ps);
-        m_run = m_new;
-      }
-      if (train && gl < CH && gl < cnt) attn[base + gl] = my_sc;  // raw score, normalised below
-    }
-    if (act) {
-      if (e == rs && pend == re) {
-        finish(r, m_run, l_run, acc);
-      } else {
-        Slot<NR, LPR> sl(s_slot, vw, e == rs ? 1 : 0);
-#pragma unroll
-        for (int i = 0; i < NR; ++i) sl.v(i, gl) = acc[i];
-        if (gl == 0) { sl.a() = m_run; sl.b() = l_run; sl.set_seg(r); }
-      }
-    }
-    e = pend;
-  }
+      });
   __syncthreads();
   softmax_merge_slots<NR, LPR, G>(s_slot, vw, gl, finish);
 
@@ -217,7 +213,7 @@ template <int NR>
 __device__ __forceinline__ void softmax_merge_e(float& m, float& l, float (&acc)[NR], float m2,
                                                 float l2, const float (&acc2)[NR]) {
   const float mn = fmaxf(m, m2);
-  const float sa = __expf(m - mn), sb = __expf(m2 - mn);
+  const float sa = fast_exp(m - mn), sb = fast_exp(m2 - mn);
   l = l * sa + l2 * sb;
 #pragma unroll
   for (int i = 0; i < NR; ++i) acc[i] = acc[i] * sa + acc2[i] * sb;
@@ -225,7 +221,7 @@ __device__ __forceinline__ void softmax_merge_e(float& m, float& l, float (&acc)
 }
 
 template <class L, int C>
-__global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 3 : 2)) gat_fwd_kernel(const GatFwdParams p) {
+__global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : 16) / kNW) gat_fwd_kernel(const GatFwdParams p) {
   constexpr int NR = L::NR, LPR = L::LPR, G = L::G, VW = kNW * G;
   static_assert(LPR % C == 0, "chunking");
   __shared__ int s_rp[kMaxRB + 1];
@@ -236,6 +232,10 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 3 : 2)) gat_fwd_kernel
   const int hid = blockIdx.y, h = p.h, f = p.f;
   const bool use_mask = p.emask != nullptr;
   const float keep_scale = 1.f / (1.f - p.drop);
+  const RowAddr<L> ra(h, f, hid, gl);
+  const char* Fb = ra.base(p.feat);
+  char* Ob = ra.base(p.out);
+  const float* acb = p.ac + hid;
 
   slots_clear<NR, LPR>(s_slot, vw, gl);
   const RowBlock b = rowblock_init<G>(s_rp, p.row_ptr, p.m, p.rb, vw);
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 3 : 2)) gat_fwd_kernel
     const float inv = l > 0.f ? 1.f / l : 0.f;
 #pragma unroll
     for (int i = 0; i < NR; ++i) acc[i] *= inv;
-    L::store(p.out + node * f, acc, gl, f);
+    L::store(ra.at(Ob, b.seg_lb + r), acc, gl, f);
     if (gl == 0 && p.emax) {  // saved for backward (fused_gatconv_kernel.cu:66-68, 89-91)
       p.emax[node] = l > 0.f ? m : -1e38f;
       p.esum[node] = l;
@@ -259,73 +259,65 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 3 : 2)) gat_fwd_kernel
       finish(r, kNeg, 0.f, z);
     }
 
-  int e = b.e;
-  int r = e < b.e_end ? find_row(s_rp, b.nseg, e) : 0;
-  while (__any_sync(kFull, e < b.e_end)) {
-    const bool act = e < b.e_end;
-    int rs = 0, re = 0, pend = e;
-    if (act) {
-      while (s_rp[r + 1] <= e) ++r;
-      rs = s_rp[r];
-      re = s_rp[r + 1];
-      pend = min(re, b.e_end);
-    }
-    const float ar_i = __ldg(p.ar + (size_t)(b.seg_lb + (act ? r : 0)) * h + hid);
-    float acc[NR];
-    zero(acc);
-    float m_run = kNeg, l_lane = 0.f;
-
-    for (int base = e; __any_sync(kFull, base < pend); base += LPR) {
-      const int cnt = pend - base;  // <= 0: group idles
-      int my_col = 0;
-      float sc = kNeg;
-      if (gl < cnt) {  // lane gl scores edge base + gl
-        my_col = __ldg(p.col_ind + base + gl);
-        sc = leaky(ar_i + __ldg(p.ac + (size_t)my_col * h + hid), p.slope);
-      }
-      const float m_new = fmaxf(m_run, group_max<LPR>(sc));
-      const float scale = __expf(m_run - m_new);
-      float pe = gl < cnt ? __expf(sc - m_new) : 0.f;
-      l_lane = fmaf(l_lane, scale, pe);
-      m_run = m_new;
-      if (use_mask && gl < cnt) {  // dropout on the attention weights
-        const size_t eid = (size_t)(base + gl) * h + hid;
-        const float u = uniform01(p.seed, eid);
-        p.emask[eid] = u;
-        pe = (u > p.drop) ? pe * keep_scale : 0.f;
-      }
-#pragma unroll
-      for (int i = 0; i < NR; ++i) acc[i] *= scale;
-#pragma unroll
-      for (int s = 0; s < LPR; s += C) {
-        if (s > 0 && !__any_sync(kFull, s < cnt)) break;
-        float vv[C][NR], pc[C];
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const int col = group_bcast<LPR>(my_col, s + c);
-          pc[c] = group_bcast<LPR>(pe, s + c);  // 0 beyond cnt
-          if (s + c < cnt) L::load(vv[c], p.feat + ((size_t)col * h + hid) * f, gl, f);
-          else zero(vv[c]);
+  float ar_i = 0.f, acc[NR], m_run = kNeg, l_lane = 0.f;
+  zero(acc);
+  walk_pieces<LPR>(
+      b, s_rp,
+      [&](int r) {
+        ar_i = __ldg(p.ar + (size_t)(b.seg_lb + r) * h + hid);
+        zero(acc);
+        m_run = kNeg;
+        l_lane = 0.f;
+      },
+      [&](int base, int cnt) {
+        int my_col = 0;
+        float sc = kNeg;
+        if (gl < cnt) {  // lane gl scores edge base + gl
+          my_col = __ldg(p.col_ind + base + gl);
+          sc = leaky(ar_i + __ldg(acb + (size_t)(unsigned)my_col * (unsigned)h), p.slope);
+        }
+        const float m_new = fmaxf(m_run, group_max<LPR>(sc));
+        const float scale = fast_exp(m_run - m_new);
+        float pe = gl < cnt ? fast_exp(sc - m_new) : 0.f;
+        l_lane = fmaf(l_lane, scale, pe);
+        m_run = m_new;
+        if (use_mask && gl < cnt) {  // dropout on the attention weights
+          const size_t eid = (size_t)(base + gl) * h + hid;
+          // attn_drop == 0 keeps every edge: any mask value in (0, 1] says so, skip the generator
+          const float u = p.drop > 0.f ? uniform01(p.seed, eid) : 1.f;
+          p.emask[eid] = u;
+          pe = (u > p.drop) ? pe * keep_scale : 0.f;
         }
 #pragma unroll
-        for (int c = 0; c < C; ++c)
+        for (int i = 0; i < NR; ++i) acc[i] *= scale;
 #pragma unroll
-          for (int i = 0; i < NR; ++i) acc[i] = fmaf(pc[c], vv[c][i], acc[i]);
-      }
-    }
-    const float l_run = group_sum<LPR>(l_lane);
-    if (act) {
-      if (e == rs && pend == re) {
-        finish(r, m_run, l_run, acc);
-      } else {
-        Slot<NR, LPR> sl(s_slot, vw, e == rs ? 1 : 0);
+        for (int s = 0; s < LPR; s += C) {
+          if (s > 0 && !__any_sync(kFull, s < cnt)) break;
+          float vv[C][NR], pc[C];
 #pragma unroll
-        for (int i = 0; i < NR; ++i) sl.v(i, gl) = acc[i];
-        if (gl == 0) { sl.a() = m_run; sl.b() = l_run; sl.set_seg(r); }
-      }
-    }
-    e = pend;
-  }
+          for (int c = 0; c < C; ++c) {
+            const int col = group_bcast<LPR>(my_col, s + c);
+            pc[c] = group_bcast<LPR>(pe, s + c);  // 0 beyond cnt
+            if (s + c < cnt) L::load(vv[c], ra.at(Fb, col), gl, f);
+            else zero(vv[c]);
+          }
+#pragma unroll
+          for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int i = 0; i < NR; ++i) acc[i] = fmaf(pc[c], vv[c][i], acc[i]);
+        }
+      },
+      [&](int r, bool first, bool last) {
+        const float l_run = group_sum_local<LPR>(l_lane, lane);
+        if (first && last) {
+          finish(r, m_run, l_run, acc);
+        } else {
+          Slot<NR, LPR> sl(s_slot, vw, first ? 1 : 0);
+#pragma unroll
+          for (int i = 0; i < NR; ++i) sl.v(i, gl) = acc[i];
+          if (gl == 0) { sl.a() = m_run; sl.b() = l_run; sl.set_seg(r); }
+        }
+      });
   __syncthreads();
   {
     Slot<NR, LPR> mine(s_slot, vw, 1);

@@ -22,7 +22,10 @@
 
 namespace dfgnn {
 
-constexpr int kNW = 8;        // warps per CTA
+#ifndef DFGNN_KNW
+#define DFGNN_KNW 8
+#endif
+constexpr int kNW = DFGNN_KNW;  // warps per CTA
 constexpr int kMaxRB = 128;   // max segments per CTA
 
 struct RowBlock {
@@ -65,6 +68,37 @@ struct Slot {
   __device__ __forceinline__ float& b() { return base[NV * LPR + 1]; }
   __device__ __forceinline__ float& v(int i, int gl) { return base[i * LPR + gl]; }
 };
+
+// The walk shared by every conv kernel.  One loop iteration = one chunk of <= CH entries
+// of every group's CURRENT piece; a group that reaches the end of its piece closes it
+// and opens the next one inside the same iteration, so the G groups of a warp stay busy
+// whatever the segment lengths are (a warp's trip count is max over its groups of
+// sum_pieces ceil(len / CH), and the slices are equal).
+//   begin(r)                 group-local (divergent): load the segment's own operands
+//   chunk(base, cnt)         warp-converged: may shuffle; cnt == 0 for an idle group
+//   end(r, first, last)      group-local: `first`/`last` = the piece contains the
+//                            segment's first/last entry (both: the piece is the segment)
+template <int CH, class Begin, class Chunk, class End>
+__device__ __forceinline__ void walk_pieces(const RowBlock& b, const int* s_ptr, Begin begin,
+                                            Chunk chunk, End end) {
+  int e = b.e, pend = b.e, pstart = b.e, rs = 0, re = 0;
+  int r = e < b.e_end ? find_row(s_ptr, b.nseg, e) : 0;
+  while (__any_sync(kFull, e < b.e_end)) {
+    const bool act = e < b.e_end;
+    if (act && e == pend) {
+      while (s_ptr[r + 1] <= e) ++r;
+      rs = s_ptr[r];
+      re = s_ptr[r + 1];
+      pend = min(re, b.e_end);
+      pstart = e;
+      begin(r);
+    }
+    const int cnt = act ? min(pend - e, CH) : 0;
+    chunk(e, cnt);
+    e += cnt;
+    if (act && e == pend) end(r, pstart == rs, pend == re);
+  }
+}
 
 template <int NV, int LPR>
 __device__ __forceinline__ void slots_clear(float* smem, int vw, int gl) {
