@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <type_traits>
@@ -13,6 +14,7 @@
 #include "../../include/dfgnn_b200.h"
 #include "common.cuh"
 #include "rowblock.cuh"
+#include "staged.cuh"
 
 #ifndef DFGNN_LPR64
 #define DFGNN_LPR64 8
@@ -70,6 +72,38 @@ inline int pick_rb(int m, int nnz, int G) {
   return rb;
 }
 
+// ---- staged-tile kernels (staged.cuh): short rows ------------------------------------
+// Used when even the smallest tile (8 rows) averages at most half the staging capacity;
+// rows per CTA then aim at ~kStageCap/2 entries, keeping >= 2 CTAs per SM in the grid.
+// DFGNN_B200_SCHEDULE=rowblock|staged overrides the choice (developer / test knob).
+inline int schedule_override() {
+  static const int v = [] {
+    const char* e = getenv("DFGNN_B200_SCHEDULE");
+    if (!e) return 0;
+    return e[0] == 'r' ? 1 : (e[0] == 's' ? 2 : 0);
+  }();
+  return v;
+}
+inline bool want_staged(int m, int nnz) {
+  const int o = schedule_override();
+  if (o) return o == 2;
+  return m > 0 && (double)nnz / (double)m * 8.0 <= kStageCap / 2;
+}
+inline int pick_rb_staged(int m, int nnz) {
+  const double avg = m > 0 ? (double)nnz / (double)m : 0.0;
+  int rb = kMaxRB;
+  while (rb > 8 && (avg * rb > kStageCap / 2 || (m + rb - 1) / rb < 2 * 148)) rb >>= 1;
+  return rb;
+}
+// entries in flight per lane group in the staged kernels
+template <class L>
+struct StageChunk {
+  static constexpr int kSpmm = L::NR <= 16 ? 4 : 2;
+  static constexpr int kSpmm2 = L::NR <= 8 ? 4 : 2;  // two operand matrices
+  static constexpr int kRaw = L::NR <= 8 ? 4 : 2;    // sddmm also holds two row operands
+  static constexpr int kSddmm = kRaw < L::LPR ? kRaw : L::LPR;
+};
+
 inline int check_common(const char* fn, int m, int nnz, int h, int f) {
   if (m < 0 || nnz < 0 || h < 1 || f < 1) {
     set_error("%s: invalid sizes m=%d nnz=%d h=%d f=%d", fn, m, nnz, h, f);
@@ -103,6 +137,12 @@ constexpr size_t slot_bytes() {
 template <class K>
 inline void ensure_smem(K kernel, size_t bytes) {
   if (bytes > 48 * 1024)
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+// same for kernels that also hold `static_bytes` of static shared memory (staged kernels)
+template <class K>
+inline void ensure_smem(K kernel, size_t bytes, size_t static_bytes) {
+  if (bytes + static_bytes > 48 * 1024)
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 

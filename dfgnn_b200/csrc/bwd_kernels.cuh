@@ -35,6 +35,7 @@ struct GtBwdParams {
   float* dK;
   float* dV;
   float* grad_edge;    // [h, nnz]
+  int cap = 0;         // > 0: process only tiles with more than `cap` entries
 };
 
 // Sum-merge of split segments: NV floats per lane + one scalar (slot.a).  Group-local.
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(kNW * 32, 16 / kNW) gt_bwd_row_kernel(const Gt
 
   slots_clear<2 * NR, LPR>(s_slot, vw, gl);
   const RowBlock b = rowblock_init<G>(s_rp, p.row_ptr, p.m, p.rb, vw);
+  if (p.cap > 0 && b.E1 - b.E0 <= p.cap) return;
 
   // Per piece: acc2 = [A1c | A2] with A1c = sum_e p_e (dA_e - c) K_e, A2 = sum_e p_e K_e,
   // c = dA of the piece's first edge.  dQ = A1c + (c - s) * A2, which equals
@@ -220,6 +222,7 @@ __global__ void __launch_bounds__(kNW * 32, 16 / kNW) gt_bwd_col_kernel(const Gt
 
   slots_clear<2 * NR, LPR>(s_slot, vw, gl);
   const RowBlock b = rowblock_init<G>(s_cp, p.col_ptr, p.n, p.rb_col, vw);
+  if (p.cap > 0 && b.E1 - b.E0 <= p.cap) return;
 
   // acc2 = [dV | dK]
   auto finish = [&](int c, float, float (&acc2)[2 * NR]) {
@@ -314,6 +317,7 @@ struct GatBwdParams {
   float* grad_ar;
   float* grad_ac;
   float* grad_edge;     // [nnz, h] scratch: t_e, then de_e
+  int cap = 0;          // > 0: process only tiles with more than `cap` entries
 };
 
 template <class L, int C>
@@ -335,6 +339,7 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : 16) / kNW) gat_bw
 
   slots_clear<1, LPR>(s_slot, vw, gl);
   const RowBlock b = rowblock_init<G>(s_rp, p.row_ptr, p.m, p.rb, vw);
+  if (p.cap > 0 && b.E1 - b.E0 <= p.cap) return;
 
   for (int r = vw; r < b.nseg; r += VW)
     if (s_rp[r + 1] == s_rp[r] && gl == 0) s_w[r] = 0.f;
@@ -441,6 +446,7 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR * C <= 32 ? 24 : 16) / kNW) g
 
   slots_clear<NR, LPR>(s_slot, vw, gl);
   const RowBlock b = rowblock_init<G>(s_cp, p.col_ptr, p.n, p.rb_col, vw);
+  if (p.cap > 0 && b.E1 - b.E0 <= p.cap) return;
 
   auto finish = [&](int c, float dac, float (&acc)[NR]) {
     const size_t node = (size_t)(b.seg_lb + c) * h + hid;

@@ -24,6 +24,7 @@ struct DotFwdParams {
   const float* rn;   // [m, h] inverse norms (AGNN) or null
   float* out;
   float* attn;       // [h, nnz] or null
+  int cap = 0;       // > 0: process only tiles with more than `cap` entries (behind a staged kernel)
 };
 
 // fold (m2, l2, acc2) into (m, l, acc): the online-softmax merge, base-2 exponent domain
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(kNW * 32, 16 / kNW) dot_fwd_kernel(const DotFw
 
   slots_clear<NR, LPR>(s_slot, vw, gl);
   const RowBlock b = rowblock_init<G>(s_rp, p.row_ptr, p.m, p.rb, vw);
+  if (p.cap > 0 && b.E1 - b.E0 <= p.cap) return;
 
   auto finish = [&](int r, float m, float l, float (&acc)[NR]) {
     const float inv = l > 0.f ? 1.f / l : 0.f;
@@ -206,6 +208,7 @@ struct GatFwdParams {
   float* emax;   // [m, h] or null
   float* esum;   // [m, h] or null
   float* emask;  // [nnz, h] or null
+  int cap = 0;   // > 0: process only tiles with more than `cap` entries (behind a staged kernel)
 };
 
 // Natural-log domain (edge_max / edge_sum are returned to the caller).
@@ -239,6 +242,7 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : 16) / kNW) gat_fw
 
   slots_clear<NR, LPR>(s_slot, vw, gl);
   const RowBlock b = rowblock_init<G>(s_rp, p.row_ptr, p.m, p.rb, vw);
+  if (p.cap > 0 && b.E1 - b.E0 <= p.cap) return;
 
   auto finish = [&](int r, float m, float l, float (&acc)[NR]) {
     const size_t node = (size_t)(b.seg_lb + r) * h + hid;

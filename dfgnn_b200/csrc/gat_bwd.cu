@@ -1,6 +1,7 @@
 // gat_bwd.cu -- GAT backward entry point of include/dfgnn_b200.h.
 #include "abi_common.h"
 #include "bwd_kernels.cuh"
+#include "staged_gat.cuh"
 
 using namespace dfgnn;
 
@@ -40,17 +41,32 @@ extern "C" int dfgnn_gat_backward(int m, int n, int nnz, int h, int f, float neg
   dispatch_layout(f, [&](auto tag) {
     using L = typename decltype(tag)::type;
     constexpr int C = ChunkOf<L>::C1;
-    p.rb = pick_rb(m, nnz, L::G);
-    p.rb_col = pick_rb(n, nnz, L::G);
+    const bool staged_r = want_staged(m, nnz), staged_c = want_staged(n, nnz);
+    p.rb = staged_r ? pick_rb_staged(m, nnz) : pick_rb(m, nnz, L::G);
+    p.rb_col = staged_c ? pick_rb_staged(n, nnz) : pick_rb(n, nnz, L::G);
     const dim3 grid((m + p.rb - 1) / p.rb, h);
     const dim3 grid_c((n + p.rb_col - 1) / p.rb_col, h);
     ensure_smem(gat_bwd_col_kernel<L, C>, slot_bytes<L::NR, L>());
     if (m > 0) {
+      if (staged_r) {
+        gat_bwd_row_staged_kernel<L, StageChunk<L>::kSddmm><<<grid, kNW * 32, 0, st>>>(p);
+        rc = check_launch(fn);
+        if (rc) return;
+        p.cap = kStageCap;
+      }
       gat_bwd_row_kernel<L, C><<<grid, kNW * 32, slot_bytes<1, L>(), st>>>(p);
       rc = check_launch(fn);
       if (rc) return;
     }
     if (n > 0) {
+      p.cap = 0;
+      if (staged_c) {
+        ensure_smem(gat_bwd_col_staged_kernel<L, StageChunk<L>::kSpmm>, slot_bytes<L::NR, L>(), 32 * 1024);
+        gat_bwd_col_staged_kernel<L, StageChunk<L>::kSpmm><<<grid_c, kNW * 32, slot_bytes<L::NR, L>(), st>>>(p);
+        rc = check_launch(fn);
+        if (rc) return;
+        p.cap = kStageCap;
+      }
       gat_bwd_col_kernel<L, C><<<grid_c, kNW * 32, slot_bytes<L::NR, L>(), st>>>(p);
       rc = check_launch(fn);
     }

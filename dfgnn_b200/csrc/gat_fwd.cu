@@ -1,6 +1,7 @@
 // gat_fwd.cu -- GAT forward / inference entry points of include/dfgnn_b200.h.
 #include "abi_common.h"
 #include "fwd_kernels.cuh"
+#include "staged_gat.cuh"
 
 namespace dfgnn {
 
@@ -27,10 +28,18 @@ int launch_gat_fwd(int m, int nnz, int h, int f, const float* ar, const float* a
   dispatch_layout(f, [&](auto tag) {
     using L = typename decltype(tag)::type;
     constexpr int C = ChunkOf<L>::C1;
-    p.rb = pick_rb(m, nnz, L::G);
+    const bool staged = want_staged(m, nnz);
+    p.rb = staged ? pick_rb_staged(m, nnz) : pick_rb(m, nnz, L::G);
     const dim3 grid((m + p.rb - 1) / p.rb, h);
     const size_t smem = slot_bytes<L::NR, L>();
     ensure_smem(gat_fwd_kernel<L, C>, smem);
+    if (staged) {
+      ensure_smem(gat_fwd_staged_kernel<L, StageChunk<L>::kSpmm>, smem, 24 * 1024);
+      gat_fwd_staged_kernel<L, StageChunk<L>::kSpmm><<<grid, kNW * 32, smem, st>>>(p);
+      rc = check_launch(fn);
+      if (rc) return;
+      p.cap = kStageCap;  // tiles the staged kernel skipped
+    }
     gat_fwd_kernel<L, C><<<grid, kNW * 32, smem, st>>>(p);
     rc = check_launch(fn);
   });
