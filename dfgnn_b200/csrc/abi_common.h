@@ -89,20 +89,39 @@ inline bool want_staged(int m, int nnz) {
   if (o) return o == 2;
   return m > 0 && (double)nnz / (double)m * 8.0 <= kStageCap / 2;
 }
+#ifndef DFGNN_STAGE_TARGET
+#define DFGNN_STAGE_TARGET (kStageCap / 2)
+#endif
 inline int pick_rb_staged(int m, int nnz) {
   const double avg = m > 0 ? (double)nnz / (double)m : 0.0;
   int rb = kMaxRB;
-  while (rb > 8 && (avg * rb > kStageCap / 2 || (m + rb - 1) / rb < 2 * 148)) rb >>= 1;
+  while (rb > 8 && (avg * rb > DFGNN_STAGE_TARGET || (m + rb - 1) / rb < 2 * 148)) rb >>= 1;
   return rb;
 }
 // entries in flight per lane group in the staged kernels
 template <class L>
 struct StageChunk {
-  static constexpr int kSpmm = L::NR <= 16 ? 4 : 2;
+#ifndef DFGNN_SPMM_C
+#define DFGNN_SPMM_C 4
+#endif
+  static constexpr int kSpmm = L::NR <= 8 ? DFGNN_SPMM_C : (L::NR <= 16 ? 4 : 2);
   static constexpr int kSpmm2 = L::NR <= 8 ? 4 : 2;  // two operand matrices
   static constexpr int kRaw = L::NR <= 8 ? 4 : 2;    // sddmm also holds two row operands
   static constexpr int kSddmm = kRaw < L::LPR ? kRaw : L::LPR;
 };
+
+// CTA -> tile remap (rowblock.cuh: tile_of).  `slots` = CTAs resident on the chip.
+struct TileGrid { int ntiles, slots, grid; };
+inline TileGrid tile_grid(int nseg, int rb, int slots) {
+  const int nt = (nseg + rb - 1) / rb;
+  if (slots <= 0 || nt <= slots) return {nt, 0, nt};
+  const int per = (nt + slots - 1) / slots;
+  return {nt, slots, slots * per};
+}
+inline int remap_slots_env() {
+  static const int v = [] { const char* e = getenv("DFGNN_B200_SLOTS"); return e ? atoi(e) : 0; }();
+  return v;
+}
 
 inline int check_common(const char* fn, int m, int nnz, int h, int f) {
   if (m < 0 || nnz < 0 || h < 1 || f < 1) {

@@ -34,7 +34,8 @@ struct GtBwdParams {
   float* dQ;
   float* dK;
   float* dV;
-  float* grad_edge;    // [h, nnz]
+  float* grad_edge;    // [h, nnz, 2] scratch: {dS_e, p_e}
+  int slots = 0, ntiles = 0, ntiles_col = 0;  // CTA -> tile remap (tile_of)
   int cap = 0;         // > 0: process only tiles with more than `cap` entries
 };
 
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(kNW * 32, 16 / kNW) gt_bwd_row_kernel(const Gt
   const int grp = lane / LPR, gl = lane % LPR, vw = w * G + grp;
   const int hid = blockIdx.y, h = p.h, f = p.f;
   const float* attn = p.attn + (size_t)hid * p.nnz;
-  float* gedge = p.grad_edge + (size_t)hid * p.nnz;
+  float2* gedge = reinterpret_cast<float2*>(p.grad_edge) + (size_t)hid * p.nnz;  // {dS_e, p_e}
   const RowAddr<L> ra(h, f, hid, gl);
   const char* Gb = ra.base(p.dO);
   const char* Kb = ra.base(p.K);
@@ -78,7 +79,9 @@ __global__ void __launch_bounds__(kNW * 32, 16 / kNW) gt_bwd_row_kernel(const Gt
   char* DQb = ra.base(p.dQ);
 
   slots_clear<2 * NR, LPR>(s_slot, vw, gl);
-  const RowBlock b = rowblock_init<G>(s_rp, p.row_ptr, p.m, p.rb, vw);
+  const int tile = tile_of(p.slots, p.ntiles);
+  if (tile >= (p.m + p.rb - 1) / p.rb) return;
+  const RowBlock b = rowblock_init<G>(s_rp, p.row_ptr, p.m, p.rb, vw, tile);
   if (p.cap > 0 && b.E1 - b.E0 <= p.cap) return;
 
   // Per piece: acc2 = [A1c | A2] with A1c = sum_e p_e (dA_e - c) K_e, A2 = sum_e p_e K_e,
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(kNW * 32, 16 / kNW) gt_bwd_row_kernel(const Gt
             }
           }
         }
-        if (gl < cnt) gedge[base + gl] = my_t;
+        if (gl < cnt) gedge[base + gl] = make_float2(my_t, my_p);  // {t_e, p_e}
       },
       [&](int r, bool first, bool last) {
         if (first && last) {
@@ -196,7 +199,8 @@ __global__ void __launch_bounds__(kNW * 32, 16 / kNW) gt_bwd_row_kernel(const Gt
   // t_e -> dS_e = t_e - s_i p_e   (fused_gtconv_backward.cu:171-176)
   for (int i = b.E0 + threadIdx.x; i < b.E1; i += kNW * 32) {
     const int rr = find_row(s_rp, b.nseg, i);
-    gedge[i] = fmaf(-s_s[rr], __ldg(attn + i), gedge[i]);
+    const float2 tp = gedge[i];
+    gedge[i].x = fmaf(-s_s[rr], tp.y, tp.x);
   }
 }
 
@@ -212,8 +216,7 @@ __global__ void __launch_bounds__(kNW * 32, 16 / kNW) gt_bwd_col_kernel(const Gt
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int grp = lane / LPR, gl = lane % LPR, vw = w * G + grp;
   const int hid = blockIdx.y, h = p.h, f = p.f;
-  const float* attn = p.attn + (size_t)hid * p.nnz;
-  const float* gedge = p.grad_edge + (size_t)hid * p.nnz;
+  const float2* gedge = reinterpret_cast<const float2*>(p.grad_edge) + (size_t)hid * p.nnz;
   const RowAddr<L> ra(h, f, hid, gl);
   const char* Gb = ra.base(p.dO);
   const char* Qb = ra.base(p.Q);
@@ -221,7 +224,9 @@ __global__ void __launch_bounds__(kNW * 32, 16 / kNW) gt_bwd_col_kernel(const Gt
   char* DKb = ra.base(p.dK);
 
   slots_clear<2 * NR, LPR>(s_slot, vw, gl);
-  const RowBlock b = rowblock_init<G>(s_cp, p.col_ptr, p.n, p.rb_col, vw);
+  const int tile = tile_of(p.slots, p.ntiles_col);
+  if (tile >= (p.n + p.rb_col - 1) / p.rb_col) return;
+  const RowBlock b = rowblock_init<G>(s_cp, p.col_ptr, p.n, p.rb_col, vw, tile);
   if (p.cap > 0 && b.E1 - b.E0 <= p.cap) return;
 
   // acc2 = [dV | dK]
@@ -251,9 +256,9 @@ __global__ void __launch_bounds__(kNW * 32, 16 / kNW) gt_bwd_col_kernel(const Gt
         float my_p = 0.f, my_ds = 0.f;
         if (gl < cnt) {
           my_rid = __ldg(p.row_ind + base + gl);
-          const int eid = __ldg(p.val_idx + base + gl);
-          my_p = __ldg(attn + eid);
-          my_ds = __ldg(gedge + eid);
+          const float2 dp = __ldg(gedge + __ldg(p.val_idx + base + gl));  // {dS_e, p_e} from the row side
+          my_p = dp.y;
+          my_ds = dp.x;
         }
 #pragma unroll
         for (int s = 0; s < CH; s += C) {
@@ -316,7 +321,8 @@ struct GatBwdParams {
   float* grad_feat;
   float* grad_ar;
   float* grad_ac;
-  float* grad_edge;     // [nnz, h] scratch: t_e, then de_e
+  float* grad_edge;     // [nnz, h, 2] scratch: {t_e then de_e, keep-scaled p_e}
+  int slots = 0, ntiles = 0, ntiles_col = 0;  // CTA -> tile remap (tile_of)
   int cap = 0;          // > 0: process only tiles with more than `cap` entries
 };
 
@@ -336,9 +342,12 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : 16) / kNW) gat_bw
   const char* Gb = ra.base(p.dO);
   const char* Fb = ra.base(p.feat);
   const float* acb = p.ac + hid;
+  float2* scratch = reinterpret_cast<float2*>(p.grad_edge);  // [nnz, h] x {de_e, keep-scaled p_e}
 
   slots_clear<1, LPR>(s_slot, vw, gl);
-  const RowBlock b = rowblock_init<G>(s_rp, p.row_ptr, p.m, p.rb, vw);
+  const int tile = tile_of(p.slots, p.ntiles);
+  if (tile >= (p.m + p.rb - 1) / p.rb) return;
+  const RowBlock b = rowblock_init<G>(s_rp, p.row_ptr, p.m, p.rb, vw, tile);
   if (p.cap > 0 && b.E1 - b.E0 <= p.cap) return;
 
   for (int r = vw; r < b.nseg; r += VW)
@@ -382,7 +391,7 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : 16) / kNW) gat_bw
             if (gl == s + c) my_t = ge * my_p;  // lane s+c owns this edge
           }
         }
-        if (gl < cnt) p.grad_edge[(size_t)(base + gl) * h + hid] = my_t;
+        if (gl < cnt) scratch[(size_t)(base + gl) * h + hid] = make_float2(my_t, my_p);  // {t_e, keep-scaled p_e}
         w_lane += my_t;
       },
       [&](int r, bool first, bool last) {
@@ -418,9 +427,9 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : 16) / kNW) gat_bw
         const float x = leaky(ar_i + __ldg(acb + (size_t)(unsigned)col * (unsigned)h), p.slope);
         const float pe = fast_exp(x - mx) * inv;
         const size_t eid = (size_t)i * h + hid;
-        float de = fmaf(-wr, pe, p.grad_edge[eid]);
+        float de = fmaf(-wr, pe, scratch[eid].x);
         if (x < 0.f) de *= p.slope;
-        p.grad_edge[eid] = de;
+        scratch[eid].x = de;
         rsum += de;
       }
     }
@@ -439,13 +448,15 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR * C <= 32 ? 24 : 16) / kNW) g
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int grp = lane / LPR, gl = lane % LPR, vw = w * G + grp;
   const int hid = blockIdx.y, h = p.h, f = p.f;
-  const float keep_scale = 1.f / (1.f - p.drop);
   const RowAddr<L> ra(h, f, hid, gl);
   const char* Gb = ra.base(p.dO);
   char* GFb = ra.base(p.grad_feat);
+  const float2* scratch = reinterpret_cast<const float2*>(p.grad_edge);
 
   slots_clear<NR, LPR>(s_slot, vw, gl);
-  const RowBlock b = rowblock_init<G>(s_cp, p.col_ptr, p.n, p.rb_col, vw);
+  const int tile = tile_of(p.slots, p.ntiles_col);
+  if (tile >= (p.n + p.rb_col - 1) / p.rb_col) return;
+  const RowBlock b = rowblock_init<G>(s_cp, p.col_ptr, p.n, p.rb_col, vw, tile);
   if (p.cap > 0 && b.E1 - b.E0 <= p.cap) return;
 
   auto finish = [&](int c, float dac, float (&acc)[NR]) {
@@ -461,12 +472,11 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR * C <= 32 ? 24 : 16) / kNW) g
       finish(c, 0.f, z);
     }
 
-  float ac_j = 0.f, acc[NR], dac_lane = 0.f;
+  float acc[NR], dac_lane = 0.f;
   zero(acc);
   walk_pieces<LPR>(
       b, s_cp,
-      [&](int c0) {
-        ac_j = __ldg(p.ac + (size_t)(b.seg_lb + c0) * h + hid);
+      [&](int) {
         zero(acc);
         dac_lane = 0.f;
       },
@@ -476,11 +486,9 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR * C <= 32 ? 24 : 16) / kNW) g
         if (gl < cnt) {
           my_rid = __ldg(p.row_ind + base + gl);
           const size_t eid = (size_t)__ldg(p.permute + base + gl) * h + hid;
-          const size_t rn = (size_t)my_rid * h + hid;
-          const float sc = leaky(__ldg(p.ar + rn) + ac_j, p.slope);
-          my_p = fast_exp(sc - __ldg(p.emax + rn)) / __ldg(p.esum + rn);
-          if (p.emask) my_p = (__ldg(p.emask + eid) > p.drop) ? my_p * keep_scale : 0.f;
-          dac_lane += __ldg(p.grad_edge + eid);
+          const float2 dp = __ldg(scratch + eid);  // {de_e, keep-scaled p_e} from the row side
+          my_p = dp.y;
+          dac_lane += dp.x;
         }
 #pragma unroll
         for (int s = 0; s < LPR; s += C) {

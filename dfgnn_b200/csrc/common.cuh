@@ -88,11 +88,18 @@ struct RowAddr {
   int hid, f, gl;
   __device__ __forceinline__ RowAddr(int h, int f_, int hid_, int gl_)
       : stride_b((uint32_t)h * (uint32_t)f_ * 4u), hid(hid_), f(f_), gl(gl_) {}
+  // The empty asm keeps base + lane offset together in one 64-bit register pair, so that a
+  // gathered row address is a single IMAD.WIDE (row * stride + base) instead of the
+  // compiler's (row * stride + lane offset) + uniform base split.
   __device__ __forceinline__ const char* base(const float* t) const {
-    return reinterpret_cast<const char*>(t + (size_t)hid * f) + L::lane_off(gl);
+    const char* b = reinterpret_cast<const char*>(t + (size_t)hid * f) + L::lane_off(gl);
+    asm volatile("" : "+l"(b));
+    return b;
   }
   __device__ __forceinline__ char* base(float* t) const {
-    return reinterpret_cast<char*>(t + (size_t)hid * f) + L::lane_off(gl);
+    char* b = reinterpret_cast<char*>(t + (size_t)hid * f) + L::lane_off(gl);
+    asm volatile("" : "+l"(b));
+    return b;
   }
   __device__ __forceinline__ const float* at(const char* b, int row) const {
     return reinterpret_cast<const float*>(b + (uint64_t)(uint32_t)row * stride_b);
@@ -184,6 +191,12 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 __device__ __forceinline__ float fast_exp(float x) { return fast_exp2(x * kLog2e); }
+// 1/x as one MUFU.RCP (1 ulp)
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // counter-based uniform in (0, 1]: two rounds of a 64-bit mix (splitmix64
 // finaliser) over (seed, edge index).  Replaces the cuRAND stream the reference

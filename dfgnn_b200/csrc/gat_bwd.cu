@@ -61,7 +61,7 @@ extern "C" int dfgnn_gat_backward(int m, int n, int nnz, int h, int f, float neg
     if (n > 0) {
       p.cap = 0;
       if (staged_c) {
-        ensure_smem(gat_bwd_col_staged_kernel<L, StageChunk<L>::kSpmm>, slot_bytes<L::NR, L>(), 32 * 1024);
+        ensure_smem(gat_bwd_col_staged_kernel<L, StageChunk<L>::kSpmm>, slot_bytes<L::NR, L>(), 42 * 1024);
         gat_bwd_col_staged_kernel<L, StageChunk<L>::kSpmm><<<grid_c, kNW * 32, slot_bytes<L::NR, L>(), st>>>(p);
         rc = check_launch(fn);
         if (rc) return;

@@ -28,6 +28,16 @@ namespace dfgnn {
 constexpr int kNW = DFGNN_KNW;  // warps per CTA
 constexpr int kMaxRB = 128;   // max segments per CTA
 
+// CTA -> tile mapping.  slots == 0: tile = blockIdx.x.  slots > 0 (the number of CTAs resident
+// on the chip): CTA b takes tile (b % slots) * per + b / slots, so the CTAs that follow one
+// another in a residency slot walk CONSECUTIVE tiles -- on block-diagonal (batched) graphs the
+// neighbour rows of consecutive tiles are the same few rows, which then stay in that SM's L1.
+__device__ __forceinline__ int tile_of(int slots, int ntiles) {
+  if (slots <= 0) return blockIdx.x;
+  const int per = (ntiles + slots - 1) / slots;
+  return (blockIdx.x % slots) * per + blockIdx.x / slots;
+}
+
 struct RowBlock {
   int seg_lb;   // first segment of this CTA
   int nseg;     // segments in this CTA
@@ -37,18 +47,21 @@ struct RowBlock {
 
 // Loads seg_ptr[seg_lb .. seg_lb+nseg] into s_ptr and computes the group's slice.
 // Contains a __syncthreads().
-template <int G>
+// ALIGN > 1 rounds the slice length up to a multiple of ALIGN (staged kernels: whole batches).
+template <int G, int ALIGN = 1>
 __device__ __forceinline__ RowBlock rowblock_init(int* s_ptr, const int* __restrict__ seg_ptr,
-                                                  int n_seg_total, int rb, int vw) {
+                                                  int n_seg_total, int rb, int vw,
+                                                  int tile = blockIdx.x) {
   RowBlock b;
-  b.seg_lb = blockIdx.x * rb;
+  b.seg_lb = tile * rb;
   b.nseg = min(rb, n_seg_total - b.seg_lb);
   for (int i = threadIdx.x; i <= b.nseg; i += blockDim.x) s_ptr[i] = __ldg(seg_ptr + b.seg_lb + i);
   __syncthreads();
   b.E0 = s_ptr[0];
   b.E1 = s_ptr[b.nseg];
   constexpr int VW = kNW * G;
-  const int per = (b.E1 - b.E0 + VW - 1) / VW;
+  int per = (b.E1 - b.E0 + VW - 1) / VW;
+  if (ALIGN > 1) per = (per + ALIGN - 1) / ALIGN * ALIGN;
   b.e = min(b.E1, b.E0 + vw * per);
   b.e_end = min(b.E1, b.e + per);
   return b;

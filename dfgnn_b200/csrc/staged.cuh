@@ -31,16 +31,35 @@ namespace dfgnn {
 #endif
 constexpr int kStageCap = DFGNN_STAGE_CAP;  // entries of a CTA tile staged in shared memory
 
-// out[seg] (+)= sum_e w[e] * X[idx[e], :] over the staged tile; NOPS = 2 walks two operand
-// matrices with two weight arrays at once; SCALAR also sums s_sc[e] per segment.
-// store(seg, scalar, acc[NOPS*NR]) is called for segments finished inside one slice;
-// split segments are left in the slots (merge with sum_merge_slots after a __syncthreads()).
-template <class L, int C, int NOPS, bool SCALAR, class Store>
-__device__ __forceinline__ void flat_spmm(const RowBlock& b, const int* s_ptr, const int* s_idx,
-                                          const float* s_w0, const float* s_w1, const float* s_sc,
+// Staged tile entries.  The arrays hold kStageCap + kStagePad entries: the C entries behind
+// the tile must be {idx = 0, weights = 0} (stage_pad) so that the last batch of the last
+// slice can be read without bounds checks.
+constexpr int kStagePad = 8;
+struct __align__(8) Ent1 { int idx; float w; };                    // one weight
+struct __align__(16) Ent2 { int idx; float w; float w1; float aux; };  // two weights (or weight + scalar)
+
+template <class E>
+__device__ __forceinline__ void stage_pad(E* s_e, int ne) {
+  if (threadIdx.x < kStagePad) {
+    E z{};
+    s_e[ne + threadIdx.x] = z;
+  }
+}
+
+enum SpmmMode { kOneOp = 0, kOneOpScalar = 1, kTwoOps = 2 };
+
+// out[seg] = sum_e w[e] * X[idx[e], :] over the staged tile (kOneOp); kOneOpScalar also sums
+// w1[e] per segment; kTwoOps walks a second operand matrix X1 with weights w1.
+// The group's slice [b.e, b.e_end) starts at a multiple of C behind b.E0 (rowblock_init<G, C>).
+// store(seg, scalar, acc[NV]) is called for segments finished inside one slice; split
+// segments are left in the slots (merge with sum_merge_slots after a __syncthreads()).
+template <class L, int C, int MODE, class E, class Store>
+__device__ __forceinline__ void flat_spmm(const RowBlock& b, const int* s_ptr, const E* s_e,
                                           const RowAddr<L>& ra, const char* X0, const char* X1,
                                           float* s_slot, int vw, int gl, int f, Store store) {
+  constexpr int NOPS = MODE == kTwoOps ? 2 : 1;
   constexpr int NR = L::NR, NV = NOPS * NR, LPR = L::LPR;
+  static_assert(C <= kStagePad, "padding");
   int e = b.e;
   const int e_end = b.e_end;
   if (e >= e_end) return;
@@ -50,34 +69,26 @@ __device__ __forceinline__ void flat_spmm(const RowBlock& b, const int* s_ptr, c
   bool head = e > s_ptr[r];
   float acc[NV], sc = 0.f;
   zero(acc);
-  const int last = e_end - 1 - b.E0;
-  for (; e < e_end; e += C) {
-    int idx[C];
-    float w0[C], w1[NOPS == 2 ? C : 1], scc[SCALAR ? C : 1];
+  const E* pe = s_e + (e - b.E0);
+  for (; e < e_end; e += C, pe += C) {
+    E en[C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const int k = min(e - b.E0 + c, last);
-      const bool ok = e + c < e_end;
-      idx[c] = s_idx[k];
-      w0[c] = ok ? s_w0[k] : 0.f;
-      if (NOPS == 2) w1[c] = ok ? s_w1[k] : 0.f;
-      if (SCALAR) scc[c] = ok ? s_sc[k] : 0.f;
-    }
+    for (int c = 0; c < C; ++c) en[c] = pe[c];
     float v0[C][NR], v1[NOPS == 2 ? C : 1][NR];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      L::load(v0[c], ra.at(X0, idx[c]), gl, f);
-      if (NOPS == 2) L::load(v1[c], ra.at(X1, idx[c]), gl, f);
+      L::load(v0[c], ra.at(X0, en[c].idx), gl, f);
+      if constexpr (MODE == kTwoOps) L::load(v1[c], ra.at(X1, en[c].idx), gl, f);
     }
 #pragma unroll
     for (int c = 0; c < C; ++c) {
 #pragma unroll
       for (int i = 0; i < NR; ++i) {
-        acc[i] = fmaf(w0[c], v0[c][i], acc[i]);
-        if (NOPS == 2) acc[NR + i] = fmaf(w1[c], v1[c][i], acc[NR + i]);
+        acc[i] = fmaf(en[c].w, v0[c][i], acc[i]);
+        if constexpr (MODE == kTwoOps) acc[NR + i] = fmaf(en[c].w1, v1[c][i], acc[NR + i]);
       }
-      if (SCALAR) sc += scc[c];
-      if (e + c + 1 == pend) {  // last entry of a piece (never true for the padded tail)
+      if constexpr (MODE == kOneOpScalar) sc += en[c].w1;
+      if (e + c + 1 == pend) {  // last entry of a piece (never true in the padded tail)
         const bool complete = pend == row_end;
         if (!head && complete) {
           store(r, sc, acc);
@@ -100,13 +111,13 @@ __device__ __forceinline__ void flat_spmm(const RowBlock& b, const int* s_ptr, c
   }
 }
 
-// s_out[e] = <Xrow[seg(e), :], Y[idx[e], :]> for every staged entry (mul_into: s_out[e] *= ...).
+// out(e, <Xrow[seg(e), :], Y[idx[e], :]>) for every staged entry e (tile-relative).
 // One lane group per entry, C entries in flight; the row operand of the NEXT segment is
 // prefetched into registers when a segment starts.  Warp-converged (shuffles inside).
-template <class L, int C>
-__device__ __forceinline__ void flat_sddmm(const RowBlock& b, const int* s_ptr, const int* s_idx,
+template <class L, int C, class E, class Out>
+__device__ __forceinline__ void flat_sddmm(const RowBlock& b, const int* s_ptr, const E* s_e,
                                            const RowAddr<L>& ra, const char* Xrow, const char* Y,
-                                           float* s_out, bool mul_into, int gl, int f) {
+                                           int gl, int f, Out out) {
   constexpr int NR = L::NR, LPR = L::LPR;
   static_assert(C <= LPR, "one result lane per entry in flight");
   int e = b.e;
@@ -125,11 +136,13 @@ __device__ __forceinline__ void flat_sddmm(const RowBlock& b, const int* s_ptr, 
       L::load(xn, ra.at(Xrow, b.seg_lb + rn), gl, f);
     }
   }
-  const int last = max(e_end - 1 - b.E0, 0);
   while (__any_sync(kFull, e < e_end)) {
+    // entries behind the slice are valid neighbours too (next slice or stage_pad); a group
+    // that has run out of entries parks on the padding
+    const E* pe = s_e + ((e < e_end ? e : b.E1) - b.E0);
     int idx[C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) idx[c] = s_idx[min(e - b.E0 + c, last)];
+    for (int c = 0; c < C; ++c) idx[c] = pe[c].idx;
     float y[C][NR];
 #pragma unroll
     for (int c = 0; c < C; ++c) L::load(y[c], ra.at(Y, idx[c]), gl, f);
@@ -150,10 +163,7 @@ __device__ __forceinline__ void flat_sddmm(const RowBlock& b, const int* s_ptr, 
       const float d = group_sum<LPR>(dot<NR>(x, y[c]));
       if (gl == c) mine = d;
     }
-    if (gl < C && e + gl < e_end) {
-      const int k = e - b.E0 + gl;
-      s_out[k] = mul_into ? s_out[k] * mine : mine;
-    }
+    if (gl < C && e + gl < e_end) out(e - b.E0 + gl, mine);
     e += C;
   }
 }

@@ -10,15 +10,46 @@
 
 namespace dfgnn {
 
-// forward: A thread per edge -> leakyrelu score; B group per row -> max, sum, exp weights;
-// C flat SpMM over feat, scaled by 1/sum at the row flush.
+#ifndef DFGNN_STAGE_WARPS
+#define DFGNN_STAGE_WARPS 24  // resident warps per SM the short-row staged kernels are compiled for
+#endif
+constexpr int kEPT = kStageCap / (kNW * 32);  // staged entries per thread
+static_assert(kMaxRB <= kNW * 32, "one thread per row in the prologues");
+
+constexpr int kShortRow = 32;  // rows up to this length are reduced by ONE thread (smem only)
+
+// Per-row passes over the staged tile.  short_row(r, rs, re) runs in the thread that owns row
+// r (rows of <= kShortRow entries); long_row(r, rs, re, valid) runs once per long row with the
+// lane groups of a warp in lockstep (valid == false: idle group, must still take part in the
+// group shuffles).  s_long / s_nlong: the tile's long rows (filled on first use).
+template <int LPR, int G, class Short, class Long>
+__device__ __forceinline__ void per_row(const RowBlock& b, const int* s_rp, int* s_long,
+                                        int* s_nlong, bool build_list, Short short_row,
+                                        Long long_row) {
+  const int w = threadIdx.x >> 5, grp = (threadIdx.x & 31) / LPR;
+  if ((int)threadIdx.x < b.nseg) {
+    const int rs = s_rp[threadIdx.x] - b.E0, re = s_rp[threadIdx.x + 1] - b.E0;
+    if (re - rs <= kShortRow) short_row((int)threadIdx.x, rs, re);
+    else if (build_list) s_long[atomicAdd(s_nlong, 1)] = threadIdx.x;
+  }
+  __syncthreads();
+  const int nlong = *s_nlong;
+  for (int k0 = w * G; k0 < nlong; k0 += kNW * G) {
+    const bool valid = k0 + grp < nlong;
+    const int rr = valid ? s_long[k0 + grp] : 0;
+    long_row(rr, valid ? s_rp[rr] - b.E0 : 0, valid ? s_rp[rr + 1] - b.E0 : 0, valid);
+  }
+}
+
+// forward: (A) every thread stages {neighbour, attn_col[neighbour]} of its entries; (B) per
+// row: leakyrelu scores -> max -> exp weights, sum; (C) flat SpMM over feat, scaled by 1/sum
+// at the row flush.
 template <class L, int C>
-__global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : 16) / kNW) gat_fwd_staged_kernel(const GatFwdParams p) {
+__global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16) / kNW) gat_fwd_staged_kernel(const GatFwdParams p) {
   constexpr int NR = L::NR, LPR = L::LPR, G = L::G, VW = kNW * G;
-  __shared__ int s_rp[kMaxRB + 1];
-  __shared__ float s_ar[kMaxRB], s_inv[kMaxRB];
-  __shared__ int s_idx[kStageCap];
-  __shared__ float s_w[kStageCap];
+  __shared__ int s_rp[kMaxRB + 1], s_long[kMaxRB], s_nlong;
+  __shared__ float s_inv[kMaxRB], s_ar[kMaxRB];
+  __shared__ Ent1 s_e[kStageCap + kStagePad];
   extern __shared__ float s_slot[];
 
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -32,62 +63,89 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : 16) / kNW) gat_fw
   const float* acb = p.ac + hid;
 
   slots_clear<NR, LPR>(s_slot, vw, gl);
-  {
-    const int lb = blockIdx.x * p.rb, ns = min(p.rb, p.m - lb);
-    for (int i = threadIdx.x; i < ns; i += kNW * 32) s_ar[i] = __ldg(p.ar + (size_t)(lb + i) * h + hid);
-  }
-  const RowBlock b = rowblock_init<G>(s_rp, p.row_ptr, p.m, p.rb, vw);
+  if (threadIdx.x == 0) s_nlong = 0;
+  const RowBlock b = rowblock_init<G, C>(s_rp, p.row_ptr, p.m, p.rb, vw);
   const int ne = b.E1 - b.E0;
   if (ne > kStageCap) return;
-
-  // A: scores
-  for (int i = threadIdx.x; i < ne; i += kNW * 32) {
-    const int col = __ldg(p.col_ind + b.E0 + i);
-    const int r = find_row(s_rp, b.nseg, b.E0 + i);
-    s_idx[i] = col;
-    s_w[i] = leaky(s_ar[r] + __ldg(acb + (size_t)(unsigned)col * (unsigned)h), p.slope);
+  stage_pad(s_e, ne);
+  // A: all index loads are issued before the dependent gathers (one DRAM + one L2 latency per CTA)
+  {
+    const int* colp = p.col_ind + b.E0;
+    int cols[kEPT];
+    float acv[kEPT];
+#pragma unroll
+    for (int k = 0; k < kEPT; ++k) {
+      const int i = threadIdx.x + k * (kNW * 32);
+      cols[k] = i < ne ? __ldg(colp + i) : 0;
+    }
+    if (threadIdx.x < b.nseg) s_ar[threadIdx.x] = __ldg(p.ar + (size_t)(b.seg_lb + threadIdx.x) * h + hid);
+#pragma unroll
+    for (int k = 0; k < kEPT; ++k) {
+      const int i = threadIdx.x + k * (kNW * 32);
+      acv[k] = i < ne ? __ldg(acb + (size_t)(unsigned)cols[k] * (unsigned)h) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < kEPT; ++k) {
+      const int i = threadIdx.x + k * (kNW * 32);
+      if (i < ne) { Ent1 en; en.idx = cols[k]; en.w = acv[k]; s_e[i] = en; }
+    }
   }
   __syncthreads();
 
-  // B: per-row softmax statistics; s_w becomes exp(x - max) (times the dropout keep factor)
-  for (int r0 = w * G; r0 < b.nseg; r0 += VW) {
-    const int rr = r0 + grp;
-    const bool valid = rr < b.nseg;
-    const int rs = valid ? s_rp[rr] - b.E0 : 0, re = valid ? s_rp[rr + 1] - b.E0 : 0;
-    float mx = kNeg;
-    for (int i = rs + gl; __any_sync(kFull, i < re); i += LPR)
-      if (i < re) mx = fmaxf(mx, s_w[i]);
-    mx = group_max<LPR>(mx);
-    float l = 0.f;
-    for (int i = rs + gl; __any_sync(kFull, i < re); i += LPR)
-      if (i < re) {
-        float pe = fast_exp(s_w[i] - mx);
-        l += pe;
-        if (use_mask) {
-          const size_t eid = (size_t)(b.E0 + i) * h + hid;
-          const float u = p.drop > 0.f ? uniform01(p.seed, eid) : 1.f;
-          p.emask[eid] = u;
-          pe = (u > p.drop) ? pe * keep_scale : 0.f;
-        }
-        s_w[i] = pe;
-      }
-    l = group_sum<LPR>(l);
-    if (valid) {
-      const size_t node = (size_t)(b.seg_lb + rr) * h + hid;
-      if (gl == 0) {
-        s_inv[rr] = l > 0.f ? 1.f / l : 0.f;
-        if (p.emax) {  // saved for backward (fused_gatconv_kernel.cu:66-68, 89-91)
-          p.emax[node] = l > 0.f ? mx : -1e38f;
-          p.esum[node] = l;
-        }
-      }
-      if (re == rs) {  // rows without edges produce zeros
-        float z[NR];
-        zero(z);
-        L::store(ra.at(Ob, b.seg_lb + rr), z, gl, f);
-      }
+  // B: softmax statistics; s_e[i].w becomes exp(x - max) (times the dropout keep factor)
+  auto weight = [&](int i, float x, float mx, float& l) {
+    float pe = fast_exp(x - mx);
+    l += pe;
+    if (use_mask) {  // dropout on the attention weights, not on the normaliser
+      const size_t eid = (size_t)(b.E0 + i) * h + hid;
+      const float u = p.drop > 0.f ? uniform01(p.seed, eid) : 1.f;
+      p.emask[eid] = u;
+      pe = (u > p.drop) ? pe * keep_scale : 0.f;
     }
-  }
+    s_e[i].w = pe;
+  };
+  auto finish_row = [&](int r, float mx, float l) {
+    s_inv[r] = l > 0.f ? fast_rcp(l) : 0.f;
+    if (p.emax) {  // saved for backward (fused_gatconv_kernel.cu:66-68, 89-91)
+      const size_t node = (size_t)(b.seg_lb + r) * h + hid;
+      p.emax[node] = l > 0.f ? mx : -1e38f;
+      p.esum[node] = l;
+    }
+  };
+  per_row<LPR, G>(
+      b, s_rp, s_long, &s_nlong, true,
+      [&](int r, int rs, int re) {
+        const float ar_i = s_ar[r];
+        float mx = kNeg, l = 0.f;
+        for (int i = rs; i < re; ++i) {
+          const float x = leaky(ar_i + s_e[i].w, p.slope);
+          s_e[i].w = x;
+          mx = fmaxf(mx, x);
+        }
+        for (int i = rs; i < re; ++i) weight(i, s_e[i].w, mx, l);
+        finish_row(r, mx, l);
+      },
+      [&](int r, int rs, int re, bool valid) {
+        const float ar_i = s_ar[r];
+        float mx = kNeg, l = 0.f;
+        for (int i = rs + gl; __any_sync(kFull, i < re); i += LPR)
+          if (i < re) {
+            const float x = leaky(ar_i + s_e[i].w, p.slope);
+            s_e[i].w = x;
+            mx = fmaxf(mx, x);
+          }
+        mx = group_max<LPR>(mx);
+        for (int i = rs + gl; __any_sync(kFull, i < re); i += LPR)
+          if (i < re) weight(i, s_e[i].w, mx, l);
+        l = group_sum<LPR>(l);
+        if (valid && gl == 0) finish_row(r, mx, l);
+      });
+  for (int r = vw; r < b.nseg; r += VW)
+    if (s_rp[r + 1] == s_rp[r]) {  // rows without edges produce zeros
+      float z[NR];
+      zero(z);
+      L::store(ra.at(Ob, b.seg_lb + r), z, gl, f);
+    }
   __syncthreads();
 
   // C: aggregation
@@ -97,21 +155,22 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : 16) / kNW) gat_fw
     for (int i = 0; i < NR; ++i) acc[i] *= inv;
     L::store(ra.at(Ob, b.seg_lb + r), acc, gl, f);
   };
-  flat_spmm<L, C, 1, false>(b, s_rp, s_idx, s_w, nullptr, nullptr, ra, Fb, nullptr, s_slot, vw, gl,
-                            f, store);
+  flat_spmm<L, C, kOneOp>(b, s_rp, s_e, ra, Fb, nullptr, s_slot, vw, gl, f, store);
   __syncthreads();
   sum_merge_slots<NR, LPR, G>(s_slot, vw, gl, store);
 }
 
-// backward, row side: A thread per edge -> p, slope factor, keep factor; flat SDDMM
-// g = <dO_i, feat_j>; B group per row -> w, de, grad_attn_row.
+// backward, row side: (A) stage {neighbour, attn_col[neighbour], keep factor}; (B) per row ->
+// p_e and lrelu'; (C) flat SDDMM g = <dO_i, feat_j>; (D) per row -> w, de, grad_attn_row, and
+// the packed scratch {de_e, keep-scaled p_e} the column side reads.
+// Entry fields: w = p_e, w1 = lrelu'(x_e), aux = keep_e / (1 - drop); s_g = g_e.
 template <class L, int C>
-__global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : 16) / kNW) gat_bwd_row_staged_kernel(const GatBwdParams p) {
-  constexpr int LPR = L::LPR, G = L::G, VW = kNW * G;
-  __shared__ int s_rp[kMaxRB + 1];
+__global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16) / kNW) gat_bwd_row_staged_kernel(const GatBwdParams p) {
+  constexpr int LPR = L::LPR, G = L::G;
+  __shared__ int s_rp[kMaxRB + 1], s_long[kMaxRB], s_nlong;
   __shared__ float s_ar[kMaxRB], s_mx[kMaxRB], s_inv[kMaxRB];
-  __shared__ int s_idx[kStageCap];
-  __shared__ float s_p[kStageCap], s_sl[kStageCap], s_g[kStageCap];
+  __shared__ Ent2 s_e[kStageCap + kStagePad];
+  __shared__ float s_g[kStageCap];
 
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int grp = lane / LPR, gl = lane % LPR, vw = w * G + grp;
@@ -121,113 +180,148 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : 16) / kNW) gat_bw
   const char* Gb = ra.base(p.dO);
   const char* Fb = ra.base(p.feat);
   const float* acb = p.ac + hid;
+  float2* scratch = reinterpret_cast<float2*>(p.grad_edge);
 
-  {
-    const int lb = blockIdx.x * p.rb, ns = min(p.rb, p.m - lb);
-    for (int i = threadIdx.x; i < ns; i += kNW * 32) {
-      const size_t node = (size_t)(lb + i) * h + hid;
-      s_ar[i] = __ldg(p.ar + node);
-      s_mx[i] = __ldg(p.emax + node);
-      s_inv[i] = 1.f / __ldg(p.esum + node);  // unused for rows without edges
-    }
-  }
-  const RowBlock b = rowblock_init<G>(s_rp, p.row_ptr, p.m, p.rb, vw);
+  if (threadIdx.x == 0) s_nlong = 0;
+  const RowBlock b = rowblock_init<G, C>(s_rp, p.row_ptr, p.m, p.rb, vw);
   const int ne = b.E1 - b.E0;
   if (ne > kStageCap) return;
-
-  for (int i = threadIdx.x; i < ne; i += kNW * 32) {
-    const int col = __ldg(p.col_ind + b.E0 + i);
-    const int r = find_row(s_rp, b.nseg, b.E0 + i);
-    const float x = leaky(s_ar[r] + __ldg(acb + (size_t)(unsigned)col * (unsigned)h), p.slope);
-    s_idx[i] = col;
-    s_p[i] = fast_exp(x - s_mx[r]) * s_inv[r];
-    s_sl[i] = x < 0.f ? p.slope : 1.f;
-    float km = 1.f;  // keep_e / (1 - drop)
-    if (p.emask) km = (__ldg(p.emask + (size_t)(b.E0 + i) * h + hid) > p.drop) ? keep_scale : 0.f;
-    s_g[i] = km;
+  stage_pad(s_e, ne);
+  {
+    const int* colp = p.col_ind + b.E0;
+    int cols[kEPT];
+    float acv[kEPT], kmv[kEPT];
+#pragma unroll
+    for (int k = 0; k < kEPT; ++k) {
+      const int i = threadIdx.x + k * (kNW * 32);
+      cols[k] = i < ne ? __ldg(colp + i) : 0;
+      kmv[k] = 1.f;  // keep_e / (1 - drop)
+      if (p.emask && i < ne)
+        kmv[k] = (__ldg(p.emask + (size_t)(b.E0 + i) * h + hid) > p.drop) ? keep_scale : 0.f;
+    }
+    if (threadIdx.x < b.nseg) {
+      const size_t node = (size_t)(b.seg_lb + threadIdx.x) * h + hid;
+      s_ar[threadIdx.x] = __ldg(p.ar + node);
+      s_mx[threadIdx.x] = __ldg(p.emax + node);
+      s_inv[threadIdx.x] = fast_rcp(__ldg(p.esum + node));  // unused for rows without edges
+    }
+#pragma unroll
+    for (int k = 0; k < kEPT; ++k) {
+      const int i = threadIdx.x + k * (kNW * 32);
+      acv[k] = i < ne ? __ldg(acb + (size_t)(unsigned)cols[k] * (unsigned)h) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < kEPT; ++k) {
+      const int i = threadIdx.x + k * (kNW * 32);
+      if (i < ne) { Ent2 en; en.idx = cols[k]; en.w = acv[k]; en.w1 = 0.f; en.aux = kmv[k]; s_e[i] = en; }
+    }
   }
   __syncthreads();
-
-  if (ne > 0) flat_sddmm<L, C>(b, s_rp, s_idx, ra, Gb, Fb, s_g, true, gl, f);
+  auto prob = [&](int i, float ar_i, float mx, float inv) {
+    const float x = leaky(ar_i + s_e[i].w, p.slope);
+    s_e[i].w = fast_exp(x - mx) * inv;
+    s_e[i].w1 = x < 0.f ? p.slope : 1.f;
+  };
+  per_row<LPR, G>(
+      b, s_rp, s_long, &s_nlong, true,
+      [&](int r, int rs, int re) {
+        const float ar_i = s_ar[r], mx = s_mx[r], inv = s_inv[r];
+        for (int i = rs; i < re; ++i) prob(i, ar_i, mx, inv);
+      },
+      [&](int r, int rs, int re, bool) {
+        const float ar_i = s_ar[r], mx = s_mx[r], inv = s_inv[r];
+        for (int i = rs + gl; i < re; i += LPR) prob(i, ar_i, mx, inv);
+      });
   __syncthreads();
 
-  // de_e = (p_e g_e - w_i p_e) * lrelu'(x_e), w_i = sum_e p_e g_e, with g_e already keep-scaled
+  if (ne > 0)
+    flat_sddmm<L, C>(b, s_rp, s_e, ra, Gb, Fb, gl, f, [&](int k, float d) { s_g[k] = d; });
+  __syncthreads();
+
+  // de_e = (t_e - w_i p_e) * lrelu'(x_e), t_e = keep-scaled p_e g_e, w_i = sum_e t_e
   // (fused_gatconv_kernel.cu:830-864)
-  for (int r0 = w * G; r0 < b.nseg; r0 += VW) {
-    const int rr = r0 + grp;
-    const bool valid = rr < b.nseg;
-    const int rs = valid ? s_rp[rr] - b.E0 : 0, re = valid ? s_rp[rr + 1] - b.E0 : 0;
-    float wsum = 0.f;
-    for (int i = rs + gl; __any_sync(kFull, i < re); i += LPR)
-      if (i < re) wsum = fmaf(s_p[i], s_g[i], wsum);
-    wsum = group_sum<LPR>(wsum);
-    float rsum = 0.f;
-    for (int i = rs + gl; __any_sync(kFull, i < re); i += LPR)
-      if (i < re) {
-        const float pe = s_p[i];
-        const float de = (pe * s_g[i] - wsum * pe) * s_sl[i];
-        p.grad_edge[(size_t)(b.E0 + i) * h + hid] = de;
-        rsum += de;
-      }
-    rsum = group_sum<LPR>(rsum);
-    if (valid && gl == 0) p.grad_ar[(size_t)(b.seg_lb + rr) * h + hid] = rsum;
-  }
+  auto edge_grad = [&](int i, float wsum, float& rsum) {
+    const Ent2 en = s_e[i];
+    const float pk = en.w * en.aux;
+    const float de = (pk * s_g[i] - wsum * en.w) * en.w1;
+    scratch[(size_t)(b.E0 + i) * h + hid] = make_float2(de, pk);
+    rsum += de;
+  };
+  per_row<LPR, G>(
+      b, s_rp, s_long, &s_nlong, false,
+      [&](int r, int rs, int re) {
+        float wsum = 0.f, rsum = 0.f;
+        for (int i = rs; i < re; ++i) wsum = fmaf(s_e[i].w * s_e[i].aux, s_g[i], wsum);
+        for (int i = rs; i < re; ++i) edge_grad(i, wsum, rsum);
+        p.grad_ar[(size_t)(b.seg_lb + r) * h + hid] = rsum;
+      },
+      [&](int r, int rs, int re, bool valid) {
+        float wsum = 0.f, rsum = 0.f;
+        for (int i = rs + gl; __any_sync(kFull, i < re); i += LPR)
+          if (i < re) wsum = fmaf(s_e[i].w * s_e[i].aux, s_g[i], wsum);
+        wsum = group_sum<LPR>(wsum);
+        for (int i = rs + gl; __any_sync(kFull, i < re); i += LPR)
+          if (i < re) edge_grad(i, wsum, rsum);
+        rsum = group_sum<LPR>(rsum);
+        if (valid && gl == 0) p.grad_ar[(size_t)(b.seg_lb + r) * h + hid] = rsum;
+      });
 }
 
-// backward, column side (CSC): A thread per entry -> p (keep-scaled), de; C flat SpMM over dO
-// carrying sum(de) per column.
+// backward, column side (CSC): (A) every thread stages {row, keep-scaled p_e, de_e} of its
+// entries from the packed scratch of the row side; (C) flat SpMM over dO carrying sum(de).
 template <class L, int C>
-__global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : 16) / kNW) gat_bwd_col_staged_kernel(const GatBwdParams p) {
+__global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16) / kNW) gat_bwd_col_staged_kernel(const GatBwdParams p) {
   constexpr int NR = L::NR, LPR = L::LPR, G = L::G, VW = kNW * G;
   __shared__ int s_cp[kMaxRB + 1];
-  __shared__ float s_ac[kMaxRB];
-  __shared__ int s_idx[kStageCap];
-  __shared__ float s_w[kStageCap], s_de[kStageCap];
+  __shared__ Ent2 s_e[kStageCap + kStagePad];
   extern __shared__ float s_slot[];
 
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int grp = lane / LPR, gl = lane % LPR, vw = w * G + grp;
   const int hid = blockIdx.y, h = p.h, f = p.f;
-  const float keep_scale = 1.f / (1.f - p.drop);
   const RowAddr<L> ra(h, f, hid, gl);
   const char* Gb = ra.base(p.dO);
   char* GFb = ra.base(p.grad_feat);
+  const float2* scratch = reinterpret_cast<const float2*>(p.grad_edge);
 
   slots_clear<NR, LPR>(s_slot, vw, gl);
-  {
-    const int lb = blockIdx.x * p.rb_col, ns = min(p.rb_col, p.n - lb);
-    for (int i = threadIdx.x; i < ns; i += kNW * 32) s_ac[i] = __ldg(p.ac + (size_t)(lb + i) * h + hid);
-  }
-  const RowBlock b = rowblock_init<G>(s_cp, p.col_ptr, p.n, p.rb_col, vw);
+  const RowBlock b = rowblock_init<G, C>(s_cp, p.col_ptr, p.n, p.rb_col, vw);
   const int ne = b.E1 - b.E0;
   if (ne > kStageCap) return;
-
-  for (int i = threadIdx.x; i < ne; i += kNW * 32) {
-    const int rid = __ldg(p.row_ind + b.E0 + i);
-    const size_t eid = (size_t)__ldg(p.permute + b.E0 + i) * h + hid;
-    const size_t rn = (size_t)rid * h + hid;
-    const int c = find_row(s_cp, b.nseg, b.E0 + i);
-    const float x = leaky(__ldg(p.ar + rn) + s_ac[c], p.slope);
-    float pe = fast_exp(x - __ldg(p.emax + rn)) / __ldg(p.esum + rn);
-    if (p.emask) pe = (__ldg(p.emask + eid) > p.drop) ? pe * keep_scale : 0.f;
-    s_idx[i] = rid;
-    s_w[i] = pe;
-    s_de[i] = __ldg(p.grad_edge + eid);
+  stage_pad(s_e, ne);
+  {
+    int rid[kEPT], eid[kEPT];
+#pragma unroll
+    for (int k = 0; k < kEPT; ++k) {
+      const int i = threadIdx.x + k * (kNW * 32);
+      rid[k] = i < ne ? __ldg(p.row_ind + b.E0 + i) : 0;
+      eid[k] = i < ne ? __ldg(p.permute + b.E0 + i) : 0;
+    }
+    float2 dp[kEPT];
+#pragma unroll
+    for (int k = 0; k < kEPT; ++k) {
+      const int i = threadIdx.x + k * (kNW * 32);
+      dp[k] = i < ne ? __ldg(scratch + (size_t)eid[k] * h + hid) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < kEPT; ++k) {
+      const int i = threadIdx.x + k * (kNW * 32);
+      if (i < ne) { Ent2 en; en.idx = rid[k]; en.w = dp[k].y; en.w1 = dp[k].x; en.aux = 0.f; s_e[i] = en; }
+    }
   }
-  __syncthreads();
-
   auto store = [&](int c, float dac, float (&acc)[NR]) {
     L::store(ra.at(GFb, b.seg_lb + c), acc, gl, f);
     if (gl == 0) p.grad_ac[(size_t)(b.seg_lb + c) * h + hid] = dac;
   };
   for (int c = vw; c < b.nseg; c += VW)
-    if (s_cp[c + 1] == s_cp[c]) {
+    if (s_cp[c + 1] == s_cp[c]) {  // columns without entries
       float z[NR];
       zero(z);
       store(c, 0.f, z);
     }
-  flat_spmm<L, C, 1, true>(b, s_cp, s_idx, s_w, nullptr, s_de, ra, Gb, nullptr, s_slot, vw, gl, f,
-                           store);
+  __syncthreads();
+
+  flat_spmm<L, C, kOneOpScalar>(b, s_cp, s_e, ra, Gb, nullptr, s_slot, vw, gl, f, store);
   __syncthreads();
   sum_merge_slots<NR, LPR, G>(s_slot, vw, gl, store);
 }

@@ -104,7 +104,7 @@ def gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem_con
         raise RuntimeError(f"{fn}: col_ptr describes {n} columns but K has {K.shape[0]} rows")
     with torch.cuda.device(Q.device):
         gq, gk, gv = torch.empty_like(Q), torch.empty_like(K), torch.empty_like(V)
-        ge = torch.empty((h, nnz), dtype=torch.float32, device=Q.device)
+        ge = torch.empty((h, nnz, 2), dtype=torch.float32, device=Q.device)  # scratch {dS, p}
         rc = _lib.lib().dfgnn_gt_backward(
             m, n, nnz, h, f, _ptr(row_ptr), _ptr(col_ind), _ptr(rows), _ptr(val), _ptr(col_ptr),
             _ptr(row_ind), _ptr(val_idx), int(smem_consume), _ptr(Q), _ptr(K), _ptr(V),
@@ -250,7 +250,7 @@ def gat_backward(negative_slope, attn_drop, row_ptr, col_ind, col_ptr, row_ind, 
         gf = torch.empty_like(in_feat)
         gr = torch.empty((m, h), dtype=torch.float32, device=dev)
         gc = torch.empty((n, h), dtype=torch.float32, device=dev)
-        ge = torch.empty((nnz, h), dtype=torch.float32, device=dev)
+        ge = torch.empty((nnz, h, 2), dtype=torch.float32, device=dev)  # scratch {de, keep-scaled p}
         rc = _lib.lib().dfgnn_gat_backward(
             m, n, nnz, h, f, float(negative_slope), float(attn_drop), _ptr(row_ptr), _ptr(col_ind),
             _ptr(col_ptr), _ptr(row_ind), _ptr(permute), _ptr(edge_max), _ptr(edge_sum),

@@ -13,7 +13,7 @@
  *     indices are int32, features / edge scalars are float32, contiguous;
  *   - shapes: Q/K/V/feat/out [m, h, f]; attn_row/attn_col/edge_max/edge_sum [m, h];
  *     row_ptr/col_ptr [m+1]; col_ind/row_ind/rows/val/val_idx/permute [nnz];
- *     GT attn_edge / grad_edge [h, nnz]; GAT edge_mask [nnz, h];
+ *     GT attn_edge [h, nnz]; GAT edge_mask [nnz, h]; backward scratch: see below;
  *   - outputs are CALLER-allocated (the reference's launchers allocate them with
  *     torch::zeros / torch::empty, e.g. fused_gtconv_hyper.cu:688-691); no entry
  *     point requires an output to be pre-zeroed;
@@ -110,8 +110,9 @@ int dfgnn_gt_hyper_forward(int m, int nnz, int h, int f, const int32_t *row_ptr,
 
 /*
  * Backward.  Replaces gt_backward (fused_gtconv.cpp:125-172 ->
- * fused_gtconv_backward.cu:193-265).  grad_edge [h, nnz] is scratch
- * (torch::empty in the reference, l.250).  m = rows (row_ptr, Q, grad_out, grad_Q),
+ * fused_gtconv_backward.cu:193-265).  grad_edge is scratch of 2 * h * nnz floats
+ * ([h, nnz] pairs {dS_e, p_e} that the row-side kernel leaves for the column-side
+ * kernel; the reference's scratch is torch::empty({h, nnz}), l.250).  m = rows (row_ptr, Q, grad_out, grad_Q),
  * n = columns (col_ptr, K, V, grad_K, grad_V); the reference reads both sizes too
  * (fused_gtconv_backward.cu:238-239) and they are equal for a square adjacency.
  */
@@ -185,8 +186,9 @@ int dfgnn_gat_forward(int m, int nnz, int h, int f, const float *attn_row,
 
 /*
  * Backward.  Replaces gat_backward (fused_gatconv.cpp:291-353 ->
- * fused_gatconv_kernel.cu:1171-1244).  grad_edge [nnz, h] is scratch
- * (grad_edge_csr, l.1225).  grad_attn_col is produced by a deterministic
+ * fused_gatconv_kernel.cu:1171-1244).  grad_edge is scratch of 2 * nnz * h floats
+ * ([nnz, h] pairs {de_e, keep-scaled p_e}; the reference's grad_edge_csr, l.1225,
+ * holds nnz * h).  grad_attn_col is produced by a deterministic
  * column-side sum (the reference uses atomicAdd, l.854).  m = rows, n = columns
  * (grad_feat, grad_attn_col, attn_col, in_feat have n rows; the rest m).
  */
