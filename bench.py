@@ -378,7 +378,8 @@ def run_ours(args):
         peak, peak_src = hbm_peak()
         fwd_bytes = alg_bytes(conv, "fwd", n_rows, e_local, dim)
         step_bytes = alg_bytes(conv, "fwd+bwd", n_rows, e_local, dim)
-        fwd_kernel = "gat_fwd_kernel" if conv == "gat" else "dot_fwd_kernel"
+        staged = e_local <= 128 * max(n_rows, 1)  # abi_common.h: want_staged (mean degree <= 128)
+        fwd_kernel = ("gat_fwd_staged_kernel" if staged else "gat_fwd_kernel") if conv == "gat" else "dot_fwd_kernel"
         line = {
             "metric": METRIC, "value": units / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,

@@ -27,6 +27,22 @@ def assert_close(name, got, want, rtol=RTOL, atol=ATOL):
             f"worst at {i}: got {got[i]!r} want {want[i]!r} (max abs err {err.max():.3e})")
 
 
+def assert_close_bulk(name, got, want, rtol=RTOL, atol=ATOL, outlier_frac=1e-6, outlier_factor=2.0):
+    """Full-size variant: fp32 accumulation of ~50 cancelling terms against an fp64 reference
+    leaves a handful of elements per 10^7 marginally outside 1e-4 / 1e-5 (the reference's own
+    check_correct tolerates one element per ROW, DFGNN/utils/util.py:226).  Every element must
+    be inside `outlier_factor` x the tolerance and at most `outlier_frac` of them outside 1x."""
+    got = got.detach().double()
+    want = want.detach().double().to(got.device)
+    assert got.shape == want.shape, f"{name}: shape {tuple(got.shape)} vs {tuple(want.shape)}"
+    err = (got - want).abs()
+    tol = atol + rtol * want.abs()
+    n_out = int((err > tol).sum())
+    worst = float((err / tol).max())
+    assert worst <= outlier_factor and n_out <= max(1, int(outlier_frac * err.numel())), (
+        f"{name}: {n_out}/{err.numel()} elements outside rtol={rtol} atol={atol}, worst {worst:.2f}x")
+
+
 def make_case(g: graphs.Graph, dim: int, seed: int, heads: int = 1):
     """CPU-side CSR/CSC (oracle) + seeded operands for a graph."""
     src, dst = g.edges()

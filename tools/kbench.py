@@ -84,7 +84,8 @@ def main():
                 t = ev.cuda_time_total
             rows_out[short] = rows_out.get(short, 0.0) + t / max(ev.count, 1)
         tot = sum(rows_out.values())
-        fwd_k = "gat_fwd_kernel" if conv == "gat" else "dot_fwd_kernel"
+        fwd_k = "gat_fwd_staged_kernel" if "gat_fwd_staged_kernel" in rows_out else (
+            "gat_fwd_kernel" if conv == "gat" else "dot_fwd_kernel")
         fb = B.alg_bytes(conv, "fwd", n, e, dim)
         sb = B.alg_bytes(conv, "fwd+bwd", n, e, dim)
         print(f"[{args.tag}] {name}: N={n} E={e} d={dim}  total {tot:.1f} us "
