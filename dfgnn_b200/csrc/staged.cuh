@@ -48,15 +48,34 @@ __device__ __forceinline__ void stage_pad(E* s_e, int ne) {
 
 enum SpmmMode { kOneOp = 0, kOneOpScalar = 1, kTwoOps = 2 };
 
+// The LAST entry of every segment carries this flag in idx (neighbour ids are < 2^31).
+constexpr int kLastFlag = (int)0x80000000u;
+
+// s_next[r] = the next segment after r that has entries (nseg if none); marks segment ends.
+template <class E>
+__device__ __forceinline__ void stage_mark_ends(const RowBlock& b, const int* s_ptr, E* s_e,
+                                                int* s_next) {
+  const int r = threadIdx.x;
+  if (r < b.nseg) {
+    const int rs = s_ptr[r], re = s_ptr[r + 1];
+    if (re > rs) s_e[re - 1 - b.E0].idx |= kLastFlag;
+    int nx = r + 1;
+    while (nx < b.nseg && s_ptr[nx + 1] == s_ptr[nx]) ++nx;
+    s_next[r] = nx;
+  }
+}
+
 // out[seg] = sum_e w[e] * X[idx[e], :] over the staged tile (kOneOp); kOneOpScalar also sums
 // w1[e] per segment; kTwoOps walks a second operand matrix X1 with weights w1.
-// The group's slice [b.e, b.e_end) starts at a multiple of C behind b.E0 (rowblock_init<G, C>).
-// store(seg, scalar, acc[NV]) is called for segments finished inside one slice; split
-// segments are left in the slots (merge with sum_merge_slots after a __syncthreads()).
+// The group's slice [b.e, b.e_end) is a whole number of C-entry batches (rowblock_init<G, C>;
+// the tile's tail is padded by stage_pad), segment ends are flagged (stage_mark_ends).
+// store(seg, scalar, acc[NV]) is called for segments that lie inside one slice; pieces of
+// split segments are left in the slots (merge with sum_merge_slots after a __syncthreads()).
 template <class L, int C, int MODE, class E, class Store>
-__device__ __forceinline__ void flat_spmm(const RowBlock& b, const int* s_ptr, const E* s_e,
-                                          const RowAddr<L>& ra, const char* X0, const char* X1,
-                                          float* s_slot, int vw, int gl, int f, Store store) {
+__device__ __forceinline__ void flat_spmm(const RowBlock& b, const int* s_ptr, const int* s_next,
+                                          const E* s_e, const RowAddr<L>& ra, const char* X0,
+                                          const char* X1, float* s_slot, int vw, int gl, int f,
+                                          Store store) {
   constexpr int NOPS = MODE == kTwoOps ? 2 : 1;
   constexpr int NR = L::NR, NV = NOPS * NR, LPR = L::LPR;
   static_assert(C <= kStagePad, "padding");
@@ -64,11 +83,15 @@ __device__ __forceinline__ void flat_spmm(const RowBlock& b, const int* s_ptr, c
   const int e_end = b.e_end;
   if (e >= e_end) return;
   int r = find_row(s_ptr, b.nseg, e);
-  int row_end = s_ptr[r + 1];
-  int pend = min(row_end, e_end);
-  bool head = e > s_ptr[r];
+  bool head = e > s_ptr[r];  // the slice starts inside a segment
   float acc[NV], sc = 0.f;
   zero(acc);
+  auto to_slot = [&](int which) {
+    Slot<NV, LPR> sl(s_slot, vw, which);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) sl.v(i, gl) = acc[i];
+    if (gl == 0) { sl.a() = sc; sl.set_seg(r); }
+  };
   const E* pe = s_e + (e - b.E0);
   for (; e < e_end; e += C, pe += C) {
     E en[C];
@@ -77,8 +100,9 @@ __device__ __forceinline__ void flat_spmm(const RowBlock& b, const int* s_ptr, c
     float v0[C][NR], v1[NOPS == 2 ? C : 1][NR];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      L::load(v0[c], ra.at(X0, en[c].idx), gl, f);
-      if constexpr (MODE == kTwoOps) L::load(v1[c], ra.at(X1, en[c].idx), gl, f);
+      const int row = en[c].idx & ~kLastFlag;
+      L::load(v0[c], ra.at(X0, row), gl, f);
+      if constexpr (MODE == kTwoOps) L::load(v1[c], ra.at(X1, row), gl, f);
     }
 #pragma unroll
     for (int c = 0; c < C; ++c) {
@@ -88,27 +112,18 @@ __device__ __forceinline__ void flat_spmm(const RowBlock& b, const int* s_ptr, c
         if constexpr (MODE == kTwoOps) acc[NR + i] = fmaf(en[c].w1, v1[c][i], acc[NR + i]);
       }
       if constexpr (MODE == kOneOpScalar) sc += en[c].w1;
-      if (e + c + 1 == pend) {  // last entry of a piece (never true in the padded tail)
-        const bool complete = pend == row_end;
-        if (!head && complete) {
-          store(r, sc, acc);
-        } else {
-          Slot<NV, LPR> sl(s_slot, vw, head ? 0 : 1);
-#pragma unroll
-          for (int i = 0; i < NV; ++i) sl.v(i, gl) = acc[i];
-          if (gl == 0) { sl.a() = sc; sl.set_seg(r); }
-        }
+      if (en[c].idx < 0) {  // last entry of segment r
+        if (head) to_slot(0);
+        else store(r, sc, acc);
         zero(acc);
         sc = 0.f;
         head = false;
-        if (pend < e_end) {
-          while (s_ptr[r + 1] <= pend) ++r;
-          row_end = s_ptr[r + 1];
-          pend = min(row_end, e_end);
-        }
+        r = s_next[r];
       }
     }
   }
+  // the slice ends inside a segment (never on the padded tail: the tile's last entry is flagged)
+  if (s_e[e_end - 1 - b.E0].idx >= 0) to_slot(head ? 0 : 1);
 }
 
 // out(e, <Xrow[seg(e), :], Y[idx[e], :]>) for every staged entry e (tile-relative).
@@ -142,7 +157,7 @@ __device__ __forceinline__ void flat_sddmm(const RowBlock& b, const int* s_ptr, 
     const E* pe = s_e + ((e < e_end ? e : b.E1) - b.E0);
     int idx[C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) idx[c] = pe[c].idx;
+    for (int c = 0; c < C; ++c) idx[c] = pe[c].idx & ~kLastFlag;
     float y[C][NR];
 #pragma unroll
     for (int c = 0; c < C; ++c) L::load(y[c], ra.at(Y, idx[c]), gl, f);

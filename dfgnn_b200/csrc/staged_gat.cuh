@@ -18,26 +18,32 @@ static_assert(kMaxRB <= kNW * 32, "one thread per row in the prologues");
 
 constexpr int kShortRow = 32;  // rows up to this length are reduced by ONE thread (smem only)
 
-// Per-row passes over the staged tile.  short_row(r, rs, re) runs in the thread that owns row
-// r (rows of <= kShortRow entries); long_row(r, rs, re, valid) runs once per long row with the
-// lane groups of a warp in lockstep (valid == false: idle group, must still take part in the
-// group shuffles).  s_long / s_nlong: the tile's long rows (filled on first use).
-template <int LPR, int G, class Short, class Long>
-__device__ __forceinline__ void per_row(const RowBlock& b, const int* s_rp, int* s_long,
-                                        int* s_nlong, bool build_list, Short short_row,
+// Per-row passes over the staged tile (shared memory only).  Warps [0, kNW/2) take the short
+// rows, one THREAD per row: short_row(r, rs, re).  Warps [kNW/2, kNW) take the rows longer than
+// kShortRow, one WARP per row: long_row(r, rs, re, lane) is called by all 32 lanes and may use
+// warp_sum / warp_max.  rs / re are tile-relative entry positions.
+static_assert(kNW * 32 >= 2 * kMaxRB, "half of the CTA's threads cover the rows of a tile");
+template <class Short, class Long>
+__device__ __forceinline__ void per_row(const RowBlock& b, const int* s_rp, Short short_row,
                                         Long long_row) {
-  const int w = threadIdx.x >> 5, grp = (threadIdx.x & 31) / LPR;
-  if ((int)threadIdx.x < b.nseg) {
-    const int rs = s_rp[threadIdx.x] - b.E0, re = s_rp[threadIdx.x + 1] - b.E0;
-    if (re - rs <= kShortRow) short_row((int)threadIdx.x, rs, re);
-    else if (build_list) s_long[atomicAdd(s_nlong, 1)] = threadIdx.x;
-  }
-  __syncthreads();
-  const int nlong = *s_nlong;
-  for (int k0 = w * G; k0 < nlong; k0 += kNW * G) {
-    const bool valid = k0 + grp < nlong;
-    const int rr = valid ? s_long[k0 + grp] : 0;
-    long_row(rr, valid ? s_rp[rr] - b.E0 : 0, valid ? s_rp[rr + 1] - b.E0 : 0, valid);
+  constexpr int kHalf = kNW * 32 / 2;
+  const int lane = threadIdx.x & 31;
+  if ((int)threadIdx.x < kHalf) {
+    const int r = threadIdx.x;
+    if (r < b.nseg) {
+      const int rs = s_rp[r] - b.E0, re = s_rp[r + 1] - b.E0;
+      if (re - rs <= kShortRow) short_row(r, rs, re);
+    }
+  } else {
+    const int r0 = threadIdx.x - kHalf - lane;  // first row of this warp's 32
+    const int r = r0 + lane;
+    const bool is_long = r < b.nseg && (s_rp[r + 1] - s_rp[r]) > kShortRow;
+    unsigned m = __ballot_sync(kFull, is_long);
+    while (m) {
+      const int rr = r0 + __ffs(m) - 1;
+      m &= m - 1;
+      long_row(rr, s_rp[rr] - b.E0, s_rp[rr + 1] - b.E0, lane);
+    }
   }
 }
 
@@ -47,7 +53,7 @@ __device__ __forceinline__ void per_row(const RowBlock& b, const int* s_rp, int*
 template <class L, int C>
 __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16) / kNW) gat_fwd_staged_kernel(const GatFwdParams p) {
   constexpr int NR = L::NR, LPR = L::LPR, G = L::G, VW = kNW * G;
-  __shared__ int s_rp[kMaxRB + 1], s_long[kMaxRB], s_nlong;
+  __shared__ int s_rp[kMaxRB + 1], s_next[kMaxRB];
   __shared__ float s_inv[kMaxRB], s_ar[kMaxRB];
   __shared__ Ent1 s_e[kStageCap + kStagePad];
   extern __shared__ float s_slot[];
@@ -63,7 +69,6 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16
   const float* acb = p.ac + hid;
 
   slots_clear<NR, LPR>(s_slot, vw, gl);
-  if (threadIdx.x == 0) s_nlong = 0;
   const RowBlock b = rowblock_init<G, C>(s_rp, p.row_ptr, p.m, p.rb, vw);
   const int ne = b.E1 - b.E0;
   if (ne > kStageCap) return;
@@ -112,8 +117,8 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16
       p.esum[node] = l;
     }
   };
-  per_row<LPR, G>(
-      b, s_rp, s_long, &s_nlong, true,
+  per_row(
+      b, s_rp,
       [&](int r, int rs, int re) {
         const float ar_i = s_ar[r];
         float mx = kNeg, l = 0.f;
@@ -125,20 +130,18 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16
         for (int i = rs; i < re; ++i) weight(i, s_e[i].w, mx, l);
         finish_row(r, mx, l);
       },
-      [&](int r, int rs, int re, bool valid) {
+      [&](int r, int rs, int re, int ln) {
         const float ar_i = s_ar[r];
         float mx = kNeg, l = 0.f;
-        for (int i = rs + gl; __any_sync(kFull, i < re); i += LPR)
-          if (i < re) {
-            const float x = leaky(ar_i + s_e[i].w, p.slope);
-            s_e[i].w = x;
-            mx = fmaxf(mx, x);
-          }
-        mx = group_max<LPR>(mx);
-        for (int i = rs + gl; __any_sync(kFull, i < re); i += LPR)
-          if (i < re) weight(i, s_e[i].w, mx, l);
-        l = group_sum<LPR>(l);
-        if (valid && gl == 0) finish_row(r, mx, l);
+        for (int i = rs + ln; i < re; i += 32) {
+          const float x = leaky(ar_i + s_e[i].w, p.slope);
+          s_e[i].w = x;
+          mx = fmaxf(mx, x);
+        }
+        mx = warp_max(mx);
+        for (int i = rs + ln; i < re; i += 32) weight(i, s_e[i].w, mx, l);
+        l = warp_sum(l);
+        if (ln == 0) finish_row(r, mx, l);
       });
   for (int r = vw; r < b.nseg; r += VW)
     if (s_rp[r + 1] == s_rp[r]) {  // rows without edges produce zeros
@@ -146,6 +149,8 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16
       zero(z);
       L::store(ra.at(Ob, b.seg_lb + r), z, gl, f);
     }
+  __syncthreads();
+  stage_mark_ends(b, s_rp, s_e, s_next);
   __syncthreads();
 
   // C: aggregation
@@ -155,7 +160,7 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16
     for (int i = 0; i < NR; ++i) acc[i] *= inv;
     L::store(ra.at(Ob, b.seg_lb + r), acc, gl, f);
   };
-  flat_spmm<L, C, kOneOp>(b, s_rp, s_e, ra, Fb, nullptr, s_slot, vw, gl, f, store);
+  flat_spmm<L, C, kOneOp>(b, s_rp, s_next, s_e, ra, Fb, nullptr, s_slot, vw, gl, f, store);
   __syncthreads();
   sum_merge_slots<NR, LPR, G>(s_slot, vw, gl, store);
 }
@@ -167,7 +172,7 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16
 template <class L, int C>
 __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16) / kNW) gat_bwd_row_staged_kernel(const GatBwdParams p) {
   constexpr int LPR = L::LPR, G = L::G;
-  __shared__ int s_rp[kMaxRB + 1], s_long[kMaxRB], s_nlong;
+  __shared__ int s_rp[kMaxRB + 1];
   __shared__ float s_ar[kMaxRB], s_mx[kMaxRB], s_inv[kMaxRB];
   __shared__ Ent2 s_e[kStageCap + kStagePad];
   __shared__ float s_g[kStageCap];
@@ -182,7 +187,6 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16
   const float* acb = p.ac + hid;
   float2* scratch = reinterpret_cast<float2*>(p.grad_edge);
 
-  if (threadIdx.x == 0) s_nlong = 0;
   const RowBlock b = rowblock_init<G, C>(s_rp, p.row_ptr, p.m, p.rb, vw);
   const int ne = b.E1 - b.E0;
   if (ne > kStageCap) return;
@@ -222,15 +226,15 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16
     s_e[i].w = fast_exp(x - mx) * inv;
     s_e[i].w1 = x < 0.f ? p.slope : 1.f;
   };
-  per_row<LPR, G>(
-      b, s_rp, s_long, &s_nlong, true,
+  per_row(
+      b, s_rp,
       [&](int r, int rs, int re) {
         const float ar_i = s_ar[r], mx = s_mx[r], inv = s_inv[r];
         for (int i = rs; i < re; ++i) prob(i, ar_i, mx, inv);
       },
-      [&](int r, int rs, int re, bool) {
+      [&](int r, int rs, int re, int ln) {
         const float ar_i = s_ar[r], mx = s_mx[r], inv = s_inv[r];
-        for (int i = rs + gl; i < re; i += LPR) prob(i, ar_i, mx, inv);
+        for (int i = rs + ln; i < re; i += 32) prob(i, ar_i, mx, inv);
       });
   __syncthreads();
 
@@ -247,23 +251,21 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16
     scratch[(size_t)(b.E0 + i) * h + hid] = make_float2(de, pk);
     rsum += de;
   };
-  per_row<LPR, G>(
-      b, s_rp, s_long, &s_nlong, false,
+  per_row(
+      b, s_rp,
       [&](int r, int rs, int re) {
         float wsum = 0.f, rsum = 0.f;
         for (int i = rs; i < re; ++i) wsum = fmaf(s_e[i].w * s_e[i].aux, s_g[i], wsum);
         for (int i = rs; i < re; ++i) edge_grad(i, wsum, rsum);
         p.grad_ar[(size_t)(b.seg_lb + r) * h + hid] = rsum;
       },
-      [&](int r, int rs, int re, bool valid) {
+      [&](int r, int rs, int re, int ln) {
         float wsum = 0.f, rsum = 0.f;
-        for (int i = rs + gl; __any_sync(kFull, i < re); i += LPR)
-          if (i < re) wsum = fmaf(s_e[i].w * s_e[i].aux, s_g[i], wsum);
-        wsum = group_sum<LPR>(wsum);
-        for (int i = rs + gl; __any_sync(kFull, i < re); i += LPR)
-          if (i < re) edge_grad(i, wsum, rsum);
-        rsum = group_sum<LPR>(rsum);
-        if (valid && gl == 0) p.grad_ar[(size_t)(b.seg_lb + r) * h + hid] = rsum;
+        for (int i = rs + ln; i < re; i += 32) wsum = fmaf(s_e[i].w * s_e[i].aux, s_g[i], wsum);
+        wsum = warp_sum(wsum);
+        for (int i = rs + ln; i < re; i += 32) edge_grad(i, wsum, rsum);
+        rsum = warp_sum(rsum);
+        if (ln == 0) p.grad_ar[(size_t)(b.seg_lb + r) * h + hid] = rsum;
       });
 }
 
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16
 template <class L, int C>
 __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16) / kNW) gat_bwd_col_staged_kernel(const GatBwdParams p) {
   constexpr int NR = L::NR, LPR = L::LPR, G = L::G, VW = kNW * G;
-  __shared__ int s_cp[kMaxRB + 1];
+  __shared__ int s_cp[kMaxRB + 1], s_next[kMaxRB];
   __shared__ Ent2 s_e[kStageCap + kStagePad];
   extern __shared__ float s_slot[];
 
@@ -320,8 +322,10 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16
       store(c, 0.f, z);
     }
   __syncthreads();
+  stage_mark_ends(b, s_cp, s_e, s_next);
+  __syncthreads();
 
-  flat_spmm<L, C, kOneOpScalar>(b, s_cp, s_e, ra, Gb, nullptr, s_slot, vw, gl, f, store);
+  flat_spmm<L, C, kOneOpScalar>(b, s_cp, s_next, s_e, ra, Gb, nullptr, s_slot, vw, gl, f, store);
   __syncthreads();
   sum_merge_slots<NR, LPR, G>(s_slot, vw, gl, store);
 }
