@@ -107,7 +107,7 @@ struct StageChunk {
   static constexpr int kSpmm = L::NR <= 8 ? DFGNN_SPMM_C : (L::NR <= 16 ? 4 : 2);
   static constexpr int kSpmm2 = L::NR <= 8 ? 4 : 2;  // two operand matrices
   static constexpr int kRaw = L::NR <= 8 ? 4 : 2;    // sddmm also holds two row operands
-  static constexpr int kSddmm = kRaw < L::LPR ? kRaw : L::LPR;
+  static constexpr int kSddmm = stage_x<L>() ? 4 : (kRaw < L::LPR ? kRaw : L::LPR);
 };
 
 // CTA -> tile remap (rowblock.cuh: tile_of).  `slots` = CTAs resident on the chip.

@@ -33,6 +33,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 template <int F4_, int LPR_>
 struct VecLayout {
   static_assert(LPR_ >= 1 && LPR_ <= 32 && (LPR_ & (LPR_ - 1)) == 0 && F4_ % LPR_ == 0, "bad layout");
+  static constexpr bool kVec = true;
   static constexpr int F4 = F4_;
   static constexpr int LPR = LPR_;
   static constexpr int VPL = F4 / LPR;
@@ -50,6 +51,15 @@ struct VecLayout {
       r[4 * v + 0] = t.x; r[4 * v + 1] = t.y; r[4 * v + 2] = t.z; r[4 * v + 3] = t.w;
     }
   }
+  // same from shared memory (`row` already holds the lane offset)
+  __device__ __forceinline__ static void load_smem(float (&r)[NR], const float* row) {
+    const float4* p = reinterpret_cast<const float4*>(row);
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const float4 t = p[v * LPR];
+      r[4 * v + 0] = t.x; r[4 * v + 1] = t.y; r[4 * v + 2] = t.z; r[4 * v + 3] = t.w;
+    }
+  }
   __device__ __forceinline__ static void store(float* __restrict__ row, const float (&r)[NR],
                                                int /*gl*/, int /*f*/) {
     float4* p = reinterpret_cast<float4*>(row);
@@ -62,6 +72,8 @@ struct VecLayout {
 // any f <= 32*NT: scalar loads, the whole warp is one group, lane l owns features l, l+32, ...
 template <int NT_>
 struct ScalarLayout {
+  static constexpr bool kVec = false;
+  static constexpr int F4 = 0;
   static constexpr int LPR = 32;
   static constexpr int G = 1;
   static constexpr int NR = NT_;
@@ -191,6 +203,13 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 __device__ __forceinline__ float fast_exp(float x) { return fast_exp2(x * kLog2e); }
+// Fire-and-forget pull of the 128-byte lines of one feature row into L2 (no register, no
+// scoreboard): the staged kernels issue it for every neighbour row while the per-row
+// passes run, so that the gathers of the aggregation phase find the rows in L2.
+__device__ __forceinline__ void prefetch_row_l2(const char* row, int row_bytes) {
+  for (int o = 0; o < row_bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
+}
+
 // 1/x as one MUFU.RCP (1 ulp)
 __device__ __forceinline__ float fast_rcp(float x) {
   float y;

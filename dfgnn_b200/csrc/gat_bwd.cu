@@ -49,7 +49,9 @@ extern "C" int dfgnn_gat_backward(int m, int n, int nnz, int h, int f, float neg
     ensure_smem(gat_bwd_col_kernel<L, C>, slot_bytes<L::NR, L>());
     if (m > 0) {
       if (staged_r) {
-        gat_bwd_row_staged_kernel<L, StageChunk<L>::kSddmm><<<grid, kNW * 32, 0, st>>>(p);
+        const size_t sx = stage_x<L>() ? (size_t)p.rb * f * sizeof(float) : 0;
+        ensure_smem(gat_bwd_row_staged_kernel<L, StageChunk<L>::kSddmm>, sx, 44 * 1024);
+        gat_bwd_row_staged_kernel<L, StageChunk<L>::kSddmm><<<grid, kNW * 32, sx, st>>>(p);
         rc = check_launch(fn);
         if (rc) return;
         p.cap = kStageCap;

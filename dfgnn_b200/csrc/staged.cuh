@@ -46,6 +46,10 @@ __device__ __forceinline__ void stage_pad(E* s_e, int ne) {
   }
 }
 
+// row operands of a tile are staged in shared memory for vector layouts up to f = 128
+template <class L>
+constexpr bool stage_x() { return L::kVec && L::NR * L::LPR <= 128; }
+
 enum SpmmMode { kOneOp = 0, kOneOpScalar = 1, kTwoOps = 2 };
 
 // The LAST entry of every segment carries this flag in idx (neighbour ids are < 2^31).
@@ -179,6 +183,79 @@ __device__ __forceinline__ void flat_sddmm(const RowBlock& b, const int* s_ptr, 
       if (gl == c) mine = d;
     }
     if (gl < C && e + gl < e_end) out(e - b.E0 + gl, mine);
+    e += C;
+  }
+}
+
+// Group totals of FOUR per-lane partial sums with 2 + log2(LPR / 2) shuffles instead of
+// 4 * log2(LPR): lanes swap halves of their values (butterfly on the values, not the lanes).
+// Returns the total of d[perm4(gl)], perm4(gl) = 2 * (gl & 1) + ((gl >> 1) & 1).
+__device__ __forceinline__ int perm4(int gl) { return ((gl & 1) << 1) | ((gl >> 1) & 1); }
+template <int LPR>
+__device__ __forceinline__ float reduce4_transposed(const float (&d)[4], int gl) {
+  static_assert(LPR >= 4, "needs at least four lanes per group");
+  const bool o1 = gl & 1, o2 = gl & 2;
+  const float s0 = o1 ? d[0] : d[2], s1 = o1 ? d[1] : d[3];
+  float k0 = o1 ? d[2] : d[0], k1 = o1 ? d[3] : d[1];
+  k0 += __shfl_xor_sync(kFull, s0, 1);
+  k1 += __shfl_xor_sync(kFull, s1, 1);
+  const float s = o2 ? k0 : k1;
+  float k = o2 ? k1 : k0;
+  k += __shfl_xor_sync(kFull, s, 2);
+#pragma unroll
+  for (int off = 4; off < LPR; off <<= 1) k += __shfl_xor_sync(kFull, k, off);
+  return k;
+}
+
+// flat_sddmm with the row operands of the tile staged in shared memory (s_x: [nseg][f], f = 4 *
+// L::F4 floats per row) and flagged segment ends: a row switch is two LDS.128 instead of a
+// register copy of a prefetched row.  C == 4 uses the transposed reduction.
+template <class L, int C, class E, class Out>
+__device__ __forceinline__ void flat_sddmm_sx(const RowBlock& b, const int* s_ptr, const int* s_next,
+                                              const E* s_e, const RowAddr<L>& ra, const float* s_x,
+                                              const char* Y, int gl, int f, Out out) {
+  constexpr int NR = L::NR, LPR = L::LPR;
+  static_assert(L::kVec && C <= LPR, "vector layouts only; one result lane per entry in flight");
+  int e = b.e;
+  const int e_end = b.e_end;
+  const float* xl = s_x + 4 * gl;  // this lane's float4 column of every staged row
+  float x[NR];
+  zero(x);
+  int r = 0;
+  if (e < e_end) {
+    r = find_row(s_ptr, b.nseg, e);
+    L::load_smem(x, xl + r * f);
+  }
+  while (__any_sync(kFull, e < e_end)) {
+    // a group that has run out of entries parks on the padding behind the tile
+    const E* pe = s_e + ((e < e_end ? e : b.E1) - b.E0);
+    int raw[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) raw[c] = pe[c].idx;
+    float y[C][NR];
+#pragma unroll
+    for (int c = 0; c < C; ++c) L::load(y[c], ra.at(Y, raw[c] & ~kLastFlag), gl, f);
+    float d[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      d[c] = dot<NR>(x, y[c]);
+      if (raw[c] < 0) {  // last entry of segment r: switch to the next segment that has entries
+        r = s_next[r];
+        if (r < b.nseg) L::load_smem(x, xl + r * f);
+      }
+    }
+    if constexpr (C == 4 && LPR >= 4) {
+      const float t = reduce4_transposed<LPR>(d, gl);
+      if (gl < 4 && e + perm4(gl) < e_end) out(e - b.E0 + perm4(gl), t);
+    } else {
+      float mine = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float t = group_sum<LPR>(d[c]);
+        if (gl == c) mine = t;
+      }
+      if (gl < C && e + gl < e_end) out(e - b.E0 + gl, mine);
+    }
     e += C;
   }
 }

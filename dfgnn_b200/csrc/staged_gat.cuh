@@ -88,6 +88,9 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16
     for (int k = 0; k < kEPT; ++k) {
       const int i = threadIdx.x + k * (kNW * 32);
       acv[k] = i < ne ? __ldg(acb + (size_t)(unsigned)cols[k] * (unsigned)h) : 0.f;
+#ifndef DFGNN_NO_PREFETCH
+      if (i < ne) prefetch_row_l2(reinterpret_cast<const char*>(p.feat + ((size_t)cols[k] * h + hid) * f), f * 4);
+#endif
     }
 #pragma unroll
     for (int k = 0; k < kEPT; ++k) {
@@ -176,6 +179,9 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16
   __shared__ float s_ar[kMaxRB], s_mx[kMaxRB], s_inv[kMaxRB];
   __shared__ Ent2 s_e[kStageCap + kStagePad];
   __shared__ float s_g[kStageCap];
+  __shared__ int s_next[kMaxRB];
+  extern __shared__ float4 s_x4[];  // dO rows of the tile (kStageX)
+  constexpr bool kStageX = stage_x<L>();
 
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int grp = lane / LPR, gl = lane % LPR, vw = w * G + grp;
@@ -213,11 +219,22 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16
     for (int k = 0; k < kEPT; ++k) {
       const int i = threadIdx.x + k * (kNW * 32);
       acv[k] = i < ne ? __ldg(acb + (size_t)(unsigned)cols[k] * (unsigned)h) : 0.f;
+#ifndef DFGNN_NO_PREFETCH
+      if (i < ne) prefetch_row_l2(reinterpret_cast<const char*>(p.feat + ((size_t)cols[k] * h + hid) * f), f * 4);
+#endif
     }
 #pragma unroll
     for (int k = 0; k < kEPT; ++k) {
       const int i = threadIdx.x + k * (kNW * 32);
       if (i < ne) { Ent2 en; en.idx = cols[k]; en.w = acv[k]; en.w1 = 0.f; en.aux = kmv[k]; s_e[i] = en; }
+    }
+  }
+  if constexpr (kStageX) {  // dO rows of the tile -> shared memory
+    constexpr int F4 = L::F4 > 0 ? L::F4 : 1;
+    const float4* src = reinterpret_cast<const float4*>(p.dO);
+    for (int i = threadIdx.x; i < b.nseg * F4; i += kNW * 32) {
+      const int r = i / F4, k = i % F4;
+      s_x4[i] = __ldg(src + ((size_t)(b.seg_lb + r) * h + hid) * F4 + k);
     }
   }
   __syncthreads();
@@ -238,8 +255,16 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16
       });
   __syncthreads();
 
-  if (ne > 0)
-    flat_sddmm<L, C>(b, s_rp, s_e, ra, Gb, Fb, gl, f, [&](int k, float d) { s_g[k] = d; });
+  if constexpr (kStageX) {
+    stage_mark_ends(b, s_rp, s_e, s_next);
+    __syncthreads();
+    if (ne > 0)
+      flat_sddmm_sx<L, C>(b, s_rp, s_next, s_e, ra, reinterpret_cast<const float*>(s_x4), Fb, gl, f,
+                          [&](int k, float d) { s_g[k] = d; });
+  } else {
+    if (ne > 0)
+      flat_sddmm<L, C>(b, s_rp, s_e, ra, Gb, Fb, gl, f, [&](int k, float d) { s_g[k] = d; });
+  }
   __syncthreads();
 
   // de_e = (t_e - w_i p_e) * lrelu'(x_e), t_e = keep-scaled p_e g_e, w_i = sum_e t_e
@@ -304,6 +329,9 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16
     for (int k = 0; k < kEPT; ++k) {
       const int i = threadIdx.x + k * (kNW * 32);
       dp[k] = i < ne ? __ldg(scratch + (size_t)eid[k] * h + hid) : make_float2(0.f, 0.f);
+#ifndef DFGNN_NO_PREFETCH
+      if (i < ne) prefetch_row_l2(reinterpret_cast<const char*>(p.dO + ((size_t)rid[k] * h + hid) * f), f * 4);
+#endif
     }
 #pragma unroll
     for (int k = 0; k < kEPT; ++k) {
