@@ -110,19 +110,6 @@ struct StageChunk {
   static constexpr int kSddmm = stage_x<L>() ? 4 : (kRaw < L::LPR ? kRaw : L::LPR);
 };
 
-// CTA -> tile remap (rowblock.cuh: tile_of).  `slots` = CTAs resident on the chip.
-struct TileGrid { int ntiles, slots, grid; };
-inline TileGrid tile_grid(int nseg, int rb, int slots) {
-  const int nt = (nseg + rb - 1) / rb;
-  if (slots <= 0 || nt <= slots) return {nt, 0, nt};
-  const int per = (nt + slots - 1) / slots;
-  return {nt, slots, slots * per};
-}
-inline int remap_slots_env() {
-  static const int v = [] { const char* e = getenv("DFGNN_B200_SLOTS"); return e ? atoi(e) : 0; }();
-  return v;
-}
-
 inline int check_common(const char* fn, int m, int nnz, int h, int f) {
   if (m < 0 || nnz < 0 || h < 1 || f < 1) {
     set_error("%s: invalid sizes m=%d nnz=%d h=%d f=%d", fn, m, nnz, h, f);
@@ -163,6 +150,31 @@ template <class K>
 inline void ensure_smem(K kernel, size_t bytes, size_t static_bytes) {
   if (bytes + static_bytes > 48 * 1024)
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+// Launch `kernel` so that it may start while the kernel in front of it on the stream is still
+// draining (programmatic dependent launch).  Used for the "big tiles only" row-block launch
+// behind a staged kernel: the two write disjoint tiles and read only inputs, so there is no
+// dependency to wait for; the staged kernel issues griddepcontrol.launch_dependents at entry.
+template <class P>
+inline void launch_overlapped(void (*kernel)(P), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              const P& p) {
+  static const bool off = getenv("DFGNN_B200_NO_PDL") != nullptr;  // developer knob
+  if (off) {
+    kernel<<<grid, block, smem, st>>>(p);
+    return;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, p);
 }
 
 // internal launchers (one per kernel family), defined in gt.cu / gat.cu

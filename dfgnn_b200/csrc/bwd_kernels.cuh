@@ -35,7 +35,6 @@ struct GtBwdParams {
   float* dK;
   float* dV;
   float* grad_edge;    // [h, nnz, 2] scratch: {dS_e, p_e}
-  int slots = 0, ntiles = 0, ntiles_col = 0;  // CTA -> tile remap (tile_of)
   int cap = 0;         // > 0: process only tiles with more than `cap` entries
 };
 
@@ -79,9 +78,7 @@ __global__ void __launch_bounds__(kNW * 32, 16 / kNW) gt_bwd_row_kernel(const Gt
   char* DQb = ra.base(p.dQ);
 
   slots_clear<2 * NR, LPR>(s_slot, vw, gl);
-  const int tile = tile_of(p.slots, p.ntiles);
-  if (tile >= (p.m + p.rb - 1) / p.rb) return;
-  const RowBlock b = rowblock_init<G>(s_rp, p.row_ptr, p.m, p.rb, vw, tile);
+  const RowBlock b = rowblock_init<G>(s_rp, p.row_ptr, p.m, p.rb, vw);
   if (p.cap > 0 && b.E1 - b.E0 <= p.cap) return;
 
   // Per piece: acc2 = [A1c | A2] with A1c = sum_e p_e (dA_e - c) K_e, A2 = sum_e p_e K_e,
@@ -224,9 +221,7 @@ __global__ void __launch_bounds__(kNW * 32, 16 / kNW) gt_bwd_col_kernel(const Gt
   char* DKb = ra.base(p.dK);
 
   slots_clear<2 * NR, LPR>(s_slot, vw, gl);
-  const int tile = tile_of(p.slots, p.ntiles_col);
-  if (tile >= (p.n + p.rb_col - 1) / p.rb_col) return;
-  const RowBlock b = rowblock_init<G>(s_cp, p.col_ptr, p.n, p.rb_col, vw, tile);
+  const RowBlock b = rowblock_init<G>(s_cp, p.col_ptr, p.n, p.rb_col, vw);
   if (p.cap > 0 && b.E1 - b.E0 <= p.cap) return;
 
   // acc2 = [dV | dK]
@@ -322,7 +317,6 @@ struct GatBwdParams {
   float* grad_ar;
   float* grad_ac;
   float* grad_edge;     // [nnz, h, 2] scratch: {t_e then de_e, keep-scaled p_e}
-  int slots = 0, ntiles = 0, ntiles_col = 0;  // CTA -> tile remap (tile_of)
   int cap = 0;          // > 0: process only tiles with more than `cap` entries
 };
 
@@ -345,9 +339,7 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : 16) / kNW) gat_bw
   float2* scratch = reinterpret_cast<float2*>(p.grad_edge);  // [nnz, h] x {de_e, keep-scaled p_e}
 
   slots_clear<1, LPR>(s_slot, vw, gl);
-  const int tile = tile_of(p.slots, p.ntiles);
-  if (tile >= (p.m + p.rb - 1) / p.rb) return;
-  const RowBlock b = rowblock_init<G>(s_rp, p.row_ptr, p.m, p.rb, vw, tile);
+  const RowBlock b = rowblock_init<G>(s_rp, p.row_ptr, p.m, p.rb, vw);
   if (p.cap > 0 && b.E1 - b.E0 <= p.cap) return;
 
   for (int r = vw; r < b.nseg; r += VW)
@@ -454,9 +446,7 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR * C <= 32 ? 24 : 16) / kNW) g
   const float2* scratch = reinterpret_cast<const float2*>(p.grad_edge);
 
   slots_clear<NR, LPR>(s_slot, vw, gl);
-  const int tile = tile_of(p.slots, p.ntiles_col);
-  if (tile >= (p.n + p.rb_col - 1) / p.rb_col) return;
-  const RowBlock b = rowblock_init<G>(s_cp, p.col_ptr, p.n, p.rb_col, vw, tile);
+  const RowBlock b = rowblock_init<G>(s_cp, p.col_ptr, p.n, p.rb_col, vw);
   if (p.cap > 0 && b.E1 - b.E0 <= p.cap) return;
 
   auto finish = [&](int c, float dac, float (&acc)[NR]) {

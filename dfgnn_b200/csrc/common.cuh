@@ -210,6 +210,12 @@ __device__ __forceinline__ void prefetch_row_l2(const char* row, int row_bytes) 
   for (int o = 0; o < row_bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
 }
 
+// lets the next kernel on the stream start early if it was launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization (abi_common.h: launch_overlapped)
+__device__ __forceinline__ void allow_dependent_launch() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // 1/x as one MUFU.RCP (1 ulp)
 __device__ __forceinline__ float fast_rcp(float x) {
   float y;

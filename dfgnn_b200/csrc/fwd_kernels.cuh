@@ -24,7 +24,6 @@ struct DotFwdParams {
   const float* rn;   // [m, h] inverse norms (AGNN) or null
   float* out;
   float* attn;       // [h, nnz] or null
-  int slots = 0, ntiles = 0;  // CTA -> tile remap (tile_of)
   int cap = 0;       // > 0: process only tiles with more than `cap` entries (behind a staged kernel)
 };
 
@@ -86,9 +85,7 @@ __global__ void __launch_bounds__(kNW * 32, 16 / kNW) dot_fwd_kernel(const DotFw
   char* Ob = ra.base(p.out);
 
   slots_clear<NR, LPR>(s_slot, vw, gl);
-  const int tile = tile_of(p.slots, p.ntiles);
-  if (tile >= (p.m + p.rb - 1) / p.rb) return;
-  const RowBlock b = rowblock_init<G>(s_rp, p.row_ptr, p.m, p.rb, vw, tile);
+  const RowBlock b = rowblock_init<G>(s_rp, p.row_ptr, p.m, p.rb, vw);
   if (p.cap > 0 && b.E1 - b.E0 <= p.cap) return;
 
   auto finish = [&](int r, float m, float l, float (&acc)[NR]) {
@@ -211,7 +208,6 @@ struct GatFwdParams {
   float* emax;   // [m, h] or null
   float* esum;   // [m, h] or null
   float* emask;  // [nnz, h] or null
-  int slots = 0, ntiles = 0;  // CTA -> tile remap (tile_of)
   int cap = 0;   // > 0: process only tiles with more than `cap` entries (behind a staged kernel)
 };
 
@@ -245,9 +241,7 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : 16) / kNW) gat_fw
   const float* acb = p.ac + hid;
 
   slots_clear<NR, LPR>(s_slot, vw, gl);
-  const int tile = tile_of(p.slots, p.ntiles);
-  if (tile >= (p.m + p.rb - 1) / p.rb) return;
-  const RowBlock b = rowblock_init<G>(s_rp, p.row_ptr, p.m, p.rb, vw, tile);
+  const RowBlock b = rowblock_init<G>(s_rp, p.row_ptr, p.m, p.rb, vw);
   if (p.cap > 0 && b.E1 - b.E0 <= p.cap) return;
 
   auto finish = [&](int r, float m, float l, float (&acc)[NR]) {

@@ -55,8 +55,10 @@ extern "C" int dfgnn_gat_backward(int m, int n, int nnz, int h, int f, float neg
         rc = check_launch(fn);
         if (rc) return;
         p.cap = kStageCap;
+        launch_overlapped(gat_bwd_row_kernel<L, C>, grid, dim3(kNW * 32), slot_bytes<1, L>(), st, p);
+      } else {
+        gat_bwd_row_kernel<L, C><<<grid, kNW * 32, slot_bytes<1, L>(), st>>>(p);
       }
-      gat_bwd_row_kernel<L, C><<<grid, kNW * 32, slot_bytes<1, L>(), st>>>(p);
       rc = check_launch(fn);
       if (rc) return;
     }
@@ -68,8 +70,10 @@ extern "C" int dfgnn_gat_backward(int m, int n, int nnz, int h, int f, float neg
         rc = check_launch(fn);
         if (rc) return;
         p.cap = kStageCap;
+        launch_overlapped(gat_bwd_col_kernel<L, C>, grid_c, dim3(kNW * 32), slot_bytes<L::NR, L>(), st, p);
+      } else {
+        gat_bwd_col_kernel<L, C><<<grid_c, kNW * 32, slot_bytes<L::NR, L>(), st>>>(p);
       }
-      gat_bwd_col_kernel<L, C><<<grid_c, kNW * 32, slot_bytes<L::NR, L>(), st>>>(p);
       rc = check_launch(fn);
     }
   });

@@ -39,8 +39,10 @@ int launch_gat_fwd(int m, int nnz, int h, int f, const float* ar, const float* a
       rc = check_launch(fn);
       if (rc) return;
       p.cap = kStageCap;  // tiles the staged kernel skipped
+      launch_overlapped(gat_fwd_kernel<L, C>, grid, dim3(kNW * 32), smem, st, p);
+    } else {
+      gat_fwd_kernel<L, C><<<grid, kNW * 32, smem, st>>>(p);
     }
-    gat_fwd_kernel<L, C><<<grid, kNW * 32, smem, st>>>(p);
     rc = check_launch(fn);
   });
   return rc;

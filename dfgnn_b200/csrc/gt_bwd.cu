@@ -32,12 +32,8 @@ extern "C" int dfgnn_gt_backward(int m, int n, int nnz, int h, int f, const int3
     constexpr int C = ChunkOf<L>::C;
     p.rb = pick_rb(m, nnz, L::G);
     p.rb_col = pick_rb(n, nnz, L::G);
-    const TileGrid tg = tile_grid(m, p.rb, remap_slots_env()), tgc = tile_grid(n, p.rb_col, remap_slots_env());
-    p.slots = tg.slots;  // (experiment: same slot count on both sides)
-    p.ntiles = tg.ntiles;
-    p.ntiles_col = tgc.ntiles;
-    const dim3 grid(tg.grid, h);
-    const dim3 grid_c(tgc.grid, h);
+    const dim3 grid((m + p.rb - 1) / p.rb, h);
+    const dim3 grid_c((n + p.rb_col - 1) / p.rb_col, h);
     const size_t smem = slot_bytes<2 * L::NR, L>();
     ensure_smem(gt_bwd_row_kernel<L, C>, smem);
     ensure_smem(gt_bwd_col_kernel<L, C>, smem);

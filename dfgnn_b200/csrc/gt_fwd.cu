@@ -15,10 +15,7 @@ int launch_dot_fwd(bool agnn, int m, int nnz, int h, int f, const int* row_ptr, 
     using L = typename decltype(tag)::type;
     constexpr int C = ChunkOf<L>::C;
     p.rb = pick_rb(m, nnz, L::G);
-    const TileGrid tg = tile_grid(m, p.rb, remap_slots_env());
-    p.slots = tg.slots;
-    p.ntiles = tg.ntiles;
-    const dim3 grid(tg.grid, h);
+    const dim3 grid((m + p.rb - 1) / p.rb, h);
     const size_t smem = slot_bytes<L::NR, L>();
     if (agnn) {
       ensure_smem(dot_fwd_kernel<L, C, true>, smem);

@@ -28,16 +28,6 @@ namespace dfgnn {
 constexpr int kNW = DFGNN_KNW;  // warps per CTA
 constexpr int kMaxRB = 128;   // max segments per CTA
 
-// CTA -> tile mapping.  slots == 0: tile = blockIdx.x.  slots > 0 (the number of CTAs resident
-// on the chip): CTA b takes tile (b % slots) * per + b / slots, so the CTAs that follow one
-// another in a residency slot walk CONSECUTIVE tiles -- on block-diagonal (batched) graphs the
-// neighbour rows of consecutive tiles are the same few rows, which then stay in that SM's L1.
-__device__ __forceinline__ int tile_of(int slots, int ntiles) {
-  if (slots <= 0) return blockIdx.x;
-  const int per = (ntiles + slots - 1) / slots;
-  return (blockIdx.x % slots) * per + blockIdx.x / slots;
-}
-
 struct RowBlock {
   int seg_lb;   // first segment of this CTA
   int nseg;     // segments in this CTA

@@ -46,6 +46,10 @@ __device__ __forceinline__ void stage_pad(E* s_e, int ne) {
   }
 }
 
+// floats of the partial-result slots of one CTA (two per lane group)
+template <int NV, class L>
+constexpr int slot_floats() { return kNW * L::G * 2 * Slot<NV, L::LPR>::kFloats; }
+
 // row operands of a tile are staged in shared memory for vector layouts up to f = 128
 template <class L>
 constexpr bool stage_x() { return L::kVec && L::NR * L::LPR <= 128; }

@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16
   __shared__ Ent1 s_e[kStageCap + kStagePad];
   extern __shared__ float s_slot[];
 
+  allow_dependent_launch();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int grp = lane / LPR, gl = lane % LPR, vw = w * G + grp;
   const int hid = blockIdx.y, h = p.h, f = p.f;
@@ -183,6 +184,7 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16
   extern __shared__ float4 s_x4[];  // dO rows of the tile (kStageX)
   constexpr bool kStageX = stage_x<L>();
 
+  allow_dependent_launch();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int grp = lane / LPR, gl = lane % LPR, vw = w * G + grp;
   const int hid = blockIdx.y, h = p.h, f = p.f;
@@ -303,6 +305,7 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16
   __shared__ Ent2 s_e[kStageCap + kStagePad];
   extern __shared__ float s_slot[];
 
+  allow_dependent_launch();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int grp = lane / LPR, gl = lane % LPR, vw = w * G + grp;
   const int hid = blockIdx.y, h = p.h, f = p.f;

@@ -74,6 +74,17 @@ def main():
                 flush.fill_(1.0)
                 step()
             torch.cuda.synchronize()
+        # whole step (all launches) with CUDA events, L2 flushed before each step
+        evs = []
+        for _ in range(args.iters):
+            flush.fill_(1.0)
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step()
+            b_.record()
+            evs.append((a, b_))
+        torch.cuda.synchronize()
+        step_us = sorted(a.elapsed_time(b_) * 1e3 for a, b_ in evs)[len(evs) // 2]
         rows_out = {}
         for ev in prof.key_averages():
             if "dfgnn" not in ev.key:
@@ -88,7 +99,7 @@ def main():
             "gat_fwd_kernel" if conv == "gat" else "dot_fwd_kernel")
         fb = B.alg_bytes(conv, "fwd", n, e, dim)
         sb = B.alg_bytes(conv, "fwd+bwd", n, e, dim)
-        print(f"[{args.tag}] {name}: N={n} E={e} d={dim}  total {tot:.1f} us "
+        print(f"[{args.tag}] {name}: N={n} E={e} d={dim}  step(events, median) {step_us:.1f} us  kernels total {tot:.1f} us "
               f"(step frac {sb / tot / 1e3 / peak:.3f})  fwd frac {fb / rows_out.get(fwd_k, 1e9) / 1e3 / peak:.3f}")
         for k, v in rows_out.items():
             print(f"    {k:24s} {v:9.1f} us")
