@@ -20,7 +20,7 @@
 #define DFGNN_LPR64 8
 #endif
 #ifndef DFGNN_LPR128
-#define DFGNN_LPR128 8
+#define DFGNN_LPR128 16
 #endif
 
 namespace dfgnn {
@@ -44,11 +44,16 @@ struct Tag { using type = T; };
 // Picks the lane-group layout for a feature width.  Returns false for f > 512.
 // 8 lanes per row wherever the row is at least 8 float4 wide: 4 rows per warp
 // instruction stream, 3-stage group reductions.
+// `long_rows` (mean degree > 128, GT kernels only): f = 128 keeps 8 lanes per row there (16 floats
+// per lane, 16 resident warps) -- on super-node graphs the deeper per-lane rows win, on short
+// and medium rows 16 lanes x 8 floats at 24 resident warps do (measured: reddit- vs PATTERN- /
+// VOC-shaped workloads).
 template <class Fn>
-inline bool dispatch_layout(int f, Fn&& fn) {
+inline bool dispatch_layout(int f, Fn&& fn, bool long_rows = false) {
   if (f == 16) fn(Tag<VecLayout<4, 4>>{});
   else if (f == 32) fn(Tag<VecLayout<8, 8>>{});
   else if (f == 64) fn(Tag<VecLayout<16, DFGNN_LPR64>>{});
+  else if (f == 128 && long_rows) fn(Tag<VecLayout<32, 8>>{});
   else if (f == 128) fn(Tag<VecLayout<32, DFGNN_LPR128>>{});
   else if (f == 256) fn(Tag<VecLayout<64, 16>>{});
   else if (f == 512) fn(Tag<VecLayout<128, 32>>{});
@@ -109,6 +114,8 @@ struct StageChunk {
   static constexpr int kRaw = L::NR <= 8 ? 4 : 2;    // sddmm also holds two row operands
   static constexpr int kSddmm = stage_x<L>() ? 4 : (kRaw < L::LPR ? kRaw : L::LPR);
 };
+
+inline bool long_rows(int m, int nnz) { return m > 0 && (double)nnz / (double)m > 128.0; }
 
 inline int check_common(const char* fn, int m, int nnz, int h, int f) {
   if (m < 0 || nnz < 0 || h < 1 || f < 1) {

@@ -125,9 +125,15 @@ struct RowAddr {
 // NR floats per edge in the GT kernels) and by the group's chunk of LPR edges.
 template <class L>
 struct ChunkOf {
-  static constexpr int kByReg = L::NR <= 4 ? 8 : (L::NR <= 8 ? 4 : (L::NR <= 16 ? 2 : 1));
+  // GT kernels hold two rows of NR floats per entry; NR <= 8 is compiled for 24 resident warps
+  // per SM (<= 80 registers), which pays more than a deeper batch (measured on PATTERN / VOC)
+  static constexpr int kByReg = L::NR <= 4 ? 4 : (L::NR <= 16 ? 2 : 1);
   static constexpr int kChunk = L::LPR < 8 ? L::LPR : 8;  // edges whose indices a group prefetches
+#ifdef DFGNN_GT_C  // developer knob: entries in flight per group in the GT kernels
+  static constexpr int C = DFGNN_GT_C;
+#else
   static constexpr int C = kByReg < kChunk ? kByReg : kChunk;
+#endif
   // kernels that gather ONE row per edge (GAT) can keep twice as many edges in flight
   static constexpr int kByReg1 = L::NR <= 4 ? 8 : (L::NR <= 8 ? 4 : (L::NR <= 16 ? 4 : 2));
   static constexpr int C1 = kByReg1 < L::LPR ? kByReg1 : L::LPR;

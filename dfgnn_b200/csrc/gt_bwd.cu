@@ -46,6 +46,6 @@ extern "C" int dfgnn_gt_backward(int m, int n, int nnz, int h, int f, const int3
       gt_bwd_col_kernel<L, C><<<grid_c, kNW * 32, smem, st>>>(p);
       rc = check_launch(fn);
     }
-  });
+  }, long_rows(m, nnz));
   return rc;
 }

@@ -25,7 +25,7 @@ int launch_dot_fwd(bool agnn, int m, int nnz, int h, int f, const int* row_ptr, 
       dot_fwd_kernel<L, C, false><<<grid, kNW * 32, smem, st>>>(p);
     }
     rc = check_launch(fn);
-  });
+  }, long_rows(m, nnz));
   return rc;
 }
 

@@ -26,6 +26,9 @@ namespace dfgnn {
 #define DFGNN_KNW 8
 #endif
 constexpr int kNW = DFGNN_KNW;  // warps per CTA
+#ifndef DFGNN_GT_WARPS
+#define DFGNN_GT_WARPS 16  // resident warps per SM the GT kernels are compiled for
+#endif
 constexpr int kMaxRB = 128;   // max segments per CTA
 
 struct RowBlock {
