@@ -62,6 +62,18 @@ def alg_bytes(conv: str, phase: str, n: int, e: int, d: int) -> float:
     return {"fwd": fwd, "fwd+bwd": both, "bwd": both - fwd}[phase]
 
 
+def kernel_alg_bytes(conv: str, n: int, e: int, d: int) -> dict:
+    """Per-kernel split of the gather model: every edge fetches the neighbour
+    rows the kernel consumes, the row operand is read once per row, every index / edge scalar once."""
+    if conv == "gt":
+        return {"fwd": 8.0 * e * d + 8.0 * n * d + 8.0 * e + 4.0 * n,            # K,V rows; Q, out; col_ind, attn_edge
+                "bwd_row": 8.0 * e * d + 8.0 * n * d + 16.0 * e + 4.0 * n,      # V,K rows; dO, dQ; col_ind, attn, {dS,p}
+                "bwd_col": 8.0 * e * d + 8.0 * n * d + 16.0 * e + 4.0 * n}      # dO,Q rows; dK, dV; row_ind, val_idx, {dS,p}
+    return {"fwd": 4.0 * e * d + 4.0 * n * d + 8.0 * e + 12.0 * n,                # feat rows; out; col_ind, attn_col[j]
+            "bwd_row": 4.0 * e * d + 4.0 * n * d + 16.0 * e + 16.0 * n,          # feat rows; dO; col_ind, attn_col[j], {de,p}
+            "bwd_col": 4.0 * e * d + 4.0 * n * d + 16.0 * e + 8.0 * n}           # dO rows; grad_feat; row_ind, permute, {de,p}
+
+
 def hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -335,19 +347,44 @@ def run_ours(args):
         n0 = _lib.launch_count()
         step_device()
         launches = (_lib.launch_count() - n0) * args.steps
-        # the forward kernel on its own (roofline leg), same flush protocol, eager launches
-        for r in recs:
-            flush.fill_(1.0)
-            r["f0"].record()
-            if conv == "gt":
-                N.gt_hyper_forward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem,
-                                   d_in["Q"], d_in["K"], d_in["V"])
-            else:
-                N.gat_forward(d_in["ar"], d_in["ac"], row_ptr, col_ind, 0.2, d_in["F"], 0.0)
-            r["f1"].record()
-        torch.cuda.synchronize()
+    # every kernel of the step on its own (roofline leg): same flush protocol, eager launches,
+    # CUDA events around the single library call that launches it
+    kern_ms = {"fwd": [], "bwd_row": [], "bwd_col": []}
+    if world == 1:
+        if conv == "gt":
+            out0, attn0 = N.gt_hyper_forward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem,
+                                             d_in["Q"], d_in["K"], d_in["V"])
+            bargs = (row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, d_in["Q"], d_in["K"],
+                     d_in["V"], attn0, d_in["dO"])
+            bufs = N.gt_backward(*bargs, _phases=1)
+            calls = {"fwd": lambda: N.gt_hyper_forward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx,
+                                                       smem, d_in["Q"], d_in["K"], d_in["V"]),
+                     "bwd_row": lambda: N.gt_backward(*bargs, _phases=1, _buffers=bufs),
+                     "bwd_col": lambda: N.gt_backward(*bargs, _phases=2, _buffers=bufs)}
+        else:
+            o0, emax0, esum0, emask0 = N.gat_forward(d_in["ar"], d_in["ac"], row_ptr, col_ind, 0.2, d_in["F"], 0.0)
+            bargs = (0.2, 0.0, row_ptr, col_ind, col_ptr, row_ind, val_idx, emax0, esum0, emask0, d_in["F"],
+                     d_in["ar"], d_in["ac"], d_in["dO"])
+            bufs = N.gat_backward(*bargs, _phases=1)
+            calls = {"fwd": lambda: N.gat_forward(d_in["ar"], d_in["ac"], row_ptr, col_ind, 0.2, d_in["F"], 0.0),
+                     "bwd_row": lambda: N.gat_backward(*bargs, _phases=1, _buffers=bufs),
+                     "bwd_col": lambda: N.gat_backward(*bargs, _phases=2, _buffers=bufs)}
+        for kname, call in calls.items():
+            call()
+            pairs = []
+            for _ in range(args.steps):
+                flush.fill_(1.0)
+                a, b_ = ev(), ev()
+                a.record()
+                call()
+                b_.record()
+                pairs.append((a, b_))
+            torch.cuda.synchronize()
+            kern_ms[kname] = [a.elapsed_time(b_) for a, b_ in pairs]
+        for r, t in zip(recs, kern_ms["fwd"]):
+            r["fwd_ms"] = t
     step_ms = [r["s"].elapsed_time(r["e"]) for r in recs]
-    fwd_ms = [r["f0"].elapsed_time(r["f1"]) for r in recs]
+    fwd_ms = kern_ms["fwd"] if kern_ms["fwd"] else [r["f0"].elapsed_time(r["f1"]) for r in recs]
     ag_ms = [r["ag0"].elapsed_time(r["ag1"]) for r in recs] if world > 1 else [0.0] * len(recs)
     rs_ms = [r["rs0"].elapsed_time(r["rs1"]) for r in recs] if world > 1 else [0.0] * len(recs)
     ms_local = sum(step_ms) / len(step_ms)
@@ -442,7 +479,28 @@ def run_ours(args):
         fwd_bytes = alg_bytes(conv, "fwd", n_rows, e_local, dim)
         step_bytes = alg_bytes(conv, "fwd+bwd", n_rows, e_local, dim)
         staged = e_local <= 128 * max(n_rows, 1)  # abi_common.h: want_staged (mean degree <= 128)
-        fwd_kernel = ("gat_fwd_staged_kernel" if staged else "gat_fwd_kernel") if conv == "gat" else "dot_fwd_kernel"
+        knames = ({"fwd": "gat_fwd_staged_kernel", "bwd_row": "gat_bwd_row_staged_kernel",
+                   "bwd_col": "gat_bwd_col_staged_kernel"} if staged else
+                  {"fwd": "gat_fwd_kernel", "bwd_row": "gat_bwd_row_kernel", "bwd_col": "gat_bwd_col_kernel"}) \
+            if conv == "gat" else {"fwd": "dot_fwd_kernel", "bwd_row": "gt_bwd_row_kernel",
+                                   "bwd_col": "gt_bwd_col_kernel"}
+        fwd_kernel = knames["fwd"]
+        kbytes = kernel_alg_bytes(conv, n_rows, e_local, dim)
+        traffic = {}
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01f_traffic.json")) as fh:
+                traffic = json.load(fh).get(name, {})
+        except Exception:
+            pass
+        kernels = {}
+        for k, ts in kern_ms.items():
+            if ts:
+                t = sum(ts) / len(ts)
+                kernels[knames[k]] = {"ms": t, "algorithmic_bytes": kbytes[k],
+                                      "achieved": kbytes[k] / (t * 1e-3) / 1e9,
+                                      "frac": kbytes[k] / (t * 1e-3) / 1e9 / peak,
+                                      "traffic": (traffic.get(knames[k]) or {}).get("dram_bytes_per_launch")}
+        dominant = max(kernels, key=lambda k: kernels[k]["ms"]) if kernels else None
         line = {
             "metric": METRIC, "value": units / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
@@ -458,10 +516,18 @@ def run_ours(args):
                     "api": "dfgnn_b200.operators.%s (autograd Function) with pinned host operands; "
                            "index formats resident" % ("GTConvFuse_hyper" if conv == "gt" else "GATConvFuse")},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": fwd_kernel, "achieved": fwd_bytes / (fwd_t * 1e-3) / 1e9,
-                         "peak": peak, "unit": "GB/s", "frac": fwd_bytes / (fwd_t * 1e-3) / 1e9 / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel_ms": fwd_t,
-                         "algorithmic_bytes": fwd_bytes,
+            "roofline": {"bound": "hbm",
+                         "kernel": dominant or fwd_kernel,
+                         "achieved": kernels[dominant]["achieved"] if dominant else fwd_bytes / (fwd_t * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s",
+                         "frac": kernels[dominant]["frac"] if dominant else fwd_bytes / (fwd_t * 1e-3) / 1e9 / peak,
+                         "traffic": kernels[dominant]["traffic"] if dominant else None,
+                         "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, "
+                                           "profiles/r01f_traffic.json" if dominant and kernels[dominant]["traffic"] else None,
+                         "peak_source": peak_src,
+                         "kernel_ms": kernels[dominant]["ms"] if dominant else fwd_t,
+                         "algorithmic_bytes": kernels[dominant]["algorithmic_bytes"] if dominant else fwd_bytes,
+                         "kernels": kernels,
                          "step": {"algorithmic_bytes": step_bytes,
                                   "achieved": step_bytes / (ms * 1e-3) / 1e9,
                                   "frac": step_bytes / (ms * 1e-3) / 1e9 / peak}},

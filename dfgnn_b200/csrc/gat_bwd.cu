@@ -5,7 +5,7 @@
 
 using namespace dfgnn;
 
-extern "C" int dfgnn_gat_backward(int m, int n, int nnz, int h, int f, float negative_slope,
+static int gat_backward_impl(int phases, int m, int n, int nnz, int h, int f, float negative_slope,
                                   float attn_drop, const int32_t* row_ptr, const int32_t* col_ind,
                                   const int32_t* col_ptr, const int32_t* row_ind,
                                   const int32_t* permute, const float* edge_max,
@@ -15,6 +15,7 @@ extern "C" int dfgnn_gat_backward(int m, int n, int nnz, int h, int f, float neg
                                   float* grad_attn_row, float* grad_attn_col, float* grad_edge,
                                   void* stream) {
   const char* fn = "dfgnn_gat_backward";
+  if (phases < 1 || phases > 3) { set_error("%s: phases=%d must be 1, 2 or 3", fn, phases); return DFGNN_ERR_INVALID_ARGUMENT; }
   if (int rc = check_common(fn, m, nnz, h, f)) return rc;
   if (n < 0) { set_error("%s: invalid n=%d", fn, n); return DFGNN_ERR_INVALID_ARGUMENT; }
   DFGNN_REQUIRE(row_ptr, fn); DFGNN_REQUIRE(col_ptr, fn);
@@ -47,7 +48,7 @@ extern "C" int dfgnn_gat_backward(int m, int n, int nnz, int h, int f, float neg
     const dim3 grid((m + p.rb - 1) / p.rb, h);
     const dim3 grid_c((n + p.rb_col - 1) / p.rb_col, h);
     ensure_smem(gat_bwd_col_kernel<L, C>, slot_bytes<L::NR, L>());
-    if (m > 0) {
+    if (m > 0 && (phases & 1)) {
       if (staged_r) {
         const size_t sx = stage_x<L>() ? (size_t)p.rb * f * sizeof(float) : 0;
         ensure_smem(gat_bwd_row_staged_kernel<L, StageChunk<L>::kSddmm>, sx, 44 * 1024);
@@ -62,7 +63,7 @@ extern "C" int dfgnn_gat_backward(int m, int n, int nnz, int h, int f, float neg
       rc = check_launch(fn);
       if (rc) return;
     }
-    if (n > 0) {
+    if (n > 0 && (phases & 2)) {
       p.cap = 0;
       if (staged_c) {
         ensure_smem(gat_bwd_col_staged_kernel<L, StageChunk<L>::kSpmm>, slot_bytes<L::NR, L>(), 42 * 1024);
@@ -79,3 +80,33 @@ extern "C" int dfgnn_gat_backward(int m, int n, int nnz, int h, int f, float neg
   });
   return rc;
 }
+
+extern "C" {
+
+int dfgnn_gat_backward(int m, int n, int nnz, int h, int f, float negative_slope, float attn_drop,
+                       const int32_t* row_ptr, const int32_t* col_ind, const int32_t* col_ptr,
+                       const int32_t* row_ind, const int32_t* permute, const float* edge_max,
+                       const float* edge_sum, const float* edge_mask, const float* in_feat,
+                       const float* attn_row, const float* attn_col, const float* grad_out,
+                       float* grad_feat, float* grad_attn_row, float* grad_attn_col, float* grad_edge,
+                       void* stream) {
+  return gat_backward_impl(3, m, n, nnz, h, f, negative_slope, attn_drop, row_ptr, col_ind, col_ptr,
+                           row_ind, permute, edge_max, edge_sum, edge_mask, in_feat, attn_row,
+                           attn_col, grad_out, grad_feat, grad_attn_row, grad_attn_col, grad_edge,
+                           stream);
+}
+
+int dfgnn_gat_backward_phase(int phases, int m, int n, int nnz, int h, int f, float negative_slope,
+                             float attn_drop, const int32_t* row_ptr, const int32_t* col_ind,
+                             const int32_t* col_ptr, const int32_t* row_ind, const int32_t* permute,
+                             const float* edge_max, const float* edge_sum, const float* edge_mask,
+                             const float* in_feat, const float* attn_row, const float* attn_col,
+                             const float* grad_out, float* grad_feat, float* grad_attn_row,
+                             float* grad_attn_col, float* grad_edge, void* stream) {
+  return gat_backward_impl(phases, m, n, nnz, h, f, negative_slope, attn_drop, row_ptr, col_ind,
+                           col_ptr, row_ind, permute, edge_max, edge_sum, edge_mask, in_feat,
+                           attn_row, attn_col, grad_out, grad_feat, grad_attn_row, grad_attn_col,
+                           grad_edge, stream);
+}
+
+}  // extern "C"

@@ -4,7 +4,7 @@
 
 using namespace dfgnn;
 
-extern "C" int dfgnn_gt_backward(int m, int n, int nnz, int h, int f, const int32_t* row_ptr,
+static int gt_backward_impl(int phases, int m, int n, int nnz, int h, int f, const int32_t* row_ptr,
                                  const int32_t* col_ind, const int32_t* /*rows*/,
                                  const float* /*val*/, const int32_t* col_ptr,
                                  const int32_t* row_ind, const int32_t* val_idx,
@@ -13,6 +13,7 @@ extern "C" int dfgnn_gt_backward(int m, int n, int nnz, int h, int f, const int3
                                  float* grad_Q, float* grad_K, float* grad_V, float* grad_edge,
                                  void* stream) {
   const char* fn = "dfgnn_gt_backward";
+  if (phases < 1 || phases > 3) { set_error("%s: phases=%d must be 1, 2 or 3", fn, phases); return DFGNN_ERR_INVALID_ARGUMENT; }
   if (int rc = check_common(fn, m, nnz, h, f)) return rc;
   if (n < 0) { set_error("%s: invalid n=%d", fn, n); return DFGNN_ERR_INVALID_ARGUMENT; }
   DFGNN_REQUIRE(row_ptr, fn); DFGNN_REQUIRE(col_ptr, fn);
@@ -37,15 +38,41 @@ extern "C" int dfgnn_gt_backward(int m, int n, int nnz, int h, int f, const int3
     const size_t smem = slot_bytes<2 * L::NR, L>();
     ensure_smem(gt_bwd_row_kernel<L, C>, smem);
     ensure_smem(gt_bwd_col_kernel<L, C>, smem);
-    if (m > 0) {
+    if (m > 0 && (phases & 1)) {
       gt_bwd_row_kernel<L, C><<<grid, kNW * 32, smem, st>>>(p);
       rc = check_launch(fn);
       if (rc) return;
     }
-    if (n > 0) {
+    if (n > 0 && (phases & 2)) {
       gt_bwd_col_kernel<L, C><<<grid_c, kNW * 32, smem, st>>>(p);
       rc = check_launch(fn);
     }
   }, long_rows(m, nnz));
   return rc;
 }
+
+extern "C" {
+
+int dfgnn_gt_backward(int m, int n, int nnz, int h, int f, const int32_t* row_ptr,
+                      const int32_t* col_ind, const int32_t* rows, const float* val,
+                      const int32_t* col_ptr, const int32_t* row_ind, const int32_t* val_idx,
+                      int smem_consume, const float* Q, const float* K, const float* V,
+                      const float* attn_edge, const float* grad_out, float* grad_Q, float* grad_K,
+                      float* grad_V, float* grad_edge, void* stream) {
+  return gt_backward_impl(3, m, n, nnz, h, f, row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx,
+                          smem_consume, Q, K, V, attn_edge, grad_out, grad_Q, grad_K, grad_V,
+                          grad_edge, stream);
+}
+
+int dfgnn_gt_backward_phase(int phases, int m, int n, int nnz, int h, int f, const int32_t* row_ptr,
+                            const int32_t* col_ind, const int32_t* rows, const float* val,
+                            const int32_t* col_ptr, const int32_t* row_ind, const int32_t* val_idx,
+                            int smem_consume, const float* Q, const float* K, const float* V,
+                            const float* attn_edge, const float* grad_out, float* grad_Q,
+                            float* grad_K, float* grad_V, float* grad_edge, void* stream) {
+  return gt_backward_impl(phases, m, n, nnz, h, f, row_ptr, col_ind, rows, val, col_ptr, row_ind,
+                          val_idx, smem_consume, Q, K, V, attn_edge, grad_out, grad_Q, grad_K, grad_V,
+                          grad_edge, stream);
+}
+
+}  // extern "C"

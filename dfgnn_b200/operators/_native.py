@@ -86,8 +86,11 @@ def gt_hyper_forward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, sme
 
 
 def gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem_consume,
-                Q, K, V, attn_edge, grad) -> List[torch.Tensor]:
-    """fused_gtconv.cpp:125-172 -> [grad_Q, grad_K, grad_V]."""
+                Q, K, V, attn_edge, grad, *, _phases: int = 3, _buffers=None) -> List[torch.Tensor]:
+    """fused_gtconv.cpp:125-172 -> [grad_Q, grad_K, grad_V].
+    Keyword-only extras (no reference counterpart, used for per-kernel timing): ``_phases``
+    1 = row-side kernel only, 2 = column-side only, 3 = both; ``_buffers`` = (gq, gk, gv, scratch)
+    from an earlier call, reused instead of allocating."""
     fn = "gt_backward"
     m, nnz, h, f = _check_gt(fn, row_ptr, col_ind, Q, K, V, rows, val)
     _chk("col_ptr", col_ptr, torch.int32)
@@ -103,13 +106,18 @@ def gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem_con
     if K.shape[0] != n:
         raise RuntimeError(f"{fn}: col_ptr describes {n} columns but K has {K.shape[0]} rows")
     with torch.cuda.device(Q.device):
-        gq, gk, gv = torch.empty_like(Q), torch.empty_like(K), torch.empty_like(V)
-        ge = torch.empty((h, nnz, 2), dtype=torch.float32, device=Q.device)  # scratch {dS, p}
-        rc = _lib.lib().dfgnn_gt_backward(
-            m, n, nnz, h, f, _ptr(row_ptr), _ptr(col_ind), _ptr(rows), _ptr(val), _ptr(col_ptr),
+        if _buffers is not None:
+            gq, gk, gv, ge = _buffers
+        else:
+            gq, gk, gv = torch.empty_like(Q), torch.empty_like(K), torch.empty_like(V)
+            ge = torch.empty((h, nnz, 2), dtype=torch.float32, device=Q.device)  # scratch {dS, p}
+        rc = _lib.lib().dfgnn_gt_backward_phase(
+            int(_phases), m, n, nnz, h, f, _ptr(row_ptr), _ptr(col_ind), _ptr(rows), _ptr(val), _ptr(col_ptr),
             _ptr(row_ind), _ptr(val_idx), int(smem_consume), _ptr(Q), _ptr(K), _ptr(V),
             _ptr(attn_edge), _ptr(grad), _ptr(gq), _ptr(gk), _ptr(gv), _ptr(ge), _stream(Q))
     _lib.check(rc, fn)
+    if _buffers is None and _phases != 3:
+        return [gq, gk, gv, ge]
     return [gq, gk, gv]
 
 
@@ -231,8 +239,10 @@ def gat_forward(attn_row, attn_col, row_ptr, col_ind, negative_slope, in_feat, a
 
 
 def gat_backward(negative_slope, attn_drop, row_ptr, col_ind, col_ptr, row_ind, permute,
-                 edge_max, edge_sum, edge_mask, in_feat, attn_row, attn_col, grad):
-    """fused_gatconv.cpp:291-353 -> [grad_feat, grad_attn_row, grad_attn_col]."""
+                 edge_max, edge_sum, edge_mask, in_feat, attn_row, attn_col, grad, *,
+                 _phases: int = 3, _buffers=None):
+    """fused_gatconv.cpp:291-353 -> [grad_feat, grad_attn_row, grad_attn_col].
+    ``_phases`` / ``_buffers``: see gt_backward (buffers = (gf, gr, gc, scratch))."""
     fn = "gat_backward"
     m, nnz, h, f = _check_gat(fn, attn_row, attn_col, row_ptr, col_ind, in_feat)
     for n, t in (("col_ptr", col_ptr), ("row_ind", row_ind), ("permute", permute)):
@@ -247,16 +257,21 @@ def gat_backward(negative_slope, attn_drop, row_ptr, col_ind, col_ptr, row_ind, 
         raise RuntimeError(f"{fn}: CSC arrays do not match the CSR")
     dev = in_feat.device
     with torch.cuda.device(dev):
-        gf = torch.empty_like(in_feat)
-        gr = torch.empty((m, h), dtype=torch.float32, device=dev)
-        gc = torch.empty((n, h), dtype=torch.float32, device=dev)
-        ge = torch.empty((nnz, h, 2), dtype=torch.float32, device=dev)  # scratch {de, keep-scaled p}
-        rc = _lib.lib().dfgnn_gat_backward(
-            m, n, nnz, h, f, float(negative_slope), float(attn_drop), _ptr(row_ptr), _ptr(col_ind),
+        if _buffers is not None:
+            gf, gr, gc, ge = _buffers
+        else:
+            gf = torch.empty_like(in_feat)
+            gr = torch.empty((m, h), dtype=torch.float32, device=dev)
+            gc = torch.empty((n, h), dtype=torch.float32, device=dev)
+            ge = torch.empty((nnz, h, 2), dtype=torch.float32, device=dev)  # scratch {de, keep-scaled p}
+        rc = _lib.lib().dfgnn_gat_backward_phase(
+            int(_phases), m, n, nnz, h, f, float(negative_slope), float(attn_drop), _ptr(row_ptr), _ptr(col_ind),
             _ptr(col_ptr), _ptr(row_ind), _ptr(permute), _ptr(edge_max), _ptr(edge_sum),
             _ptr(edge_mask), _ptr(in_feat), _ptr(attn_row), _ptr(attn_col), _ptr(grad), _ptr(gf),
             _ptr(gr), _ptr(gc), _ptr(ge), _stream(in_feat))
     _lib.check(rc, fn)
+    if _buffers is None and _phases != 3:
+        return [gf, gr, gc, ge]
     return [gf, gr, gc]
 
 

@@ -124,6 +124,19 @@ int dfgnn_gt_backward(int m, int n, int nnz, int h, int f, const int32_t *row_pt
                       float *grad_K, float *grad_V, float *grad_edge, void *stream);
 
 /*
+ * The same with the two kernels of the backward selectable: phases = 1 row side only
+ * (grad_Q and the {dS, p} scratch), 2 column side only (grad_K, grad_V; needs the scratch
+ * a row-side call left), 3 both.  For per-kernel timing; no reference counterpart.
+ */
+int dfgnn_gt_backward_phase(int phases, int m, int n, int nnz, int h, int f,
+                            const int32_t *row_ptr, const int32_t *col_ind, const int32_t *rows,
+                            const float *val, const int32_t *col_ptr, const int32_t *row_ind,
+                            const int32_t *val_idx, int smem_consume, const float *Q,
+                            const float *K, const float *V, const float *attn_edge,
+                            const float *grad_out, float *grad_Q, float *grad_K, float *grad_V,
+                            float *grad_edge, void *stream);
+
+/*
  * Inference entry points; all compute the same function, the name selects the
  * schedule heuristics.  Replace gt_hyper_inference (fused_gtconv.cpp:278-314),
  * gt_softmax_inference (l.316-352), gt_softmax_gm_inference (l.354-389),
@@ -200,6 +213,17 @@ int dfgnn_gat_backward(int m, int n, int nnz, int h, int f, float negative_slope
                        const float *attn_row, const float *attn_col, const float *grad_out,
                        float *grad_feat, float *grad_attn_row, float *grad_attn_col,
                        float *grad_edge, void *stream);
+
+/* Row side (1: grad_attn_row + scratch), column side (2: grad_feat, grad_attn_col) or both (3). */
+int dfgnn_gat_backward_phase(int phases, int m, int n, int nnz, int h, int f,
+                             float negative_slope, float attn_drop, const int32_t *row_ptr,
+                             const int32_t *col_ind, const int32_t *col_ptr,
+                             const int32_t *row_ind, const int32_t *permute,
+                             const float *edge_max, const float *edge_sum,
+                             const float *edge_mask, const float *in_feat, const float *attn_row,
+                             const float *attn_col, const float *grad_out, float *grad_feat,
+                             float *grad_attn_row, float *grad_attn_col, float *grad_edge,
+                             void *stream);
 
 /*
  * Inference entry points (one function, several schedule names).  Replace

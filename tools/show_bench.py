@@ -8,4 +8,4 @@ for tag in sys.argv[2:]:
     r=d["roofline"]
     ref=d.get("gpu_reference") or {}
     refs="; ".join(f"{k.split(' (')[0]} {v['ms']:.3f}" for k,v in ref.items() if isinstance(v,dict) and 'ms' in v)
-    print(f"{w:11s} step {d['ms_per_step']:.4f} ms (frac {r['step']['frac']:.2f})  fwd {r['kernel_ms']:.4f} ms (frac {r['frac']:.2f})  e2e {d['e2e']['ms_per_step']:.2f} ms | ref: {refs}")
+    print(f"{w:11s} step {d['ms_per_step']:.4f} ms (frac {r['step']['frac']:.2f})  {r['kernel'][:22]} {r['kernel_ms']:.4f} ms (frac {r['frac']:.2f})  e2e {d['e2e']['ms_per_step']:.2f} ms | ref: {refs}")
