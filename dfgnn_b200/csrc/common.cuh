@@ -181,6 +181,26 @@ __device__ __forceinline__ T group_bcast(T v, int src) {
   return __shfl_sync(kFull, v, src, LPR);
 }
 
+// Group totals of FOUR per-lane partial sums with 2 + log2(LPR / 2) shuffles instead of
+// 4 * log2(LPR): lanes swap halves of their values (butterfly on the values, not the lanes).
+// Returns the total of d[perm4(gl)], perm4(gl) = 2 * (gl & 1) + ((gl >> 1) & 1).
+__device__ __forceinline__ int perm4(int gl) { return ((gl & 1) << 1) | ((gl >> 1) & 1); }
+template <int LPR>
+__device__ __forceinline__ float reduce4_transposed(const float (&d)[4], int gl) {
+  static_assert(LPR >= 4, "needs at least four lanes per group");
+  const bool o1 = gl & 1, o2 = gl & 2;
+  const float s0 = o1 ? d[0] : d[2], s1 = o1 ? d[1] : d[3];
+  float k0 = o1 ? d[2] : d[0], k1 = o1 ? d[3] : d[1];
+  k0 += __shfl_xor_sync(kFull, s0, 1);
+  k1 += __shfl_xor_sync(kFull, s1, 1);
+  const float s = o2 ? k0 : k1;
+  float k = o2 ? k1 : k0;
+  k += __shfl_xor_sync(kFull, s, 2);
+#pragma unroll
+  for (int off = 4; off < LPR; off <<= 1) k += __shfl_xor_sync(kFull, k, off);
+  return k;
+}
+
 __device__ __forceinline__ float warp_sum(float v) { return group_sum<32>(v); }
 
 __device__ __forceinline__ float warp_max(float v) {
