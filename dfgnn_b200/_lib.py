@@ -40,7 +40,7 @@ _SIGNATURES = {
     "dfgnn_launch_count": (c_uint64, []),
     "dfgnn_format_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "dfgnn_coo_to_csr": (c_int, [c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
-    "dfgnn_csr_to_csc": (c_int, [c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "dfgnn_csr_to_csc": (c_int, [c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "dfgnn_gt_hyper_forward": (c_int, [c_int] * 4 + [_P] * 7 + [c_int] + [_P] * 5 + [_P]),
     "dfgnn_gt_backward": (c_int, [c_int] * 5 + [_P] * 7 + [c_int] + [_P] * 9 + [_P]),
     "dfgnn_gt_backward_phase": (c_int, [c_int] * 6 + [_P] * 7 + [c_int] + [_P] * 9 + [_P]),

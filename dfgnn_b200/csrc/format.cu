@@ -18,15 +18,26 @@ static inline int key_bits(int64_t n) {
   return b;
 }
 
+// Validates the endpoints, builds the sort keys, and -- speculating that the COO is already
+// sorted by row (what DGL graphs and batched graphs usually are) -- writes the CSR arrays of
+// that case directly.  flags[0] = an endpoint is out of range, flags[1] = rows are not
+// non-decreasing (the radix sort then overwrites the speculative output).
 __global__ void coo_keys_kernel(int64_t nnz, int64_t n, int64_t n_cols, const int64_t* __restrict__ row,
                                 const int64_t* __restrict__ col, int32_t* __restrict__ keys,
-                                int32_t* __restrict__ ids, int* __restrict__ bad) {
+                                int32_t* __restrict__ ids, int32_t* __restrict__ rows,
+                                int32_t* __restrict__ col_ind, int32_t* __restrict__ perm,
+                                float* __restrict__ val, int* __restrict__ flags) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nnz) return;
   const int64_t r = row[i], c = col[i];
-  if (r < 0 || r >= n || c < 0 || c >= n_cols) { *bad = 1; keys[i] = 0; }
+  if (r < 0 || r >= n || c < 0 || c >= n_cols) { flags[0] = 1; keys[i] = 0; }
   else keys[i] = (int32_t)r;
   ids[i] = (int32_t)i;
+  if (i > 0 && row[i - 1] > r) flags[1] = 1;
+  rows[i] = (int32_t)r;
+  col_ind[i] = (int32_t)c;
+  if (perm) perm[i] = (int32_t)i;
+  if (val) val[i] = 1.0f;
 }
 
 __global__ void iota_kernel(int64_t nnz, int32_t* __restrict__ ids) {
@@ -51,6 +62,13 @@ __global__ void seg_ptr_kernel(int64_t nnz, int64_t n, const int32_t* __restrict
   const int64_t prev = p > 0 ? sorted[p - 1] : -1;
   const int64_t cur = p < nnz ? sorted[p] : n;
   for (int64_t s = prev + 1; s <= cur; ++s) ptr[s] = (int32_t)p;
+}
+
+// row_ind[p] = rows[val_idx[p]] when the caller has the expanded row ids of the CSR
+__global__ void row_gather_kernel(int64_t nnz, const int32_t* __restrict__ rows,
+                                  const int32_t* __restrict__ val_idx, int32_t* __restrict__ row_ind) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nnz) row_ind[i] = __ldg(rows + val_idx[i]);
 }
 
 // row_ind[p] = the row whose CSR range contains position val_idx[p]
@@ -125,31 +143,34 @@ int dfgnn_coo_to_csr(int64_t n, int64_t n_cols, int64_t nnz, const int64_t* row,
   void* temp = ws + 3 * e + 256;
   size_t temp_bytes = workspace_bytes - (3 * e + 256);
 
-  cudaMemsetAsync(bad, 0, sizeof(int), st);
-  coo_keys_kernel<<<blocks(nnz), 256, 0, st>>>(nnz, n, n_cols, row, col, keys_in, ids_in, bad);
+  cudaMemsetAsync(bad, 0, 2 * sizeof(int), st);
+  coo_keys_kernel<<<blocks(nnz), 256, 0, st>>>(nnz, n, n_cols, row, col, keys_in, ids_in, rows, col_ind,
+                                               perm_buf, val, bad);
   if (int rc = check_launch(fn)) return rc;
-  cudaError_t err = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, rows, ids_in,
-                                                    perm_buf, (int)nnz, 0, bits, st);
-  launch_counter().fetch_add(1);
-  if (err != cudaSuccess) { set_error("%s: radix sort: %s", fn, cudaGetErrorString(err)); return (int)err; }
-  gather_col_kernel<<<blocks(nnz), 256, 0, st>>>(nnz, col, perm_buf, col_ind, val);
-  if (int rc = check_launch(fn)) return rc;
-  seg_ptr_kernel<<<blocks(nnz + 1), 256, 0, st>>>(nnz, n, rows, row_ptr);
-  if (int rc = check_launch(fn)) return rc;
-  int h_bad = 0;  // index validation needs one small readback (format construction is not the timed conv)
-  err = cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, st);
+  // one small readback: index validation, and whether the input still has to be sorted
+  int h_flags[2] = {0, 0};
+  cudaError_t err = cudaMemcpyAsync(h_flags, bad, 2 * sizeof(int), cudaMemcpyDeviceToHost, st);
   if (err == cudaSuccess) err = cudaStreamSynchronize(st);
   if (err != cudaSuccess) { set_error("%s: %s", fn, cudaGetErrorString(err)); return (int)err; }
-  if (h_bad) {
+  if (h_flags[0]) {
     set_error("%s: edge endpoint outside [0, %lld) x [0, %lld)", fn, (long long)n, (long long)n_cols);
     return DFGNN_ERR_INVALID_ARGUMENT;
   }
-  return DFGNN_OK;
+  if (h_flags[1]) {  // not sorted by row: stable radix sort, then gather the columns
+    err = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, rows, ids_in, perm_buf, (int)nnz, 0,
+                                          bits, st);
+    launch_counter().fetch_add(1);
+    if (err != cudaSuccess) { set_error("%s: radix sort: %s", fn, cudaGetErrorString(err)); return (int)err; }
+    gather_col_kernel<<<blocks(nnz), 256, 0, st>>>(nnz, col, perm_buf, col_ind, val);
+    if (int rc = check_launch(fn)) return rc;
+  }
+  seg_ptr_kernel<<<blocks(nnz + 1), 256, 0, st>>>(nnz, n, rows, row_ptr);
+  return check_launch(fn);
 }
 
 int dfgnn_csr_to_csc(int64_t n_rows, int64_t n, int64_t nnz, const int32_t* row_ptr, const int32_t* col_ind,
-                     int32_t* col_ptr, int32_t* row_ind, int32_t* val_idx, void* workspace,
-                     size_t workspace_bytes, void* stream) {
+                     const int32_t* rows, int32_t* col_ptr, int32_t* row_ind, int32_t* val_idx,
+                     void* workspace, size_t workspace_bytes, void* stream) {
   const char* fn = "dfgnn_csr_to_csc";
   if (n < 0 || n_rows < 0 || nnz < 0 || n > INT32_MAX || n_rows > INT32_MAX || nnz > INT32_MAX) {
     set_error("%s: n_rows=%lld n_cols=%lld nnz=%lld out of int32 range", fn, (long long)n_rows,
@@ -186,7 +207,8 @@ int dfgnn_csr_to_csc(int64_t n_rows, int64_t n, int64_t nnz, const int32_t* row_
   if (err != cudaSuccess) { set_error("%s: radix sort: %s", fn, cudaGetErrorString(err)); return (int)err; }
   seg_ptr_kernel<<<blocks(nnz + 1), 256, 0, st>>>(nnz, n, keys_out, col_ptr);
   if (int rc = check_launch(fn)) return rc;
-  row_of_kernel<<<blocks(nnz), 256, 0, st>>>(nnz, n_rows, row_ptr, val_idx, row_ind);
+  if (rows) row_gather_kernel<<<blocks(nnz), 256, 0, st>>>(nnz, rows, val_idx, row_ind);
+  else row_of_kernel<<<blocks(nnz), 256, 0, st>>>(nnz, n_rows, row_ptr, val_idx, row_ind);
   return check_launch(fn);
 }
 

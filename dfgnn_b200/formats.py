@@ -76,9 +76,11 @@ def coo_to_csr(row: torch.Tensor, col: torch.Tensor, n: int, n_cols: int = None)
     return row_ptr, col_ind, rows, perm, val
 
 
-def csr_to_csc(row_ptr: torch.Tensor, col_ind: torch.Tensor, n_cols: int = None):
+def csr_to_csc(row_ptr: torch.Tensor, col_ind: torch.Tensor, n_cols: int = None,
+               rows: torch.Tensor = None):
     """-> col_ptr[n_cols+1], row_ind[E], val_idx[E] (all int32); val_idx = CSC pos -> CSR pos.
-    n_cols defaults to the number of rows (square adjacency)."""
+    n_cols defaults to the number of rows (square adjacency).  ``rows`` (the expanded row ids
+    that coo_to_csr returns) is optional: with it row_ind is a gather instead of a search."""
     _require_cuda(row_ptr, "row_ptr")
     _require_cuda(col_ind, "col_ind")
     if row_ptr.dtype != torch.int32 or col_ind.dtype != torch.int32:
@@ -96,7 +98,10 @@ def csr_to_csc(row_ptr: torch.Tensor, col_ind: torch.Tensor, n_cols: int = None)
         val_idx = torch.empty(nnz, dtype=torch.int32, device=dev)
         ws_bytes = int(L.dfgnn_format_workspace_bytes(max(n, n_rows), nnz))
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        if rows is not None and (rows.dtype != torch.int32 or rows.numel() != nnz or not rows.is_contiguous()):
+            raise RuntimeError("rows must be a contiguous int32 tensor of nnz entries")
         rc = L.dfgnn_csr_to_csc(n_rows, n, nnz, row_ptr.data_ptr(), col_ind.data_ptr() if nnz else None,
+                                rows.data_ptr() if (rows is not None and nnz) else None,
                                 col_ptr.data_ptr(), row_ind.data_ptr() if nnz else None,
                                 val_idx.data_ptr() if nnz else None, ws.data_ptr(), ws_bytes,
                                 torch.cuda.current_stream(dev).cuda_stream)

@@ -55,7 +55,7 @@ def preprocess_Hyper_fw_bw(g, fused=True):
     if not fused:
         return A, None, None, None, None, None, None, None, None
     row_ptr, col_ind, rows, _, val = coo_to_csr(A.row, A.col, A.shape[0], A.shape[1])
-    col_ptr, row_ind, val_idx = csr_to_csc(row_ptr, col_ind, A.shape[1])
+    col_ptr, row_ind, val_idx = csr_to_csc(row_ptr, col_ind, A.shape[1], rows)
     return A, rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx, _smem(max_neigh, 8)
 
 
@@ -64,8 +64,8 @@ def preprocess_gat_fw_bw(g):
     DFGNN/script/train/train_gatconv.py:119-136 builds with scipy).
     -> (row_ptr, col_ind, col_ptr, row_ind, permute)."""
     A, _ = g_to_SPmatrix(g)
-    row_ptr, col_ind, _, _, _ = coo_to_csr(A.row, A.col, A.shape[0], A.shape[1])
-    col_ptr, row_ind, permute = csr_to_csc(row_ptr, col_ind, A.shape[1])
+    row_ptr, col_ind, rows, _, _ = coo_to_csr(A.row, A.col, A.shape[0], A.shape[1])
+    col_ptr, row_ind, permute = csr_to_csc(row_ptr, col_ind, A.shape[1], rows)
     return row_ptr, col_ind, col_ptr, row_ind, permute
 
 

@@ -74,6 +74,8 @@ size_t dfgnn_format_workspace_bytes(int64_t n, int64_t nnz); /* n = max(n_rows, 
  *   row_ptr  : [n_rows+1]; col_ind, rows : [nnz]
  *   perm     : [nnz] sorted position -> input edge id (A.csr()'s value_indices), may be NULL
  *   val      : [nnz] float32, filled with 1.0f (A.val[val_idx] of an unweighted graph), may be NULL
+ * A COO that is already sorted by row (the usual case) skips the sort.  The call synchronises
+ * the stream once (index validation).
  */
 int dfgnn_coo_to_csr(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t *row,
                      const int64_t *col,
@@ -87,7 +89,7 @@ int dfgnn_coo_to_csr(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t 
  * DFGNN/script/train/train_gatconv.py:119-136.  Stable by column.
  */
 int dfgnn_csr_to_csc(int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t *row_ptr,
-                     const int32_t *col_ind,
+                     const int32_t *col_ind, const int32_t *rows /* [nnz] from dfgnn_coo_to_csr, or NULL */,
                      int32_t *col_ptr, int32_t *row_ind, int32_t *val_idx, void *workspace,
                      size_t workspace_bytes, void *stream);
 

@@ -53,6 +53,9 @@ def test_csr_csc_bit_exact(cuda, name, shuffle):
     _eq("col_ptr", d_cp, cp)
     _eq("row_ind", d_ri, ri)
     _eq("val_idx", d_vi, vi)
+    # the same with the expanded row ids handed over (row_ind by gather instead of search)
+    for a, b in zip(formats.csr_to_csc(d_rp, d_ci, None, d_rows), (d_cp, d_ri, d_vi)):
+        assert torch.equal(a, b)
     # second oracle: scipy (train_gatconv.py:119-136 builds `permute` exactly like this)
     if len(ci):
         A = sp.csr_matrix((np.arange(len(ci), dtype=np.int32), ci, rp), shape=(n, n)).tocsc()
