@@ -504,7 +504,7 @@ def run_ours(args):
             peak, peak_src = hbm_peak()
             fwd_bytes = alg_bytes(conv, "fwd", n_rows, e_local, dim)
             step_bytes = alg_bytes(conv, "fwd+bwd", n_rows, e_local, dim)
-            staged = e_local <= 128 * max(n_rows, 1)  # abi_common.h: want_staged (mean degree <= 128)
+            staged = e_local <= 16 * max(n_rows, 1)  # abi_common.h: want_staged (mean degree <= 16)
             knames = ({"fwd": "gat_fwd_staged_kernel", "bwd_row": "gat_bwd_row_staged_kernel",
                        "bwd_col": "gat_bwd_col_staged_kernel"} if staged else
                       {"fwd": "gat_fwd_kernel", "bwd_row": "gat_bwd_row_kernel", "bwd_col": "gat_bwd_col_kernel"}) \

@@ -78,9 +78,12 @@ inline int pick_rb(int m, int nnz, int G) {
 }
 
 // ---- staged-tile kernels (staged.cuh): short rows ------------------------------------
-// Used when even the smallest tile (8 rows) averages at most half the staging capacity;
-// rows per CTA then aim at ~kStageCap/2 entries, keeping >= 2 CTAs per SM in the grid.
+// Used (GAT kernels) when the mean degree is at most kStagedMaxDegree: measured crossover on
+// B200 with 200k-node log-normal graphs, f = 64 / 128 -- staged wins at mean degree 10 and 16
+// (by 8 % / 0-1 %), the row-block kernels win from 24 up (PATTERN-shaped, degree 51: by 1.5-1.8x).
+// Rows per CTA aim at ~kStageCap/2 entries, keeping >= 2 CTAs per SM in the grid.
 // DFGNN_B200_SCHEDULE=rowblock|staged overrides the choice (developer / test knob).
+constexpr double kStagedMaxDegree = 16.0;
 inline int schedule_override() {
   static const int v = [] {
     const char* e = getenv("DFGNN_B200_SCHEDULE");
@@ -92,7 +95,7 @@ inline int schedule_override() {
 inline bool want_staged(int m, int nnz) {
   const int o = schedule_override();
   if (o) return o == 2;
-  return m > 0 && (double)nnz / (double)m * 8.0 <= kStageCap / 2;
+  return m > 0 && (double)nnz / (double)m <= kStagedMaxDegree;
 }
 #ifndef DFGNN_STAGE_TARGET
 #define DFGNN_STAGE_TARGET (kStageCap / 2)

@@ -35,6 +35,8 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--tag", default=os.environ.get("DFGNN_B200_LIB", "default"))
     ap.add_argument("--reddit-scale", type=float, default=1.0)
+    ap.add_argument("--dim", type=int, default=0, help="override the feature width of the workloads")
+    ap.add_argument("--conv", default="", help="override the conv (gt | gat)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
@@ -42,8 +44,17 @@ def main():
     summary = {"tag": args.tag}
 
     for name in args.workloads.split(","):
-        conv, dim, fn, kw, fmt, cfg = B.WORKLOADS[name]
-        if name == "reddit-gt" and args.reddit_scale != 1.0:
+        if name.startswith("rand:"):  # rand:<mean degree> -- 200k-node full graph, log-normal degrees
+            deg = float(name.split(":")[1])
+            conv, dim, fn, kw, fmt, cfg = "gat", 64, None, {}, "softmax", -1
+            B.SEEDS[name] = 77
+        else:
+            conv, dim, fn, kw, fmt, cfg = B.WORKLOADS[name]
+        dim = args.dim or dim
+        conv = args.conv or conv
+        if name.startswith("rand:"):
+            g = graphs.full_graph(200000, int(200000 * deg), deg, 0.4 * deg, 1, int(4 * deg), 77, name)
+        elif name == "reddit-gt" and args.reddit_scale != 1.0:
             g = graphs.reddit_like(args.reddit_scale)
         else:
             g = B.build_graph(name)
