@@ -179,6 +179,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm runs on rank 0 alone and
+    # may use all host cores (libgomp reads the variable when the oracle library is loaded)
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     name = args.workload
     # bounded sample: the big workloads are shrunk so that K steps finish in minutes
     scale = {"reddit-gt": 0.05}.get(name, 1.0)
@@ -593,6 +596,7 @@ def run_ours(args):
 
 def cpu_baseline(name, g_full):
     cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     if name == "reddit-gt":
         from dfgnn_b200 import graphs
         g = graphs.reddit_like(0.05)
