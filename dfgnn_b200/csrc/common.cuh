@@ -229,13 +229,6 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 __device__ __forceinline__ float fast_exp(float x) { return fast_exp2(x * kLog2e); }
-// Fire-and-forget pull of the 128-byte lines of one feature row into L2 (no register, no
-// scoreboard): the staged kernels issue it for every neighbour row while the per-row
-// passes run, so that the gathers of the aggregation phase find the rows in L2.
-__device__ __forceinline__ void prefetch_row_l2(const char* row, int row_bytes) {
-  for (int o = 0; o < row_bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
-}
-
 // lets the next kernel on the stream start early if it was launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization (abi_common.h: launch_overlapped)
 __device__ __forceinline__ void allow_dependent_launch() {

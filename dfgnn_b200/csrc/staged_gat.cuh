@@ -81,20 +81,20 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16
     float acv[kEPT];
 #pragma unroll
     for (int k = 0; k < kEPT; ++k) {
+      if (k * (kNW * 32) >= ne) break;  // uniform: no entry of the tile in this slot
       const int i = threadIdx.x + k * (kNW * 32);
       cols[k] = i < ne ? __ldg(colp + i) : 0;
     }
     if (threadIdx.x < b.nseg) s_ar[threadIdx.x] = __ldg(p.ar + (size_t)(b.seg_lb + threadIdx.x) * h + hid);
 #pragma unroll
     for (int k = 0; k < kEPT; ++k) {
+      if (k * (kNW * 32) >= ne) break;  // uniform: no entry of the tile in this slot
       const int i = threadIdx.x + k * (kNW * 32);
       acv[k] = i < ne ? __ldg(acb + (size_t)(unsigned)cols[k] * (unsigned)h) : 0.f;
-#ifndef DFGNN_NO_PREFETCH
-      if (i < ne) prefetch_row_l2(reinterpret_cast<const char*>(p.feat + ((size_t)cols[k] * h + hid) * f), f * 4);
-#endif
     }
 #pragma unroll
     for (int k = 0; k < kEPT; ++k) {
+      if (k * (kNW * 32) >= ne) break;  // uniform: no entry of the tile in this slot
       const int i = threadIdx.x + k * (kNW * 32);
       if (i < ne) { Ent1 en; en.idx = cols[k]; en.w = acv[k]; s_e[i] = en; }
     }
@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16
     float acv[kEPT], kmv[kEPT];
 #pragma unroll
     for (int k = 0; k < kEPT; ++k) {
+      if (k * (kNW * 32) >= ne) break;  // uniform: no entry of the tile in this slot
       const int i = threadIdx.x + k * (kNW * 32);
       cols[k] = i < ne ? __ldg(colp + i) : 0;
       kmv[k] = 1.f;  // keep_e / (1 - drop)
@@ -219,14 +220,13 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16
     }
 #pragma unroll
     for (int k = 0; k < kEPT; ++k) {
+      if (k * (kNW * 32) >= ne) break;  // uniform: no entry of the tile in this slot
       const int i = threadIdx.x + k * (kNW * 32);
       acv[k] = i < ne ? __ldg(acb + (size_t)(unsigned)cols[k] * (unsigned)h) : 0.f;
-#ifndef DFGNN_NO_PREFETCH
-      if (i < ne) prefetch_row_l2(reinterpret_cast<const char*>(p.feat + ((size_t)cols[k] * h + hid) * f), f * 4);
-#endif
     }
 #pragma unroll
     for (int k = 0; k < kEPT; ++k) {
+      if (k * (kNW * 32) >= ne) break;  // uniform: no entry of the tile in this slot
       const int i = threadIdx.x + k * (kNW * 32);
       if (i < ne) { Ent2 en; en.idx = cols[k]; en.w = acv[k]; en.w1 = 0.f; en.aux = kmv[k]; s_e[i] = en; }
     }
@@ -323,6 +323,7 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16
     int rid[kEPT], eid[kEPT];
 #pragma unroll
     for (int k = 0; k < kEPT; ++k) {
+      if (k * (kNW * 32) >= ne) break;  // uniform: no entry of the tile in this slot
       const int i = threadIdx.x + k * (kNW * 32);
       rid[k] = i < ne ? __ldg(p.row_ind + b.E0 + i) : 0;
       eid[k] = i < ne ? __ldg(p.permute + b.E0 + i) : 0;
@@ -330,14 +331,13 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16
     float2 dp[kEPT];
 #pragma unroll
     for (int k = 0; k < kEPT; ++k) {
+      if (k * (kNW * 32) >= ne) break;  // uniform: no entry of the tile in this slot
       const int i = threadIdx.x + k * (kNW * 32);
       dp[k] = i < ne ? __ldg(scratch + (size_t)eid[k] * h + hid) : make_float2(0.f, 0.f);
-#ifndef DFGNN_NO_PREFETCH
-      if (i < ne) prefetch_row_l2(reinterpret_cast<const char*>(p.dO + ((size_t)rid[k] * h + hid) * f), f * 4);
-#endif
     }
 #pragma unroll
     for (int k = 0; k < kEPT; ++k) {
+      if (k * (kNW * 32) >= ne) break;  // uniform: no entry of the tile in this slot
       const int i = threadIdx.x + k * (kNW * 32);
       if (i < ne) { Ent2 en; en.idx = rid[k]; en.w = dp[k].y; en.w1 = dp[k].x; en.aux = 0.f; s_e[i] = en; }
     }
