@@ -517,7 +517,7 @@ def run_ours(args):
             kbytes = kernel_alg_bytes(conv, n_rows, e_local, dim)
             traffic = {}
             try:
-                with open(os.path.join(ROOT, "profiles", "r01f_traffic.json")) as fh:
+                with open(os.path.join(ROOT, "profiles", "r01i_traffic.json")) as fh:
                     traffic = json.load(fh).get(name, {})
             except Exception:
                 pass
@@ -552,7 +552,7 @@ def run_ours(args):
                              "frac": kernels[dominant]["frac"] if dominant else fwd_bytes / (fwd_t * 1e-3) / 1e9 / peak,
                              "traffic": kernels[dominant]["traffic"] if dominant else None,
                              "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, "
-                                               "profiles/r01f_traffic.json" if dominant and kernels[dominant]["traffic"] else None,
+                                               "profiles/r01i_traffic.json" if dominant and kernels[dominant]["traffic"] else None,
                              "peak_source": peak_src,
                              "kernel_ms": kernels[dominant]["ms"] if dominant else fwd_t,
                              "algorithmic_bytes": kernels[dominant]["algorithmic_bytes"] if dominant else fwd_bytes,
@@ -665,8 +665,8 @@ def time_gpu_reference(name, conv, dim, idx, d_in, flush, steps, e_total):
                 e.record()
                 e.synchronize()
                 ts.append(s.elapsed_time(e))
-            ms = sum(ts) / len(ts)
-            res[label] = {"ms": ms, "edges_x_dim_per_s": e_total * dim / (ms * 1e-3)}
+            ms = sorted(ts)[len(ts) // 2]  # median: gat_forward creates a cuRAND generator per call
+            res[label] = {"ms": ms, "ms_min": min(ts), "edges_x_dim_per_s": e_total * dim / (ms * 1e-3)}
     except Exception as exc:  # the reference kernels abort on launch errors
         res["error"] = repr(exc)[:300]
     return res
