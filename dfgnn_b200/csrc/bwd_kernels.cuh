@@ -373,9 +373,8 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : 16) / kNW) gat_bw
           float ff[C][NR];
 #pragma unroll
           for (int c = 0; c < C; ++c) {
-            const int col = group_bcast<LPR>(my_col, s + c);
-            if (s + c < cnt) L::load(ff[c], ra.at(Fb, col), gl, f);
-            else zero(ff[c]);
+            const int col = group_bcast<LPR>(my_col, s + c < cnt ? s + c : 0);  // beyond cnt: first neighbour, unused
+            L::load(ff[c], ra.at(Fb, col), gl, f);
           }
 #pragma unroll
           for (int c = 0; c < C; ++c) {
@@ -486,10 +485,9 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR * C <= 32 ? 24 : 16) / kNW) g
           float go[C][NR], pc[C];
 #pragma unroll
           for (int c = 0; c < C; ++c) {
-            const int rid = group_bcast<LPR>(my_rid, s + c);
+            const int rid = group_bcast<LPR>(my_rid, s + c < cnt ? s + c : 0);  // beyond cnt: first entry, weight 0
             pc[c] = group_bcast<LPR>(my_p, s + c);
-            if (s + c < cnt) L::load(go[c], ra.at(Gb, rid), gl, f);
-            else zero(go[c]);
+            L::load(go[c], ra.at(Gb, rid), gl, f);
           }
 #pragma unroll
           for (int c = 0; c < C; ++c)

@@ -300,10 +300,9 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : 16) / kNW) gat_fw
           float vv[C][NR], pc[C];
 #pragma unroll
           for (int c = 0; c < C; ++c) {
-            const int col = group_bcast<LPR>(my_col, s + c);
+            const int col = group_bcast<LPR>(my_col, s + c < cnt ? s + c : 0);  // beyond cnt: first neighbour again
             pc[c] = group_bcast<LPR>(pe, s + c);  // 0 beyond cnt
-            if (s + c < cnt) L::load(vv[c], ra.at(Fb, col), gl, f);
-            else zero(vv[c]);
+            L::load(vv[c], ra.at(Fb, col), gl, f);
           }
 #pragma unroll
           for (int c = 0; c < C; ++c)
