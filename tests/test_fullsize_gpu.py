@@ -151,3 +151,60 @@ def test_super_rows_beyond_the_staging_capacity(cuda, conv):
                                     dtype=np.float64)
         for nme, a, b in (("out", out, o64), ("dfeat", gf, rf), ("d attn_row", gr, rr), ("d attn_col", gc, rc)):
             assert_close(nme, a, b)
+
+
+# --------------------------------------------------------------------------- #
+# BASELINE.json sizes against the reference's own CUDA kernels (oracle/_ref,     #
+# compiled unchanged for sm_100a), inside their valid envelope                  #
+# --------------------------------------------------------------------------- #
+from oracle import ref_gpu  # noqa: E402
+
+needs_ref = pytest.mark.skipif(not ref_gpu.available(), reason="oracle/_ref not built")
+
+
+@needs_ref
+def test_gat_arxiv_full_size_vs_reference_kernels(cuda):
+    ref = ref_gpu.fused_gatconv()
+    g = graphs.arxiv_like()
+    n = g.num_nodes()
+    row_ptr, col_ind, col_ptr, row_ind, permute = preprocess_gat_fw_bw(g.to(cuda))
+    X = graphs.conv_inputs(n, 64, 1002)
+    ar, ac, F, dO = (t.to(cuda) for t in (X.attn_row, X.attn_col, X.V, X.dO))
+    rows, _ = _rows_of(row_ptr)
+    rows = rows.int()
+    # BASELINE.json configs[1]: GAT d=64, softmax format
+    mine = N.gat_inference_softmax(128, ar, ac, row_ptr, col_ind, rows, 0.2, F)
+    ss = ref_gpu.softmax_smem(row_ptr)
+    assert_close("inference vs ref softmax", mine, ref.gat_inference_softmax(ss, ar, ac, row_ptr, col_ind, rows, 0.2, F))
+    out, emax, esum, emask = N.gat_forward(ar, ac, row_ptr, col_ind, 0.2, F, 0.0)
+    r_out, r_emax, r_esum, r_emask = ref.gat_forward(ar, ac, row_ptr, col_ind, 0.2, F, 0.0)
+    assert_close("out", out, r_out)
+    assert_close("edge_max", emax, r_emax)
+    assert_close("edge_sum", esum, r_esum)
+    mine_g = N.gat_backward(0.2, 0.0, row_ptr, col_ind, col_ptr, row_ind, permute, r_emax, r_esum, r_emask,
+                            F, ar, ac, dO)
+    ref_g = ref.gat_backward(0.2, 0.0, row_ptr, col_ind, col_ptr, row_ind, permute, r_emax, r_esum, r_emask,
+                             F, ar, ac, dO)
+    for name, a, b in zip(("grad_feat", "grad_attn_row", "grad_attn_col"), mine_g, ref_g):
+        assert_close_bulk(name, a, b)
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["pattern", "voc"])
+def test_gt_batched_full_size_vs_reference_kernels(cuda, name):
+    ref = ref_gpu.fused_gtconv()
+    g = {"pattern": graphs.pattern_like, "voc": graphs.pascalvoc_like}[name]()
+    n = g.num_nodes()
+    A, rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx, smem = preprocess_Hyper_fw_bw(g.to(cuda))
+    X = graphs.conv_inputs(n, 128, 1003)
+    Q, K, V, dO = (t.to(cuda) for t in (X.Q, X.K, X.V, X.dO))
+    hs = ref_gpu.hyper_smem(row_ptr)
+    assert hs <= 12288, "the reference hyper kernels need the 8-row block scores in 48 KB"
+    out, attn = N.gt_hyper_forward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V)
+    r_out, r_attn = ref.gt_hyper_forward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, hs, Q, K, V)
+    assert_close("out", out, r_out)
+    assert_close("attn_edge", attn, r_attn)
+    mine_g = N.gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V, r_attn, dO)
+    ref_g = ref.gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, hs, Q, K, V, r_attn, dO)
+    for nm, a, b in zip(("grad_Q", "grad_K", "grad_V"), mine_g, ref_g):
+        assert_close_bulk(nm, a, b)
