@@ -229,6 +229,15 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 __device__ __forceinline__ float fast_exp(float x) { return fast_exp2(x * kLog2e); }
+// 16-byte asynchronous global -> shared copy (LDGSTS): no register staging, the issuing thread
+// goes on; cp_async_wait_all() + a barrier make the data visible to the CTA.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // lets the next kernel on the stream start early if it was launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization (abi_common.h: launch_overlapped)
 __device__ __forceinline__ void allow_dependent_launch() {

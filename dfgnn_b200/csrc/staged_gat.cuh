@@ -199,6 +199,14 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16
   const int ne = b.E1 - b.E0;
   if (ne > kStageCap) return;
   stage_pad(s_e, ne);
+  if constexpr (kStageX) {  // dO rows of the tile -> shared memory, asynchronously (LDGSTS)
+    constexpr int F4 = L::F4 > 0 ? L::F4 : 1;
+    const float4* src = reinterpret_cast<const float4*>(p.dO);
+    for (int i = threadIdx.x; i < b.nseg * F4; i += kNW * 32) {
+      const int r = i / F4, k = i % F4;
+      cp_async16(s_x4 + i, src + ((size_t)(b.seg_lb + r) * h + hid) * F4 + k);
+    }
+  }
   {
     const int* colp = p.col_ind + b.E0;
     int cols[kEPT];
@@ -231,14 +239,7 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16
       if (i < ne) { Ent2 en; en.idx = cols[k]; en.w = acv[k]; en.w1 = 0.f; en.aux = kmv[k]; s_e[i] = en; }
     }
   }
-  if constexpr (kStageX) {  // dO rows of the tile -> shared memory
-    constexpr int F4 = L::F4 > 0 ? L::F4 : 1;
-    const float4* src = reinterpret_cast<const float4*>(p.dO);
-    for (int i = threadIdx.x; i < b.nseg * F4; i += kNW * 32) {
-      const int r = i / F4, k = i % F4;
-      s_x4[i] = __ldg(src + ((size_t)(b.seg_lb + r) * h + hid) * F4 + k);
-    }
-  }
+  if constexpr (kStageX) cp_async_wait_all();
   __syncthreads();
   auto prob = [&](int i, float ar_i, float mx, float inv) {
     const float x = leaky(ar_i + s_e[i].w, p.slope);
