@@ -67,13 +67,16 @@ inline bool dispatch_layout(int f, Fn&& fn, bool long_rows = false) {
   return true;
 }
 
-// Segments (rows / columns) per CTA: aim at ~48 entries per lane group (kNW * G groups
+// Segments (rows / columns) per CTA: aim at ~96 entries per lane group (measured on the PATTERN-
+// and VOC-shaped batches: 16 / 32 / 64 rows per CTA -> 1.33 / 1.29 / 1.35 ms resp. 1.53 / 1.20 / 1.04 ms) (kNW * G groups
 // per CTA), but keep at least ~4 CTAs per SM in the grid (148 SMs) so that small graphs
 // still fill the chip; [8, kMaxRB].
 inline int pick_rb(int m, int nnz, int G) {
+  static const int forced = [] { const char* e = getenv("DFGNN_B200_RB"); return e ? atoi(e) : 0; }();
+  if (forced >= 8 && forced <= kMaxRB) return forced;  // developer knob
   const double avg = m > 0 ? (double)nnz / (double)m : 0.0;
   int rb = 8;
-  while (rb < kMaxRB && avg * rb < 48.0 * kNW * G && (m / (2 * rb)) >= 4 * 148) rb <<= 1;
+  while (rb < kMaxRB && avg * rb < 96.0 * kNW * G && (m / (2 * rb)) >= 4 * 148) rb <<= 1;
   return rb;
 }
 

@@ -79,7 +79,10 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : DFGNN_GT_WARPS) /
 
   slots_clear<2 * NR, LPR>(s_slot, vw, gl);
   const RowBlock b = rowblock_init<G>(s_rp, p.row_ptr, p.m, p.rb, vw);
-  if (p.cap > 0 && b.E1 - b.E0 <= p.cap) return;
+  if (p.cap > 0 && b.E1 - b.E0 <= p.cap) {  // not a big tile: nothing to do here
+    dependency_wait();
+    return;
+  }
 
   // Per piece: acc2 = [A1c | A2] with A1c = sum_e p_e (dA_e - c) K_e, A2 = sum_e p_e K_e,
   // c = dA of the piece's first edge.  dQ = A1c + (c - s) * A2, which equals
@@ -199,6 +202,7 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : DFGNN_GT_WARPS) /
     const float2 tp = gedge[i];
     gedge[i].x = fmaf(-s_s[rr], tp.y, tp.x);
   }
+  if (p.cap > 0) dependency_wait();  // see common.cuh
 }
 
 // Column side: segments are CSC columns.  dV_j = sum p dO_i, dK_j = sum dS Q_i.
@@ -222,7 +226,10 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : DFGNN_GT_WARPS) /
 
   slots_clear<2 * NR, LPR>(s_slot, vw, gl);
   const RowBlock b = rowblock_init<G>(s_cp, p.col_ptr, p.n, p.rb_col, vw);
-  if (p.cap > 0 && b.E1 - b.E0 <= p.cap) return;
+  if (p.cap > 0 && b.E1 - b.E0 <= p.cap) {  // not a big tile: nothing to do here
+    dependency_wait();
+    return;
+  }
 
   // acc2 = [dV | dK]
   auto finish = [&](int c, float, float (&acc2)[2 * NR]) {
@@ -294,6 +301,7 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : DFGNN_GT_WARPS) /
       });
   __syncthreads();
   sum_merge_slots<2 * NR, LPR, G>(s_slot, vw, gl, finish);
+  if (p.cap > 0) dependency_wait();  // see common.cuh
 }
 
 // ------------------------------------------------------------------------- //
@@ -340,7 +348,10 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : 16) / kNW) gat_bw
 
   slots_clear<1, LPR>(s_slot, vw, gl);
   const RowBlock b = rowblock_init<G>(s_rp, p.row_ptr, p.m, p.rb, vw);
-  if (p.cap > 0 && b.E1 - b.E0 <= p.cap) return;
+  if (p.cap > 0 && b.E1 - b.E0 <= p.cap) {  // not a big tile: nothing to do here
+    dependency_wait();
+    return;
+  }
 
   for (int r = vw; r < b.nseg; r += VW)
     if (s_rp[r + 1] == s_rp[r] && gl == 0) s_w[r] = 0.f;
@@ -427,6 +438,7 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : 16) / kNW) gat_bw
     rsum = group_sum<LPR>(rsum);
     if (valid && gl == 0) p.grad_ar[node] = rsum;
   }
+  if (p.cap > 0) dependency_wait();  // see common.cuh
 }
 
 template <class L, int C>
@@ -446,7 +458,10 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR * C <= 32 ? 24 : 16) / kNW) g
 
   slots_clear<NR, LPR>(s_slot, vw, gl);
   const RowBlock b = rowblock_init<G>(s_cp, p.col_ptr, p.n, p.rb_col, vw);
-  if (p.cap > 0 && b.E1 - b.E0 <= p.cap) return;
+  if (p.cap > 0 && b.E1 - b.E0 <= p.cap) {  // not a big tile: nothing to do here
+    dependency_wait();
+    return;
+  }
 
   auto finish = [&](int c, float dac, float (&acc)[NR]) {
     const size_t node = (size_t)(b.seg_lb + c) * h + hid;
@@ -508,6 +523,7 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR * C <= 32 ? 24 : 16) / kNW) g
       });
   __syncthreads();
   sum_merge_slots<NR, LPR, G>(s_slot, vw, gl, finish);
+  if (p.cap > 0) dependency_wait();  // see common.cuh
 }
 
 }  // namespace dfgnn

@@ -244,6 +244,15 @@ __device__ __forceinline__ void allow_dependent_launch() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+// Counterpart for a kernel launched that way: returns once every kernel in front of it on the
+// stream has completed and its writes are visible.  The "big tiles only" row-block kernels call
+// it before they exit, so that THEIR completion implies the staged kernel's: without it a
+// dependent grid that finishes early would let later work on the stream run while the primary
+// kernel is still writing.  A no-op for a normally launched kernel.
+__device__ __forceinline__ void dependency_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // 1/x as one MUFU.RCP (1 ulp)
 __device__ __forceinline__ float fast_rcp(float x) {
   float y;

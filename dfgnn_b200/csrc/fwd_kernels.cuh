@@ -86,7 +86,10 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : DFGNN_GT_WARPS) /
 
   slots_clear<NR, LPR>(s_slot, vw, gl);
   const RowBlock b = rowblock_init<G>(s_rp, p.row_ptr, p.m, p.rb, vw);
-  if (p.cap > 0 && b.E1 - b.E0 <= p.cap) return;
+  if (p.cap > 0 && b.E1 - b.E0 <= p.cap) {  // not a big tile: nothing to do here
+    dependency_wait();
+    return;
+  }
 
   auto finish = [&](int r, float m, float l, float (&acc)[NR]) {
     const float inv = l > 0.f ? 1.f / l : 0.f;
@@ -191,6 +194,7 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : DFGNN_GT_WARPS) /
       attn[i] = fast_exp2(attn[i] - s_m[rr]) * s_inv[rr];
     }
   }
+  if (p.cap > 0) dependency_wait();  // see common.cuh
 }
 
 // ------------------------------------------------------------------------- //
@@ -242,7 +246,10 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : 16) / kNW) gat_fw
 
   slots_clear<NR, LPR>(s_slot, vw, gl);
   const RowBlock b = rowblock_init<G>(s_rp, p.row_ptr, p.m, p.rb, vw);
-  if (p.cap > 0 && b.E1 - b.E0 <= p.cap) return;
+  if (p.cap > 0 && b.E1 - b.E0 <= p.cap) {  // not a big tile: nothing to do here
+    dependency_wait();
+    return;
+  }
 
   auto finish = [&](int r, float m, float l, float (&acc)[NR]) {
     const size_t node = (size_t)(b.seg_lb + r) * h + hid;
@@ -340,6 +347,7 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : 16) / kNW) gat_fw
       finish(seg, m, l, acc);
     }
   }
+  if (p.cap > 0) dependency_wait();  // see common.cuh
 }
 
 // ------------------------------------------------------------------------- //

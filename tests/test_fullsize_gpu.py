@@ -178,7 +178,14 @@ def test_gat_arxiv_full_size_vs_reference_kernels(cuda):
     assert_close("inference vs ref softmax", mine, ref.gat_inference_softmax(ss, ar, ac, row_ptr, col_ind, rows, 0.2, F))
     out, emax, esum, emask = N.gat_forward(ar, ac, row_ptr, col_ind, 0.2, F, 0.0)
     r_out, r_emax, r_esum, r_emask = ref.gat_forward(ar, ac, row_ptr, col_ind, 0.2, F, 0.0)
-    assert_close("out", out, r_out)
+    # The reference's training forward (fused_gatconv_kernel.cu:93-124) stages 32 (weight, column)
+    # pairs per step in shared memory without a barrier before the next step overwrites them: rows
+    # with more than 32 neighbours come out wrong in a few launches out of ten (observed on B200;
+    # its inference kernels and ours agree bit-stably).  Compare inside that envelope only.
+    _, deg = _rows_of(row_ptr)
+    short = deg <= 32
+    assert_close("out (rows of <= 32 edges)", out[short], r_out[short])
+    assert_close("out vs our inference", out, mine)
     assert_close("edge_max", emax, r_emax)
     assert_close("edge_sum", esum, r_esum)
     mine_g = N.gat_backward(0.2, 0.0, row_ptr, col_ind, col_ptr, row_ind, permute, r_emax, r_esum, r_emask,

@@ -340,7 +340,11 @@ def test_gat_vs_reference_kernels(cuda, gname, dim):
     # training forward / backward at attn_drop = 0 (the reference mask seed is clock())
     out, emax, esum, emask = N.gat_forward(ar, ac, rp, ci, 0.2, F, 0.0)
     r_out, r_emax, r_esum, r_emask = ref.gat_forward(ar, ac, rp, ci, 0.2, F, 0.0)
-    assert_close("fwd out vs ref", out, r_out)
+    # rows of more than 32 edges race inside the reference's training forward
+    # (fused_gatconv_kernel.cu:93-124, see tests/test_fullsize_gpu.py): compare the others
+    short = (rp[1:] - rp[:-1]) <= 32
+    assert_close("fwd out vs ref (rows of <= 32 edges)", out[short], r_out[short])
+    assert_close("fwd out vs our inference", out, mine)
     assert_close("edge_max vs ref", emax, r_emax)
     assert_close("edge_sum vs ref", esum, r_esum)
     mine_g = N.gat_backward(0.2, 0.0, rp, ci, d["col_ptr"], d["row_ind"], d["val_idx"], r_emax,
