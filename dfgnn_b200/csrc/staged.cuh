@@ -3,17 +3,20 @@
 // The segmented row-block kernels (rowblock.cuh) carry an online softmax through
 // every row piece; on graphs whose rows are a handful of entries long (arxiv-,
 // cora-, PascalVOC-shaped: mean degree 4-7) that bookkeeping costs more issue slots
-// than the gathers themselves.  The staged kernels split a CTA's tile of <= kStageCap
-// entries into three phases with the per-entry scalars held in shared memory:
+// than the gathers themselves.  The staged kernels (staged_gat.cuh) split a CTA's tile
+// of <= kStageCap entries into phases over per-entry records held in shared memory:
 //
-//   A  entry-parallel  one thread per entry: neighbour index, score / probability
-//      (GAT), or   flat_sddmm: one lane group per entry, dot of the row operand
-//      with the gathered neighbour row (GT scores, dA, GAT g)
-//   B  segment-parallel  one lane group per row: max / sum / normalise in smem
-//   C  flat_spmm  every lane group walks an EQUAL slice of the tile's entries and
-//      accumulates weight * gathered row; a row boundary inside the slice costs one
-//      short divergent flush, rows cut by a slice boundary are merged through the
-//      same shared-memory slots as in rowblock.cuh (deterministic order).
+//   A  stage     every thread loads the indices of up to kEPT entries, then issues all
+//                dependent 4/8-byte gathers at once, and writes {neighbour, scalar} records
+//   B  per row   shared memory only: short rows one THREAD each, long rows one WARP each
+//                (max / sum / exp weights, or the backward's row sums)
+//   C  flat_spmm every lane group walks an EQUAL, whole-batch slice of the tile's entries
+//                and accumulates weight * gathered row; the last entry of a row is flagged,
+//                so a row boundary costs one short divergent flush; rows cut by a slice
+//                boundary are merged through the same shared-memory slots as in
+//                rowblock.cuh (deterministic order)
+//      flat_sddmm(_sx)  the same walk producing one dot product per entry (backward:
+//                g = <dO_i, feat_j>), row operands of the tile staged in shared memory
 //
 // This is the reference's CSR+COO "hyper" idea (edge-balanced SDDMM into shared
 // memory, then row-parallel softmax + SpMM; fused_gtconv_hyper.cu:63-161,
