@@ -58,7 +58,7 @@ __device__ __forceinline__ void sum_merge_slots(float* s_slot, int vw, int gl, F
 }
 
 template <class L, int C>
-__global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : DFGNN_GT_WARPS) / kNW) gt_bwd_row_kernel(const GtBwdParams p) {
+__global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_GT_WARPS_SMALL : DFGNN_GT_WARPS) / kNW) gt_bwd_row_kernel(const GtBwdParams p) {
   constexpr int NR = L::NR, LPR = L::LPR, G = L::G, VW = kNW * G;
   constexpr int CH = ChunkOf<L>::kChunk;
   static_assert(CH % C == 0 && CH <= LPR, "chunking");
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : DFGNN_GT_WARPS) /
 
 // Column side: segments are CSC columns.  dV_j = sum p dO_i, dK_j = sum dS Q_i.
 template <class L, int C>
-__global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : DFGNN_GT_WARPS) / kNW) gt_bwd_col_kernel(const GtBwdParams p) {
+__global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_GT_WARPS_SMALL : DFGNN_GT_WARPS) / kNW) gt_bwd_col_kernel(const GtBwdParams p) {
   constexpr int NR = L::NR, LPR = L::LPR, G = L::G, VW = kNW * G;
   constexpr int CH = ChunkOf<L>::kChunk;
   static_assert(CH % C == 0 && CH <= LPR, "chunking");

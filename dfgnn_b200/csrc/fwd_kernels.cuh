@@ -64,7 +64,7 @@ __device__ __forceinline__ void softmax_merge_slots(float* s_slot, int vw, int g
 // Scores are kept in the base-2 exponent domain (Q is pre-multiplied by log2 e),
 // so every exponential is one ex2.approx.
 template <class L, int C, bool AGNN>
-__global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : DFGNN_GT_WARPS) / kNW) dot_fwd_kernel(const DotFwdParams p) {
+__global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_GT_WARPS_SMALL : DFGNN_GT_WARPS) / kNW) dot_fwd_kernel(const DotFwdParams p) {
   constexpr int NR = L::NR, LPR = L::LPR, G = L::G, VW = kNW * G;
   constexpr int CH = ChunkOf<L>::kChunk;  // edges per index prefetch (<= LPR)
   static_assert(CH % C == 0 && CH <= LPR, "chunking");

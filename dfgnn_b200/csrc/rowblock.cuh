@@ -26,6 +26,9 @@ namespace dfgnn {
 #define DFGNN_KNW 8
 #endif
 constexpr int kNW = DFGNN_KNW;  // warps per CTA
+#ifndef DFGNN_GT_WARPS_SMALL
+#define DFGNN_GT_WARPS_SMALL 24  // the same for layouts of <= 8 floats per lane
+#endif
 #ifndef DFGNN_GT_WARPS
 #define DFGNN_GT_WARPS 16  // resident warps per SM the GT kernels are compiled for
 #endif
