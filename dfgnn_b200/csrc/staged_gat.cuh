@@ -169,10 +169,10 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16
   sum_merge_slots<NR, LPR, G>(s_slot, vw, gl, store);
 }
 
-// backward, row side: (A) stage {neighbour, attn_col[neighbour], keep factor}; (B) per row ->
-// p_e and lrelu'; (C) flat SDDMM g = <dO_i, feat_j>; (D) per row -> w, de, grad_attn_row, and
-// the packed scratch {de_e, keep-scaled p_e} the column side reads.
-// Entry fields: w = p_e, w1 = lrelu'(x_e), aux = keep_e / (1 - drop); s_g = g_e.
+// backward, row side: (A) stage {neighbour, attn_col[neighbour], keep factor}, dO rows -> smem;
+// (C) flat SDDMM g = <dO_i, feat_j>; (D) per row -> p_e, lrelu', w, de, grad_attn_row, and the
+// packed scratch {de_e, keep-scaled p_e} the column side reads.
+// Entry fields: w = attn_col[j], then p_e; w1 = lrelu'(x_e); aux = keep_e / (1 - drop); s_g = g_e.
 template <class L, int C>
 __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16) / kNW) gat_bwd_row_staged_kernel(const GatBwdParams p) {
   constexpr int LPR = L::LPR, G = L::G;
@@ -241,23 +241,6 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16
   }
   if constexpr (kStageX) cp_async_wait_all();
   __syncthreads();
-  auto prob = [&](int i, float ar_i, float mx, float inv) {
-    const float x = leaky(ar_i + s_e[i].w, p.slope);
-    s_e[i].w = fast_exp(x - mx) * inv;
-    s_e[i].w1 = x < 0.f ? p.slope : 1.f;
-  };
-  per_row(
-      b, s_rp,
-      [&](int r, int rs, int re) {
-        const float ar_i = s_ar[r], mx = s_mx[r], inv = s_inv[r];
-        for (int i = rs; i < re; ++i) prob(i, ar_i, mx, inv);
-      },
-      [&](int r, int rs, int re, int ln) {
-        const float ar_i = s_ar[r], mx = s_mx[r], inv = s_inv[r];
-        for (int i = rs + ln; i < re; i += 32) prob(i, ar_i, mx, inv);
-      });
-  __syncthreads();
-
   if constexpr (kStageX) {
     stage_mark_ends(b, s_rp, s_e, s_next);
     __syncthreads();
@@ -270,8 +253,17 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16
   }
   __syncthreads();
 
-  // de_e = (t_e - w_i p_e) * lrelu'(x_e), t_e = keep-scaled p_e g_e, w_i = sum_e t_e
-  // (fused_gatconv_kernel.cu:830-864)
+  // Per row: p_e = exp(x_e - max_i) / sum_i, x_e = leakyrelu(ar_i + ac_j) from the staged ac_j;
+  // t_e = keep-scaled p_e g_e, w_i = sum_e t_e, de_e = (t_e - w_i p_e) * lrelu'(x_e)
+  // (fused_gatconv_kernel.cu:830-864).  The probabilities are only needed here, so they are
+  // not a phase of their own.
+  auto prob = [&](int i, float ar_i, float mx, float inv, float& wsum) {
+    const float x = leaky(ar_i + s_e[i].w, p.slope);
+    const float pe = fast_exp(x - mx) * inv;
+    s_e[i].w = pe;
+    s_e[i].w1 = x < 0.f ? p.slope : 1.f;
+    wsum = fmaf(pe * s_e[i].aux, s_g[i], wsum);
+  };
   auto edge_grad = [&](int i, float wsum, float& rsum) {
     const Ent2 en = s_e[i];
     const float pk = en.w * en.aux;
@@ -282,14 +274,16 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_STAGE_WARPS : 16
   per_row(
       b, s_rp,
       [&](int r, int rs, int re) {
+        const float ar_i = s_ar[r], mx = s_mx[r], inv = s_inv[r];
         float wsum = 0.f, rsum = 0.f;
-        for (int i = rs; i < re; ++i) wsum = fmaf(s_e[i].w * s_e[i].aux, s_g[i], wsum);
+        for (int i = rs; i < re; ++i) prob(i, ar_i, mx, inv, wsum);
         for (int i = rs; i < re; ++i) edge_grad(i, wsum, rsum);
         p.grad_ar[(size_t)(b.seg_lb + r) * h + hid] = rsum;
       },
       [&](int r, int rs, int re, int ln) {
+        const float ar_i = s_ar[r], mx = s_mx[r], inv = s_inv[r];
         float wsum = 0.f, rsum = 0.f;
-        for (int i = rs + ln; i < re; i += 32) wsum = fmaf(s_e[i].w * s_e[i].aux, s_g[i], wsum);
+        for (int i = rs + ln; i < re; i += 32) prob(i, ar_i, mx, inv, wsum);
         wsum = warp_sum(wsum);
         for (int i = rs + ln; i < re; i += 32) edge_grad(i, wsum, rsum);
         rsum = warp_sum(rsum);
