@@ -44,6 +44,7 @@ _SIGNATURES = {
     "dfgnn_gt_hyper_forward": (c_int, [c_int] * 4 + [_P] * 7 + [c_int] + [_P] * 5 + [_P]),
     "dfgnn_gt_backward": (c_int, [c_int] * 5 + [_P] * 7 + [c_int] + [_P] * 9 + [_P]),
     "dfgnn_gt_backward_phase": (c_int, [c_int] * 6 + [_P] * 7 + [c_int] + [_P] * 9 + [_P]),
+    "dfgnn_gt_backward_cols": (c_int, [c_int] * 8 + [_P] * 7 + [c_int] + [_P] * 9 + [_P]),
     "dfgnn_gt_hyper_inference": (c_int, [c_int] * 4 + [_P] * 4 + [c_int] + [_P] * 4 + [_P]),
     "dfgnn_gt_softmax_inference": (c_int, [c_int] * 4 + [_P] * 4 + [c_int] + [_P] * 4 + [_P]),
     "dfgnn_gt_softmax_gm_inference": (c_int, [c_int] * 4 + [_P] * 4 + [_P] * 4 + [_P]),
@@ -54,6 +55,7 @@ _SIGNATURES = {
     "dfgnn_gat_forward": (c_int, [c_int] * 4 + [_P] * 4 + [c_float, _P, c_float, c_uint64] + [_P] * 4 + [_P]),
     "dfgnn_gat_backward": (c_int, [c_int] * 5 + [c_float, c_float] + [_P] * 16 + [_P]),
     "dfgnn_gat_backward_phase": (c_int, [c_int] * 6 + [c_float, c_float] + [_P] * 16 + [_P]),
+    "dfgnn_gat_backward_cols": (c_int, [c_int] * 8 + [c_float, c_float] + [_P] * 16 + [_P]),
     "dfgnn_gat_inference": (c_int, [c_int] * 4 + [_P] * 4 + [c_float, _P, _P, _P]),
     "dfgnn_gat_inference_hyper": (c_int, [c_int] * 5 + [_P] * 5 + [c_float, _P, _P, _P]),
     "dfgnn_gat_inference_hyper_recompute": (c_int, [c_int] * 4 + [_P] * 4 + [c_float, _P, _P, _P]),

@@ -30,6 +30,7 @@ struct GtBwdParams {
   const float* K;
   const float* V;
   const float* attn;   // [h, nnz] probabilities
+  const float* val;    // [nnz] edge weights of the forward scores, or null (all ones)
   const float* dO;
   float* dQ;
   float* dK;
@@ -116,10 +117,11 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_GT_WARPS_SMALL :
       },
       [&](int base, int cnt) {
         int my_col = 0;
-        float my_p = 0.f, my_t = 0.f;
+        float my_p = 0.f, my_t = 0.f, my_w = 1.f;
         if (gl < cnt) {
           my_col = __ldg(p.col_ind + base + gl);
           my_p = __ldg(attn + base + gl);
+          if (p.val) my_w = __ldg(p.val + base + gl);
         }
 #pragma unroll
         for (int s = 0; s < CH; s += C) {
@@ -146,13 +148,18 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_GT_WARPS_SMALL :
           for (int c = 0; c < C; ++c) {
             const float pc = group_bcast<LPR>(my_p, s + c);  // 0 beyond cnt
             const float t = dA[c] * pc;
-            const float u = (dA[c] - c_ref) * pc;
+            float u = (dA[c] - c_ref) * pc, pw = pc;
+            if (p.val) {  // s_e = <Q_i, K_j> * val_e: the K-side factors carry val_e
+              const float wv = group_bcast<LPR>(my_w, s + c);
+              u *= wv;
+              pw *= wv;
+            }
             if (gl == s + c) my_t = t;
             s_part += t;
 #pragma unroll
             for (int i = 0; i < NR; ++i) {
               acc2[i] = fmaf(u, kk[c][i], acc2[i]);
-              acc2[NR + i] = fmaf(pc, kk[c][i], acc2[NR + i]);
+              acc2[NR + i] = fmaf(pw, kk[c][i], acc2[NR + i]);
             }
           }
         }
@@ -196,11 +203,15 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_GT_WARPS_SMALL :
     }
   }
   __syncthreads();
-  // t_e -> dS_e = t_e - s_i p_e   (fused_gtconv_backward.cu:171-176)
+  // t_e -> dS_e = t_e - s_i p_e   (fused_gtconv_backward.cu:171-176); times val_e when the
+  // forward scores were weighted, so that the column side sees d(score)/d<Q,K> (the reference
+  // drops val in its backward, l.126 -- identical for its all-ones val)
   for (int i = b.E0 + threadIdx.x; i < b.E1; i += kNW * 32) {
     const int rr = find_row(s_rp, b.nseg, i);
     const float2 tp = gedge[i];
-    gedge[i].x = fmaf(-s_s[rr], tp.y, tp.x);
+    float ds = fmaf(-s_s[rr], tp.y, tp.x);
+    if (p.val) ds *= __ldg(p.val + i);
+    gedge[i].x = ds;
   }
   if (p.cap > 0) dependency_wait();  // see common.cuh
 }

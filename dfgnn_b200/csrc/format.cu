@@ -40,9 +40,14 @@ __global__ void coo_keys_kernel(int64_t nnz, int64_t n, int64_t n_cols, const in
   if (val) val[i] = 1.0f;
 }
 
-__global__ void iota_kernel(int64_t nnz, int32_t* __restrict__ ids) {
+// ids = 0..nnz-1; flag[0] = a column id lies outside [0, n_cols)
+__global__ void iota_check_kernel(int64_t nnz, int64_t n_cols, const int32_t* __restrict__ col_ind,
+                                  int32_t* __restrict__ ids, int* __restrict__ flag) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nnz) ids[i] = (int32_t)i;
+  if (i >= nnz) return;
+  ids[i] = (int32_t)i;
+  const int32_t c = col_ind[i];
+  if (c < 0 || c >= n_cols) flag[0] = 1;
 }
 
 __global__ void gather_col_kernel(int64_t nnz, const int64_t* __restrict__ col,
@@ -59,8 +64,11 @@ __global__ void seg_ptr_kernel(int64_t nnz, int64_t n, const int32_t* __restrict
                                int32_t* __restrict__ ptr) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p > nnz) return;
-  const int64_t prev = p > 0 ? sorted[p - 1] : -1;
-  const int64_t cur = p < nnz ? sorted[p] : n;
+  int64_t prev = p > 0 ? sorted[p - 1] : -1;
+  int64_t cur = p < nnz ? sorted[p] : n;
+  // keys outside [0, n) are rejected by the callers' validation; never write outside ptr[0..n]
+  prev = prev < -1 ? -1 : (prev > n ? n : prev);
+  cur = cur < 0 ? 0 : (cur > n ? n : cur);
   for (int64_t s = prev + 1; s <= cur; ++s) ptr[s] = (int32_t)p;
 }
 
@@ -196,12 +204,22 @@ int dfgnn_csr_to_csc(int64_t n_rows, int64_t n, int64_t nnz, const int32_t* row_
   char* ws = (char*)workspace;
   int32_t* ids_in = (int32_t*)ws;
   int32_t* keys_out = (int32_t*)(ws + e);
+  int* bad = (int*)(ws + 3 * e);
   void* temp = ws + 3 * e + 256;
   size_t temp_bytes = workspace_bytes - (3 * e + 256);
 
-  iota_kernel<<<blocks(nnz), 256, 0, st>>>(nnz, ids_in);
+  cudaMemsetAsync(bad, 0, sizeof(int), st);
+  iota_check_kernel<<<blocks(nnz), 256, 0, st>>>(nnz, n, col_ind, ids_in, bad);
   if (int rc = check_launch(fn)) return rc;
-  cudaError_t err = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, col_ind, keys_out, ids_in,
+  int h_flag = 0;  // one small readback, like dfgnn_coo_to_csr: the sort below trusts the key range
+  cudaError_t err = cudaMemcpyAsync(&h_flag, bad, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+  if (err != cudaSuccess) { set_error("%s: %s", fn, cudaGetErrorString(err)); return (int)err; }
+  if (h_flag) {
+    set_error("%s: column index outside [0, %lld)", fn, (long long)n);
+    return DFGNN_ERR_INVALID_ARGUMENT;
+  }
+  err = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, col_ind, keys_out, ids_in,
                                                     val_idx, (int)nnz, 0, bits, st);
   launch_counter().fetch_add(1);
   if (err != cudaSuccess) { set_error("%s: radix sort: %s", fn, cudaGetErrorString(err)); return (int)err; }

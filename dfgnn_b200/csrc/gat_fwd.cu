@@ -10,6 +10,7 @@ int launch_gat_fwd(int m, int nnz, int h, int f, const float* ar, const float* a
                    float drop, uint64_t seed, float* out, float* emax, float* esum, float* emask,
                    cudaStream_t st, const char* fn) {
   if (int rc = check_common(fn, m, nnz, h, f)) return rc;
+  if (m == 0) return DFGNN_OK;  // an empty graph: nothing to read or write
   DFGNN_REQUIRE(ar, fn); DFGNN_REQUIRE(ac, fn); DFGNN_REQUIRE(row_ptr, fn);
   if (nnz > 0) DFGNN_REQUIRE(col_ind, fn);
   DFGNN_REQUIRE(feat, fn); DFGNN_REQUIRE(out, fn);
@@ -74,6 +75,7 @@ int dfgnn_gat_forward(int m, int nnz, int h, int f, const float* attn_row, const
                       const float* in_feat, float attn_drop, uint64_t seed, float* out_feat,
                       float* edge_max, float* edge_sum, float* edge_mask, void* stream) {
   const char* fn = "dfgnn_gat_forward";
+  if (m == 0) return check_common(fn, m, nnz, h, f);
   DFGNN_REQUIRE(edge_max, fn); DFGNN_REQUIRE(edge_sum, fn);
   if (attn_drop > 0.f && nnz > 0) DFGNN_REQUIRE(edge_mask, fn);
   return launch_gat_fwd(m, nnz, h, f, attn_row, attn_col, row_ptr, col_ind, negative_slope,

@@ -32,6 +32,7 @@ int launch_dot_fwd(bool agnn, int m, int nnz, int h, int f, const int* row_ptr, 
 static int gt_infer(const char* fn, int m, int nnz, int h, int f, const int32_t* indptr,
                     const int32_t* indices, const float* val, const float* Q, const float* K,
                     const float* V, float* out, void* stream) {
+  if (m == 0) return check_common(fn, m, nnz, h, f);
   DFGNN_REQUIRE(indptr, fn);
   if (nnz > 0) DFGNN_REQUIRE(indices, fn);
   DFGNN_REQUIRE(Q, fn); DFGNN_REQUIRE(K, fn); DFGNN_REQUIRE(V, fn); DFGNN_REQUIRE(out, fn);
@@ -52,6 +53,7 @@ int dfgnn_gt_hyper_forward(int m, int nnz, int h, int f, const int32_t* row_ptr,
                            const float* K, const float* V, float* out_feat, float* attn_edge,
                            void* stream) {
   const char* fn = "dfgnn_gt_hyper_forward";
+  if (m == 0) return check_common(fn, m, nnz, h, f);
   DFGNN_REQUIRE(row_ptr, fn);
   if (nnz > 0) { DFGNN_REQUIRE(col_ind, fn); DFGNN_REQUIRE(attn_edge, fn); }
   DFGNN_REQUIRE(Q, fn); DFGNN_REQUIRE(K, fn); DFGNN_REQUIRE(V, fn); DFGNN_REQUIRE(out_feat, fn);
@@ -98,10 +100,10 @@ int dfgnn_agnn_forward(int m, int nnz, int h, int f, const int32_t* indptr, cons
                        void* stream) {
   const char* fn = "dfgnn_agnn_forward";
   if (int rc = check_common(fn, m, nnz, h, f)) return rc;
+  if (m == 0) return DFGNN_OK;
   DFGNN_REQUIRE(indptr, fn);
   if (nnz > 0) DFGNN_REQUIRE(indices, fn);
   DFGNN_REQUIRE(H, fn); DFGNN_REQUIRE(inv_norm, fn); DFGNN_REQUIRE(out_feat, fn);
-  if (m == 0) return DFGNN_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const long long warps = (long long)m * h;
   inv_norm_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(m, h, f, H, inv_norm);

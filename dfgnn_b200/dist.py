@@ -11,14 +11,29 @@ is new design, following SURVEY.md 8(e):
   feat, attn_col) of the same nodes.  Forward: an all-gather of the column-side
   operands ("halo"; for the dense-halo graphs of the benchmark the halo is every
   node).  Backward: the column-indexed partial gradients are reduce-scattered.
-  Owned slices have different lengths, so they are padded to ``max_rows`` and the
-  shard's column ids are relabelled once to ``owner * max_rows + local`` -- the
-  gathered buffer is then indexed directly by the kernels, no unpacking pass.
+
+Padded column space.  Owned slices have different lengths, so every rank keeps its
+slice in a buffer of ``max_rows`` rows (zero tail) and the shard's column ids are
+relabelled ONCE so that the gathered buffer is indexed directly by the kernels (no
+unpacking pass).  The padded space is cut into ``chunks`` equal column chunks:
+
+    local row l of owner w  ->  c = l // q, lq = l % q          (q = max_rows / chunks)
+    column id               =   c * (world * q) + w * q + lq
+
+i.e. chunk c of the gathered buffer is the all-gather of every rank's c-th slice
+``x[c*q:(c+1)*q]`` -- one ``ncclAllGather`` per chunk and operand, all of them issued as
+ONE coalesced NCCL group -- and chunk c of the column-side gradients is reduce-scattered
+on a side stream while the column-side kernel of chunk c+1 runs (``chunks`` > 1).
+
+Public operators (autograd Functions, same argument meaning as the single-GPU
+``GTConvFuse_hyper`` / ``GATConvFuse`` with the column-side operands given as owned slices):
+``GTConvFuse_hyper_dist`` and ``GATConvFuse_dist``; ``HaloExchange.gather`` on its own is
+differentiable too (its backward is the reduce-scatter).
 """
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Optional
+from typing import List, Optional, Sequence
 
 import torch
 
@@ -39,6 +54,20 @@ class Partition:
     max_rows: int              # padded slice length (row partition)
     bounds: Optional[torch.Tensor]  # [world+1] row boundaries (row partition)
     describe: str
+    chunks: int = 1            # column chunks of the padded space (row partition)
+
+    @property
+    def q(self) -> int:
+        """rows of one chunk slice"""
+        return self.max_rows // self.chunks
+
+    def padded_index(self, node: torch.Tensor) -> torch.Tensor:
+        """global node id -> column id in the padded gathered space (row partition)."""
+        b = self.bounds
+        owner = torch.searchsorted(b[1:].contiguous(), node, right=True)
+        loc = node - b[owner]
+        q = self.q
+        return (loc // q) * (self.world * q) + owner * q + (loc % q)
 
 
 def row_bounds(deg: torch.Tensor, world: int) -> torch.Tensor:
@@ -63,8 +92,9 @@ def graph_bounds(g: Graph, world: int) -> torch.Tensor:
     return row_bounds(edges_per_graph, world), offs
 
 
-def make_partition(g: Graph, world: int, rank: int, mode: str = "auto") -> Partition:
-    """Shard ``g`` (a CPU graph with canonical edge order) for ``rank`` of ``world``."""
+def make_partition(g: Graph, world: int, rank: int, mode: str = "auto", chunks: int = 1) -> Partition:
+    """Shard ``g`` (a CPU graph with canonical edge order) for ``rank`` of ``world``.
+    ``chunks``: column chunks of the padded space of a row partition (see module docstring)."""
     n = g.num_nodes()
     if world == 1:
         return Partition(rank, world, "single", "weak", g, n, g.num_cols, slice(0, n), slice(0, n),
@@ -83,92 +113,316 @@ def make_partition(g: Graph, world: int, rank: int, mode: str = "auto") -> Parti
                          slice(lo, hi), hi - lo, None,
                          f"global batch sharded by whole graph over {world} ranks (edge balanced), "
                          f"no collective")
+    chunks = max(1, int(chunks))
     deg = torch.bincount(src, minlength=n)
     bounds = row_bounds(deg, world)
     sizes = bounds[1:] - bounds[:-1]
-    max_rows = int(sizes.max())
+    max_rows = (int(sizes.max()) + chunks - 1) // chunks * chunks
     lo, hi = int(bounds[rank]), int(bounds[rank + 1])
     keep = (src >= lo) & (src < hi)
-    d = dst[keep]
-    owner = torch.searchsorted(bounds[1:].contiguous(), d, right=True)
-    col = owner * max_rows + (d - bounds[owner])
-    local = Graph(src[keep] - lo, col, hi - lo, None, g.name + f"[rows {lo}:{hi}]",
-                  num_cols=world * max_rows)
-    return Partition(rank, world, "row", "strong", local, hi - lo, world * max_rows, slice(lo, hi),
+    part = Partition(rank, world, "row", "strong", g, hi - lo, world * max_rows, slice(lo, hi),
                      slice(lo, hi), max_rows, bounds,
                      f"1-D row partition over {world} ranks (nnz balanced), halo all-gather of the "
-                     f"column-side operands + reduce-scatter of their gradients")
+                     f"column-side operands + reduce-scatter of their gradients"
+                     + (f", {chunks} column chunks (reduce-scatter overlapped with the column-side kernels)"
+                        if chunks > 1 else ""), chunks)
+    col = part.padded_index(dst[keep])
+    part.local_graph = Graph(src[keep] - lo, col, hi - lo, None, g.name + f"[rows {lo}:{hi}]",
+                             num_cols=world * max_rows)
+    return part
 
+
+# --------------------------------------------------------------------------------------- #
+# halo exchange                                                                            #
+# --------------------------------------------------------------------------------------- #
 
 class HaloExchange:
     """All-gather of the column-side operands / reduce-scatter of their gradients for a
     row partition.  Identity for the other partition kinds.  Works on any backend
-    (NCCL on the GPUs; gloo in the CPU tests, where reduce-scatter is an all-reduce + slice)."""
+    (NCCL on the GPUs; gloo in the CPU tests, where the collectives are emulated with
+    all_gather / all_reduce + slice).
 
-    def __init__(self, part: Partition, device, world: int):
+    Buffers: every call returns FRESH tensors (they may be saved for backward by the conv
+    Functions); an operand that already has ``max_rows`` rows is sent in place, a shorter one
+    (the ``n_rows`` owned rows) is zero-padded first.
+
+    ``record=True`` brackets every collective with CUDA events on the stream it runs on;
+    ``pop_times()`` returns the accumulated {"allgather_ms", "reduce_scatter_ms"}."""
+
+    def __init__(self, part: Partition, device, world: int, record: bool = False):
+        import torch.distributed as dist
         self.part = part
         self.active = part.kind == "row" and world > 1
-        self.device = device
+        self.device = torch.device(device)
         self.world = world
-        self._send = {}
-        self._recv = {}
+        self.record = record and self.device.type == "cuda"
+        self._events = {"allgather_ms": [], "reduce_scatter_ms": []}
+        self._nccl = self.active and dist.get_backend() == "nccl"
+        self._comm = torch.cuda.Stream(self.device) if (self.active and self.device.type == "cuda") else None
 
-    def _buf(self, store, key, shape, like):
-        t = store.get(key)
-        if t is None or t.shape != torch.Size(shape) or t.dtype != like.dtype:
-            t = torch.zeros(shape, dtype=like.dtype, device=like.device)
-            store[key] = t
-        return t
-
-    def gather(self, x: torch.Tensor, key: str = "a") -> torch.Tensor:
-        """x: this rank's owned slice [n_owned, ...] -> [world*max_rows, ...] in padded order."""
-        import torch.distributed as dist
-        if not self.active:
-            return x
+    # -- helpers ---------------------------------------------------------------------------
+    def pad(self, x: torch.Tensor) -> torch.Tensor:
+        """owned slice [n_rows, ...] -> [max_rows, ...] (zero tail); already padded: unchanged."""
         mr = self.part.max_rows
-        send = self._buf(self._send, key, (mr,) + tuple(x.shape[1:]), x)
-        send[: x.shape[0]].copy_(x)
-        out = self._buf(self._recv, key, (self.world * mr,) + tuple(x.shape[1:]), x)
-        dist.all_gather_into_tensor(out, send)
+        if not self.active or x.shape[0] == mr:
+            return x
+        if x.shape[0] != self.part.n_rows:
+            raise RuntimeError(f"halo operand has {x.shape[0]} rows, expected {self.part.n_rows} or {mr}")
+        out = x.new_zeros((mr,) + tuple(x.shape[1:]))
+        out[: x.shape[0]].copy_(x)
         return out
 
-    def gather_pair(self, a, b, rec=None):
-        if not self.active:
-            if rec is not None and "ag0" in rec:
-                rec["ag0"].record()
-                rec["ag1"].record()
-            return a, b
-        if rec is not None:
-            rec["ag0"].record()
-        oa, ob = self.gather(a, "a"), self.gather(b, "b")
-        if rec is not None:
-            rec["ag1"].record()
-        return oa, ob
+    def _ev(self, key):
+        if not self.record:
+            return None
+        pair = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        self._events[key].append(pair)
+        pair[0].record()
+        return pair
 
-    def reduce(self, g: torch.Tensor, key: str = "ga") -> torch.Tensor:
-        """g: partial gradient over ALL padded columns [world*max_rows, ...] -> owned slice."""
+    def pop_times(self) -> dict:
+        """Sum of the recorded collective durations since the last call (synchronises)."""
+        out = {}
+        if self.record:
+            torch.cuda.synchronize(self.device)
+        for k, pairs in self._events.items():
+            out[k] = float(sum(a.elapsed_time(b) for a, b in pairs))
+            pairs.clear()
+        return out
+
+    # -- raw collectives ---------------------------------------------------------------------
+    def all_gather(self, xs: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+        """xs: owned slices -> gathered [world*max_rows, ...] tensors in the padded order."""
         import torch.distributed as dist
         if not self.active:
-            return g
-        mr = self.part.max_rows
-        n_owned = self.part.n_rows
-        if dist.get_backend() == "gloo":
-            dist.all_reduce(g)
+            return list(xs)
+        C, q, W = self.part.chunks, self.part.q, self.world
+        xs = [self.pad(x.detach()).contiguous() for x in xs]
+        outs = [x.new_empty((C, W * q) + tuple(x.shape[1:])) for x in xs]
+        pair = self._ev("allgather_ms")
+        if self._nccl:
+            with dist._coalescing_manager():  # one NCCL group launch for all chunks and operands
+                for x, o in zip(xs, outs):
+                    for c in range(C):
+                        dist.all_gather_into_tensor(o[c], x[c * q:(c + 1) * q])
+        else:
+            for x, o in zip(xs, outs):
+                for c in range(C):
+                    parts = [torch.empty_like(x[:q]) for _ in range(W)]
+                    dist.all_gather(parts, x[c * q:(c + 1) * q].contiguous())
+                    o[c].copy_(torch.cat(parts, 0))
+        if pair:
+            pair[1].record()
+        return [o.view((W * C * q,) + tuple(o.shape[2:])) for o in outs]
+
+    def reduce_scatter_chunk(self, c: int, gs: Sequence[torch.Tensor], outs: Sequence[torch.Tensor]):
+        """Chunk c of the column-indexed partial gradients gs ([world*max_rows, ...]) summed over
+        the ranks into rows [c*q, (c+1)*q) of outs ([max_rows, ...]).  Runs on the current stream."""
+        import torch.distributed as dist
+        C, q, W = self.part.chunks, self.part.q, self.world
+        pair = self._ev("reduce_scatter_ms")
+        if self._nccl:
+            with dist._coalescing_manager():
+                for g, o in zip(gs, outs):
+                    dist.reduce_scatter_tensor(o[c * q:(c + 1) * q], g[c * W * q:(c + 1) * W * q])
+        else:
             r = self.part.rank
-            return g[r * mr: r * mr + n_owned]
-        out = self._buf(self._recv, key, (mr,) + tuple(g.shape[1:]), g)
-        dist.reduce_scatter_tensor(out, g.contiguous())
-        return out[:n_owned]
+            for g, o in zip(gs, outs):
+                blk = g[c * W * q:(c + 1) * W * q].clone()
+                dist.all_reduce(blk)
+                o[c * q:(c + 1) * q].copy_(blk[r * q:(r + 1) * q])
+        if pair:
+            pair[1].record()
+
+    def reduce_scatter(self, gs: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+        """gs: partial gradients over ALL padded columns -> owned slices [n_rows, ...]."""
+        if not self.active:
+            return list(gs)
+        mr = self.part.max_rows
+        gs = [g.contiguous() for g in gs]
+        outs = [g.new_empty((mr,) + tuple(g.shape[1:])) for g in gs]
+        for c in range(self.part.chunks):
+            self.reduce_scatter_chunk(c, gs, outs)
+        return [o[: self.part.n_rows] for o in outs]
+
+    # -- overlapped reduce-scatter (used by the distributed conv Functions) --------------------
+    def begin_overlapped_reduce(self, gs: Sequence[torch.Tensor]):
+        mr = self.part.max_rows
+        self._ov = ([g.new_empty((mr,) + tuple(g.shape[1:])) for g in gs], list(gs))
+        return self._ov[0]
+
+    def reduce_chunk_async(self, c: int):
+        """Called after the kernels that produce chunk c were launched on the current stream:
+        its reduce-scatter runs on the communication stream behind them."""
+        outs, gs = self._ov
+        if self._comm is None:
+            self.reduce_scatter_chunk(c, gs, outs)
+            return
+        cur = torch.cuda.current_stream(self.device)
+        self._comm.wait_stream(cur)
+        with torch.cuda.stream(self._comm):
+            self.reduce_scatter_chunk(c, gs, outs)
+        for t in list(gs) + list(outs):
+            t.record_stream(self._comm)
+
+    def end_overlapped_reduce(self) -> List[torch.Tensor]:
+        outs, _ = self._ov
+        self._ov = None
+        if self._comm is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._comm)
+        return [o[: self.part.n_rows] for o in outs]
+
+    # -- differentiable gather --------------------------------------------------------------
+    def gather(self, *xs: torch.Tensor):
+        """Differentiable halo all-gather: owned slices -> gathered tensors; the backward
+        reduce-scatters the gradients back to the owned rows."""
+        if not self.active:
+            return xs if len(xs) > 1 else xs[0]
+        out = _HaloGather.apply(self, *xs)
+        return out if len(xs) > 1 else out[0]
+
+    # round-1 names, kept for callers that time the two directions by hand
+    def gather_pair(self, a, b, rec=None):
+        return tuple(self.all_gather([a, b]))
 
     def reduce_pair(self, ga, gb, rec=None):
-        if not self.active:
-            if rec is not None and "rs0" in rec:
-                rec["rs0"].record()
-                rec["rs1"].record()
-            return ga, gb
-        if rec is not None:
-            rec["rs0"].record()
-        oa, ob = self.reduce(ga, "ga"), self.reduce(gb, "gb")
-        if rec is not None:
-            rec["rs1"].record()
-        return oa, ob
+        return tuple(self.reduce_scatter([ga, gb]))
+
+
+class _HaloGather(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, halo: HaloExchange, *xs):
+        ctx.halo = halo
+        ctx.rows = [x.shape[0] for x in xs]
+        return tuple(halo.all_gather(xs))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        outs = ctx.halo.reduce_scatter([g.contiguous() for g in grads])
+        # an operand that was passed padded gets a padded gradient back
+        fixed = []
+        for o, r in zip(outs, ctx.rows):
+            if r != o.shape[0]:
+                p = o.new_zeros((r,) + tuple(o.shape[1:]))
+                p[: o.shape[0]].copy_(o)
+                o = p
+            fixed.append(o)
+        return (None, *fixed)
+
+
+# --------------------------------------------------------------------------------------- #
+# distributed conv operators                                                               #
+# --------------------------------------------------------------------------------------- #
+
+def _col_chunks(halo: HaloExchange):
+    """[(first column, number of columns)] of the column-side launches."""
+    p = halo.part
+    if not halo.active or p.chunks == 1:
+        return [(0, p.n_cols)]
+    w = halo.world * p.q
+    return [(c * w, w) for c in range(p.chunks)]
+
+
+def _fit_grad(g: torch.Tensor, rows: int) -> torch.Tensor:
+    """Gradient of an operand that was given with `rows` rows (owned or padded)."""
+    if g.shape[0] == rows:
+        return g
+    out = g.new_zeros((rows,) + tuple(g.shape[1:]))
+    out[: g.shape[0]].copy_(g)
+    return out
+
+
+class DistGTFunction(torch.autograd.Function):
+    """Row-partitioned FusedGTFunction_hyper (operators/fused_gtconv.py:79-158 on a shard):
+    forward = halo all-gather of K, V + fused conv; backward = row-side kernel, then the
+    column-side kernel chunk by chunk with the reduce-scatter of dK, dV of chunk c running
+    behind the kernel of chunk c+1."""
+
+    @staticmethod
+    def forward(ctx, halo, rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx, smem_consume,
+                Q, K_own, V_own):
+        from .operators import _native as N
+        K, V = halo.all_gather([K_own, V_own])
+        out, attn = N.gt_hyper_forward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx,
+                                       smem_consume, Q, K, V)
+        ctx.halo, ctx.smem = halo, smem_consume
+        ctx.own_rows = (K_own.shape[0], V_own.shape[0])
+        ctx.save_for_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, Q, K, V, attn)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        from .operators import _native as N
+        row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, Q, K, V, attn = ctx.saved_tensors
+        halo = ctx.halo
+        grad_out = grad_out.contiguous()
+        bufs = N.gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, ctx.smem,
+                             Q, K, V, attn, grad_out, _phases=1)
+        gq, gk, gv, ge = bufs
+        if not halo.active:
+            N.gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, ctx.smem,
+                          Q, K, V, attn, grad_out, _phases=2, _buffers=bufs)
+            return (None,) * 9 + (gq, gk, gv)
+        halo.begin_overlapped_reduce([gk, gv])
+        for c, (c0, nc) in enumerate(_col_chunks(halo)):
+            N.gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, ctx.smem,
+                          Q, K, V, attn, grad_out, _phases=2, _buffers=bufs, _cols=(c0, nc))
+            halo.reduce_chunk_async(c)
+        gk_own, gv_own = halo.end_overlapped_reduce()
+        return (None,) * 9 + (gq, _fit_grad(gk_own, ctx.own_rows[0]), _fit_grad(gv_own, ctx.own_rows[1]))
+
+
+class DistGATFunction(torch.autograd.Function):
+    """Row-partitioned FusedGATFunction (operators/fused_gatconv.py:95-176 on a shard)."""
+
+    @staticmethod
+    def forward(ctx, halo, attn_row, attn_col_own, row_ptr, col_ind, col_ptr, row_ind, permute,
+                negative_slope, feat_own, attn_drop):
+        from .operators import _native as N
+        feat, ac = halo.all_gather([feat_own, attn_col_own])
+        out, emax, esum, emask = N.gat_forward(attn_row, ac, row_ptr, col_ind, negative_slope, feat,
+                                               attn_drop)
+        ctx.halo, ctx.slope, ctx.drop = halo, negative_slope, attn_drop
+        ctx.own_rows = (feat_own.shape[0], attn_col_own.shape[0])
+        ctx.save_for_backward(row_ptr, col_ind, col_ptr, row_ind, permute, emax, esum, emask, feat,
+                              attn_row, ac)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        from .operators import _native as N
+        (row_ptr, col_ind, col_ptr, row_ind, permute, emax, esum, emask, feat, attn_row,
+         ac) = ctx.saved_tensors
+        halo = ctx.halo
+        grad_out = grad_out.contiguous()
+        args = (ctx.slope, ctx.drop, row_ptr, col_ind, col_ptr, row_ind, permute, emax, esum, emask,
+                feat, attn_row, ac, grad_out)
+        bufs = N.gat_backward(*args, _phases=1)
+        gf, gr, gc, ge = bufs
+        if not halo.active:
+            N.gat_backward(*args, _phases=2, _buffers=bufs)
+            return (None, gr, gc) + (None,) * 6 + (gf, None)
+        halo.begin_overlapped_reduce([gf, gc])
+        for c, (c0, nc) in enumerate(_col_chunks(halo)):
+            N.gat_backward(*args, _phases=2, _buffers=bufs, _cols=(c0, nc))
+            halo.reduce_chunk_async(c)
+        gf_own, gc_own = halo.end_overlapped_reduce()
+        return (None, gr, _fit_grad(gc_own, ctx.own_rows[1])) + (None,) * 6 + \
+            (_fit_grad(gf_own, ctx.own_rows[0]), None)
+
+
+def GTConvFuse_hyper_dist(halo: HaloExchange, rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx,
+                          smem_consume, Q, K_own, V_own):
+    """GTConvFuse_hyper (operators/fused_gtconv.py:51-76) on a row-partitioned shard: Q holds the
+    rank's rows, K_own / V_own the rank's slice of the column-side operands ([n_rows, h, f] or
+    already padded to [max_rows, h, f]); the index arrays describe the shard in the padded column
+    space (``Partition.local_graph``).  Returns out [n_rows, h, f]; differentiable in Q, K_own, V_own."""
+    return DistGTFunction.apply(halo, rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx,
+                                smem_consume, Q, K_own, V_own)
+
+
+def GATConvFuse_dist(halo: HaloExchange, attn_row, attn_col_own, row_ptr, col_ind, col_ptr, row_ind,
+                     permute, negative_slope, feat_own, attn_drop):
+    """GATConvFuse (operators/fused_gatconv.py:5-28) on a row-partitioned shard."""
+    return DistGATFunction.apply(halo, attn_row, attn_col_own, row_ptr, col_ind, col_ptr, row_ind,
+                                 permute, negative_slope, feat_own, attn_drop)

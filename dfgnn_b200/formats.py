@@ -24,6 +24,7 @@ class SparseMatrix:
         self.col = col
         self.shape = tuple(shape)
         self.val = torch.ones(row.numel(), dtype=torch.float32, device=row.device)
+        self.val._dfgnn_ones = True
 
     @property
     def nnz(self) -> int:
@@ -73,6 +74,7 @@ def coo_to_csr(row: torch.Tensor, col: torch.Tensor, n: int, n_cols: int = None)
                                 val.data_ptr() if nnz else None, ws.data_ptr(), ws_bytes,
                                 torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(rc, "coo_to_csr")
+    val._dfgnn_ones = True  # operators/_native.py: the kernels skip the weight loads for this tensor
     return row_ptr, col_ind, rows, perm, val
 
 

@@ -37,6 +37,12 @@ def _ptr(t):
     return None if t is None or t.numel() == 0 else t.data_ptr()
 
 
+def _val_ptr(val):
+    """Edge weights of the GT scores.  The preprocessing (formats.coo_to_csr) marks its all-ones
+    `val` tensor; for those the kernels skip the weight loads (NULL == all ones)."""
+    return None if (val is None or getattr(val, "_dfgnn_ones", False)) else _ptr(val)
+
+
 def _stream(ref: torch.Tensor):
     return torch.cuda.current_stream(ref.device).cuda_stream
 
@@ -78,7 +84,7 @@ def gt_hyper_forward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, sme
         out = torch.empty_like(Q)
         attn = torch.empty((h, nnz), dtype=torch.float32, device=Q.device)
         rc = _lib.lib().dfgnn_gt_hyper_forward(
-            m, nnz, h, f, _ptr(row_ptr), _ptr(col_ind), _ptr(rows), _ptr(val), _ptr(col_ptr),
+            m, nnz, h, f, _ptr(row_ptr), _ptr(col_ind), _ptr(rows), _val_ptr(val), _ptr(col_ptr),
             _ptr(row_ind), _ptr(val_idx), int(smem_consume), _ptr(Q), _ptr(K), _ptr(V),
             _ptr(out), _ptr(attn), _stream(Q))
     _lib.check(rc, fn)
@@ -86,11 +92,14 @@ def gt_hyper_forward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, sme
 
 
 def gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem_consume,
-                Q, K, V, attn_edge, grad, *, _phases: int = 3, _buffers=None) -> List[torch.Tensor]:
+                Q, K, V, attn_edge, grad, *, _phases: int = 3, _buffers=None,
+                _cols=None) -> List[torch.Tensor]:
     """fused_gtconv.cpp:125-172 -> [grad_Q, grad_K, grad_V].
-    Keyword-only extras (no reference counterpart, used for per-kernel timing): ``_phases``
-    1 = row-side kernel only, 2 = column-side only, 3 = both; ``_buffers`` = (gq, gk, gv, scratch)
-    from an earlier call, reused instead of allocating."""
+    Keyword-only extras (no reference counterpart, used for per-kernel timing and by the
+    multi-GPU operator): ``_phases`` 1 = row-side kernel only, 2 = column-side only, 3 = both;
+    ``_buffers`` = (gq, gk, gv, scratch) from an earlier call, reused instead of allocating;
+    ``_cols`` = (first column, number of columns[, entries]) restricts a column-side call to a
+    column range (needs ``_buffers``)."""
     fn = "gt_backward"
     m, nnz, h, f = _check_gt(fn, row_ptr, col_ind, Q, K, V, rows, val)
     _chk("col_ptr", col_ptr, torch.int32)
@@ -111,10 +120,16 @@ def gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem_con
         else:
             gq, gk, gv = torch.empty_like(Q), torch.empty_like(K), torch.empty_like(V)
             ge = torch.empty((h, nnz, 2), dtype=torch.float32, device=Q.device)  # scratch {dS, p}
-        rc = _lib.lib().dfgnn_gt_backward_phase(
-            int(_phases), m, n, nnz, h, f, _ptr(row_ptr), _ptr(col_ind), _ptr(rows), _ptr(val), _ptr(col_ptr),
-            _ptr(row_ind), _ptr(val_idx), int(smem_consume), _ptr(Q), _ptr(K), _ptr(V),
-            _ptr(attn_edge), _ptr(grad), _ptr(gq), _ptr(gk), _ptr(gv), _ptr(ge), _stream(Q))
+        tail = (m, n, nnz, h, f, _ptr(row_ptr), _ptr(col_ind), _ptr(rows), _val_ptr(val), _ptr(col_ptr),
+                _ptr(row_ind), _ptr(val_idx), int(smem_consume), _ptr(Q), _ptr(K), _ptr(V),
+                _ptr(attn_edge), _ptr(grad), _ptr(gq), _ptr(gk), _ptr(gv), _ptr(ge), _stream(Q))
+        if _cols is not None:
+            if _buffers is None or _phases != 2:
+                raise RuntimeError(f"{fn}: _cols needs _phases=2 and _buffers")
+            c0, nc = int(_cols[0]), int(_cols[1])
+            rc = _lib.lib().dfgnn_gt_backward_cols(c0, nc, int(_cols[2]) if len(_cols) > 2 else -1, *tail)
+        else:
+            rc = _lib.lib().dfgnn_gt_backward_phase(int(_phases), *tail)
     _lib.check(rc, fn)
     if _buffers is None and _phases != 3:
         return [gq, gk, gv, ge]
@@ -128,7 +143,7 @@ def _gt_inference(cname, fn, indptr, indices, rows, val, smem_consume, Q, K, V, 
         args = [m, nnz, h, f, _ptr(indptr), _ptr(indices)]
         if has_rows:
             args.append(_ptr(rows))
-        args.append(_ptr(val))
+        args.append(_val_ptr(val))
         if has_smem:
             args.append(int(smem_consume))
         args += [_ptr(Q), _ptr(K), _ptr(V), _ptr(out), _stream(Q)]
@@ -240,9 +255,9 @@ def gat_forward(attn_row, attn_col, row_ptr, col_ind, negative_slope, in_feat, a
 
 def gat_backward(negative_slope, attn_drop, row_ptr, col_ind, col_ptr, row_ind, permute,
                  edge_max, edge_sum, edge_mask, in_feat, attn_row, attn_col, grad, *,
-                 _phases: int = 3, _buffers=None):
+                 _phases: int = 3, _buffers=None, _cols=None):
     """fused_gatconv.cpp:291-353 -> [grad_feat, grad_attn_row, grad_attn_col].
-    ``_phases`` / ``_buffers``: see gt_backward (buffers = (gf, gr, gc, scratch))."""
+    ``_phases`` / ``_buffers`` / ``_cols``: see gt_backward (buffers = (gf, gr, gc, scratch))."""
     fn = "gat_backward"
     m, nnz, h, f = _check_gat(fn, attn_row, attn_col, row_ptr, col_ind, in_feat)
     for n, t in (("col_ptr", col_ptr), ("row_ind", row_ind), ("permute", permute)):
@@ -264,11 +279,17 @@ def gat_backward(negative_slope, attn_drop, row_ptr, col_ind, col_ptr, row_ind, 
             gr = torch.empty((m, h), dtype=torch.float32, device=dev)
             gc = torch.empty((n, h), dtype=torch.float32, device=dev)
             ge = torch.empty((nnz, h, 2), dtype=torch.float32, device=dev)  # scratch {de, keep-scaled p}
-        rc = _lib.lib().dfgnn_gat_backward_phase(
-            int(_phases), m, n, nnz, h, f, float(negative_slope), float(attn_drop), _ptr(row_ptr), _ptr(col_ind),
-            _ptr(col_ptr), _ptr(row_ind), _ptr(permute), _ptr(edge_max), _ptr(edge_sum),
-            _ptr(edge_mask), _ptr(in_feat), _ptr(attn_row), _ptr(attn_col), _ptr(grad), _ptr(gf),
-            _ptr(gr), _ptr(gc), _ptr(ge), _stream(in_feat))
+        tail = (m, n, nnz, h, f, float(negative_slope), float(attn_drop), _ptr(row_ptr), _ptr(col_ind),
+                _ptr(col_ptr), _ptr(row_ind), _ptr(permute), _ptr(edge_max), _ptr(edge_sum),
+                _ptr(edge_mask), _ptr(in_feat), _ptr(attn_row), _ptr(attn_col), _ptr(grad), _ptr(gf),
+                _ptr(gr), _ptr(gc), _ptr(ge), _stream(in_feat))
+        if _cols is not None:
+            if _buffers is None or _phases != 2:
+                raise RuntimeError(f"{fn}: _cols needs _phases=2 and _buffers")
+            c0, nc = int(_cols[0]), int(_cols[1])
+            rc = _lib.lib().dfgnn_gat_backward_cols(c0, nc, int(_cols[2]) if len(_cols) > 2 else -1, *tail)
+        else:
+            rc = _lib.lib().dfgnn_gat_backward_phase(int(_phases), *tail)
     _lib.check(rc, fn)
     if _buffers is None and _phases != 3:
         return [gf, gr, gc, ge]

@@ -117,6 +117,9 @@ int dfgnn_gt_hyper_forward(int m, int nnz, int h, int f, const int32_t *row_ptr,
  * kernel; the reference's scratch is torch::empty({h, nnz}), l.250).  m = rows (row_ptr, Q, grad_out, grad_Q),
  * n = columns (col_ptr, K, V, grad_K, grad_V); the reference reads both sizes too
  * (fused_gtconv_backward.cu:238-239) and they are equal for a square adjacency.
+ * `val` (NULL == all ones) weights the scores as in the forward: grad_Q and grad_K carry the
+ * factor val_e.  (The reference's backward ignores val, fused_gtconv_backward.cu:126, which is
+ * the same thing for the all-ones val its preprocessing produces.)
  */
 int dfgnn_gt_backward(int m, int n, int nnz, int h, int f, const int32_t *row_ptr,
                       const int32_t *col_ind, const int32_t *rows, const float *val,
@@ -137,6 +140,21 @@ int dfgnn_gt_backward_phase(int phases, int m, int n, int nnz, int h, int f,
                             const float *K, const float *V, const float *attn_edge,
                             const float *grad_out, float *grad_Q, float *grad_K, float *grad_V,
                             float *grad_edge, void *stream);
+
+/*
+ * Column side only, restricted to columns [col_begin, col_begin + n_sub) of the n columns:
+ * writes grad_K / grad_V rows of that range (pointers are the FULL arrays).  nnz_sub = entries
+ * of those columns (schedule heuristics; < 0: unknown).  Used by the row-partitioned multi-GPU
+ * operator (dfgnn_b200/dist.py) to reduce-scatter one column chunk while the next is computed;
+ * no reference counterpart (the reference is single-GPU).
+ */
+int dfgnn_gt_backward_cols(int col_begin, int n_sub, int nnz_sub, int m, int n, int nnz, int h,
+                           int f, const int32_t *row_ptr, const int32_t *col_ind,
+                           const int32_t *rows, const float *val, const int32_t *col_ptr,
+                           const int32_t *row_ind, const int32_t *val_idx, int smem_consume,
+                           const float *Q, const float *K, const float *V,
+                           const float *attn_edge, const float *grad_out, float *grad_Q,
+                           float *grad_K, float *grad_V, float *grad_edge, void *stream);
 
 /*
  * Inference entry points; all compute the same function, the name selects the
@@ -226,6 +244,17 @@ int dfgnn_gat_backward_phase(int phases, int m, int n, int nnz, int h, int f,
                              const float *attn_col, const float *grad_out, float *grad_feat,
                              float *grad_attn_row, float *grad_attn_col, float *grad_edge,
                              void *stream);
+
+/* Column side on columns [col_begin, col_begin + n_sub) only; see dfgnn_gt_backward_cols. */
+int dfgnn_gat_backward_cols(int col_begin, int n_sub, int nnz_sub, int m, int n, int nnz, int h,
+                            int f, float negative_slope, float attn_drop,
+                            const int32_t *row_ptr, const int32_t *col_ind,
+                            const int32_t *col_ptr, const int32_t *row_ind,
+                            const int32_t *permute, const float *edge_max,
+                            const float *edge_sum, const float *edge_mask, const float *in_feat,
+                            const float *attn_row, const float *attn_col, const float *grad_out,
+                            float *grad_feat, float *grad_attn_row, float *grad_attn_col,
+                            float *grad_edge, void *stream);
 
 /*
  * Inference entry points (one function, several schedule names).  Replace

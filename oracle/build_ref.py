@@ -64,8 +64,33 @@ def built() -> bool:
     )
 
 
+OPERATOR_FILES = ("fused_gtconv.py", "fused_gatconv.py")
+
+
+def stage_operators() -> bool:
+    """Place the reference's UNMODIFIED Python operator files (DFGNN/operators/*.py) next to the
+    compiled extensions, under the git-ignored oracle/_ref/operators/, so that the GPU box (which
+    has no /root/reference) can run them against the drop-in shim of integration/
+    (tests/test_integration_gpu.py).  Byte-for-byte copies, never committed."""
+    import shutil
+    src_dir = os.path.join(REF_ROOT, "DFGNN", "operators")
+    if not os.path.isdir(src_dir):
+        return operators_staged()
+    dst_dir = os.path.join(OUT, "operators")
+    os.makedirs(dst_dir, exist_ok=True)
+    for f in OPERATOR_FILES:
+        shutil.copyfile(os.path.join(src_dir, f), os.path.join(dst_dir, f))
+    return operators_staged()
+
+
+def operators_staged() -> bool:
+    return all(os.path.exists(os.path.join(OUT, "operators", f)) for f in OPERATOR_FILES)
+
+
 def build(verbose: bool = False) -> bool:
     """Compile both reference extensions.  Returns True when both .so exist."""
+    if have_reference():
+        stage_operators()
     if built():
         return True
     if not have_reference():

@@ -28,11 +28,11 @@ def _worker(rank, world, port, kind, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        g = graphs.arxiv_like(0.01) if kind == "row" else graphs.pattern_like(batch=5)
+        g = graphs.arxiv_like(0.01) if kind.startswith("row") else graphs.pattern_like(batch=5)
         n, dim = g.num_nodes(), 16
         X = graphs.conv_inputs(n, dim, 5)
-        part = ddist.make_partition(g, world, rank)
-        assert part.kind == ("row" if kind == "row" else "by-graph")
+        part = ddist.make_partition(g, world, rank, chunks=3 if kind == "row-chunked" else 1)
+        assert part.kind == ("row" if kind.startswith("row") else "by-graph")
         halo = ddist.HaloExchange(part, "cpu", world)
         lg = part.local_graph
         src, dst = lg.edges()
@@ -93,11 +93,11 @@ def _rect_backward(rp, ci, cp, ri, vi, Q, K, V, attn, dO, n_cols):
     return dQ, dK, dV
 
 
-@pytest.mark.parametrize("kind", ["row", "by-graph"])
+@pytest.mark.parametrize("kind", ["row", "row-chunked", "by-graph"])
 def test_two_rank_partition_matches_single_process(tmp_path, kind):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), kind, str(tmp_path)), nprocs=world, join=True)
-    g = graphs.arxiv_like(0.01) if kind == "row" else graphs.pattern_like(batch=5)
+    g = graphs.arxiv_like(0.01) if kind.startswith("row") else graphs.pattern_like(batch=5)
     n = g.num_nodes()
     X = graphs.conv_inputs(n, 16, 5)
     src, dst = g.edges()
@@ -128,3 +128,57 @@ def test_row_bounds_balance_edges():
     src, dst = part.local_graph.edges()
     assert int(dst.max()) < part.n_cols == 4 * part.max_rows
     assert part.local_graph.num_nodes() == part.n_rows == part.row_slice.stop - part.row_slice.start
+
+
+def _autograd_worker(rank, world, port, chunks, out_dir):
+    """HaloExchange.gather is differentiable: its backward is the reduce-scatter."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = graphs.arxiv_like(0.01)
+        n = g.num_nodes()
+        part = ddist.make_partition(g, world, rank, chunks=chunks)
+        halo = ddist.HaloExchange(part, "cpu", world)
+        gen = torch.Generator().manual_seed(11)
+        X = torch.randn(n, 2, 4, generator=gen, dtype=torch.float64)
+        a = torch.randn(n, 2, generator=gen, dtype=torch.float64)
+        W = torch.randn(world, part.n_cols, 2, 4, generator=gen, dtype=torch.float64)  # per-rank loss weights
+        x_own = X[part.col_owned].clone().requires_grad_()
+        a_pad = halo.pad(a[part.col_owned].clone()).requires_grad_()  # an operand given already padded
+        Xg, ag = halo.gather(x_own, a_pad)
+        idx = part.padded_index(torch.arange(n))
+        assert torch.equal(Xg[idx], X) and torch.equal(ag[idx], a)
+        ((Xg * W[rank]).sum() + (ag * W[rank][:, :, 0]).sum()).backward()
+        want_x = W.sum(0)[idx][part.col_owned]
+        want_a = W.sum(0)[:, :, 0][idx][part.col_owned]
+        assert x_own.grad.shape == x_own.shape and a_pad.grad.shape == a_pad.shape
+        assert torch.allclose(x_own.grad, want_x, rtol=1e-12, atol=1e-12)
+        assert torch.allclose(a_pad.grad[: part.n_rows], want_a, rtol=1e-12, atol=1e-12)
+        assert float(a_pad.grad[part.n_rows:].abs().sum()) == 0.0
+        open(os.path.join(out_dir, f"ok{rank}"), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("chunks", [1, 2])
+def test_halo_gather_backward_is_the_reduce_scatter(tmp_path, chunks):
+    world = 2
+    mp.spawn(_autograd_worker, args=(world, _free_port(), chunks, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+def test_padded_index_is_a_bijection_onto_the_owned_slots():
+    g = graphs.arxiv_like(0.02)
+    n = g.num_nodes()
+    for world, chunks in ((2, 1), (4, 2), (8, 4)):
+        parts = [ddist.make_partition(g, world, r, chunks=chunks) for r in range(world)]
+        p0 = parts[0]
+        idx = p0.padded_index(torch.arange(n))
+        assert idx.unique().numel() == n and int(idx.max()) < p0.n_cols == world * p0.max_rows
+        assert p0.max_rows % chunks == 0
+        q = p0.q
+        for r, p in enumerate(parts):
+            own = idx[p.col_owned]
+            loc = torch.arange(p.n_rows)
+            assert torch.equal(own, (loc // q) * (world * q) + r * q + loc % q)
+            assert torch.equal(p.padded_index(torch.arange(n)), idx)

@@ -91,6 +91,15 @@ def test_format_rejects_bad_input(cuda):
         formats.coo_to_csr(torch.tensor([0, 5], device=cuda), torch.tensor([1, 1], device=cuda), 3)
     with pytest.raises(RuntimeError, match="CUDA"):
         formats.coo_to_csr(torch.tensor([0]), torch.tensor([0]), 3)
+    # a CSR whose column ids do not fit the stated column count (a shard handed the wrong n_cols)
+    rp = torch.tensor([0, 2, 3], dtype=torch.int32, device=cuda)
+    ci = torch.tensor([0, 9, 1], dtype=torch.int32, device=cuda)
+    with pytest.raises(RuntimeError, match="column index outside"):
+        formats.csr_to_csc(rp, ci, 4)
+    with pytest.raises(RuntimeError, match="column index outside"):
+        formats.csr_to_csc(rp, torch.tensor([0, -1, 1], dtype=torch.int32, device=cuda), 4)
+    cp, ri, vi = formats.csr_to_csc(rp, ci, 10)   # fine once the column count is right
+    assert cp.tolist() == [0, 1, 2, 2, 2, 2, 2, 2, 2, 2, 3] and ri.tolist() == [0, 1, 0] and vi.tolist() == [0, 2, 1]
 
 
 def test_full_size_arxiv_and_pattern_properties(cuda):

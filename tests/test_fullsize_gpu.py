@@ -215,3 +215,75 @@ def test_gt_batched_full_size_vs_reference_kernels(cuda, name):
     ref_g = ref.gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, hs, Q, K, V, r_attn, dO)
     for nm, a, b in zip(("grad_Q", "grad_K", "grad_V"), mine_g, ref_g):
         assert_close_bulk(nm, a, b)
+
+
+# --------------------------------------------------------------------------- #
+# BASELINE.json config 4: the reddit-shaped super-node graph at full size        #
+# (232 965 nodes, 114.6 M edges, d = 128; long-row layout of the GT kernels)     #
+# --------------------------------------------------------------------------- #
+
+def _gt_reference_chunked(row_ptr, col_ind, Q, K, V, dO, rows_per_chunk=4096):
+    """fp64 restatement of GT forward + backward on the device, row block by row block (the
+    whole edge set at once would need E x d x 8 B = 117 GB per gathered operand)."""
+    n, d = Q.shape[0], Q.shape[2]
+    dev = Q.device
+    Qd, Kd, Vd, Gd = (t[:, 0].double() for t in (Q, K, V, dO))
+    out = torch.zeros(n, d, dtype=torch.float64, device=dev)
+    dQ = torch.zeros_like(out)
+    dK = torch.zeros(K.shape[0], d, dtype=torch.float64, device=dev)
+    dV = torch.zeros_like(dK)
+    attn = torch.empty(col_ind.numel(), dtype=torch.float64, device=dev)
+    rp = row_ptr.long()
+    for r0 in range(0, n, rows_per_chunk):
+        r1 = min(n, r0 + rows_per_chunk)
+        e0, e1 = int(rp[r0]), int(rp[r1])
+        if e1 == e0:
+            continue
+        deg = rp[r0 + 1:r1 + 1] - rp[r0:r1]
+        r = torch.repeat_interleave(torch.arange(r1 - r0, device=dev), deg)
+        c = col_ind[e0:e1].long()
+        Kc, Vc = Kd[c], Vd[c]
+        p = _softmax_rows((Qd[r0:r1][r] * Kc).sum(-1), r, r1 - r0)
+        attn[e0:e1] = p
+        out[r0:r1].index_add_(0, r, p[:, None] * Vc)
+        g = Gd[r0:r1][r]
+        dA = (g * Vc).sum(-1)
+        t = p * dA
+        s = torch.zeros(r1 - r0, dtype=torch.float64, device=dev).index_add_(0, r, t)
+        dS = t - s[r] * p
+        dQ[r0:r1].index_add_(0, r, dS[:, None] * Kc)
+        dK.index_add_(0, c, dS[:, None] * Qd[r0:r1][r])
+        dV.index_add_(0, c, p[:, None] * g)
+    return out, attn, dQ, dK, dV
+
+
+def test_gt_reddit_full_size(cuda):
+    """Forward against the reference's own tiling kernel (gt_tiling_inference, the format config 4
+    names; fused_gtconv.cpp:244-276) and forward + backward against the chunked fp64 restatement."""
+    g = graphs.reddit_like()
+    n = g.num_nodes()
+    assert g.num_edges() > 110_000_000
+    A, rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx, smem = preprocess_Hyper_fw_bw(g.to(cuda))
+    del A
+    X = graphs.conv_inputs(n, 128, 1004)
+    Q, K, V, dO = (t.to(cuda) for t in (X.Q, X.K, X.V, X.dO))
+    out, attn = N.gt_hyper_forward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V)
+    inf = N.gt_tiling_inference(row_ptr, col_ind, val, 128, Q, K, V)[0]
+    assert torch.equal(inf, out)  # every GT entry point is the same kernel
+    if ref_gpu.available():
+        r_out = ref_gpu.fused_gtconv().gt_tiling_inference(row_ptr, col_ind, val, 128, Q, K, V)[0]
+        assert_close_bulk("out vs reference gt_tiling_inference", out, r_out)
+        del r_out
+    gq, gk, gv = N.gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V, attn, dO)
+    ro, rp_, rq, rk, rv = _gt_reference_chunked(row_ptr, col_ind, Q, K, V, dO)
+    assert_close_bulk("out", out[:, 0], ro)
+    assert_close_bulk("attn_edge", attn[0], rp_)
+    assert_close_bulk("grad_Q", gq[:, 0], rq)
+    assert_close_bulk("grad_K", gk[:, 0], rk)
+    assert_close_bulk("grad_V", gv[:, 0], rv)
+    # size-independent properties
+    r, deg = _rows_of(row_ptr)
+    rowsum = torch.zeros(n, dtype=torch.float64, device=cuda).index_add(0, r, attn[0].double())
+    assert_close("attn_edge row sums", rowsum, (deg > 0).double())
+    assert_close("sum_j dV_j == sum_i dO_i over rows with edges", gv.double().sum(0),
+                 (dO.double() * (deg > 0)[:, None, None]).sum(0), rtol=1e-4, atol=1e-3)

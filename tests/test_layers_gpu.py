@@ -53,26 +53,128 @@ def test_agnn_literal_two_step_path(cuda):
     assert_close("agnn fused-normalize vs F.normalize + GT op", fused, literal)
 
 
-@pytest.mark.parametrize("heads", [1, 2])
+def _head_major_rows(out_size, heads):
+    """Row permutation of a projection weight that turns the fused branch's [N, heads, head_dim]
+    split of the projection output into the non-fused branch's [N, head_dim, heads] split
+    (gtconv_layer_forward.py:22-26 vs 46-50): nonfused row d * heads + h  <-  fused row h * hd + d."""
+    hd = out_size // heads
+    o2 = torch.arange(out_size)
+    return (o2 % heads) * hd + o2 // heads
+
+
+@pytest.mark.parametrize("heads", [1, 2, 4])
 def test_gt_training_gradients_match_autograd(cuda, heads):
+    """Layer-level gradients of the fused training branch (our kernels) against autograd through
+    the non-fused DGL-sparse restatement.  The two branches split the projection output into
+    heads differently, so the non-fused layer gets the fused layer's weights with permuted rows:
+    both then compute the same function and the weight gradients must agree row for row."""
+    import copy
     torch.manual_seed(1)
     g = graphs.pascalvoc_like(batch=3).to(cuda)
     params = preprocess_Hyper_fw_bw(g)
-    layer = SparseMHA_forward(64, 64, heads).to(cuda).train()
+    fused = SparseMHA_forward(64, 64, heads).to(cuda).train()
+    plain = copy.deepcopy(fused)
+    perm = _head_major_rows(64, heads).to(cuda)
+    with torch.no_grad():
+        for name in ("q_proj", "k_proj", "v_proj"):
+            getattr(plain, name).weight.copy_(getattr(fused, name).weight[perm])
+            getattr(plain, name).bias.copy_(getattr(fused, name).bias[perm])
     x = torch.randn(g.num_nodes(), 64, device=cuda)
     w = torch.randn(g.num_nodes(), 64, device=cuda)
+    out_f = fused(params, x, fuse=True)                      # [N, heads * hd]
+    out_p = plain(params, x, fuse=False)                     # [N, hd * heads]
+    out_p = out_p.reshape(-1, 64 // heads, heads).transpose(1, 2).reshape(-1, 64)
+    assert_close("layer out", out_f, out_p, rtol=1e-3, atol=1e-5)
+    (out_f * w).sum().backward()
+    (out_p * w).sum().backward()
+    for name in ("q_proj", "k_proj", "v_proj"):
+        gf, gp = getattr(fused, name).weight.grad, getattr(plain, name).weight.grad
+        assert_close(f"{name}.weight.grad (heads={heads})", gf[perm], gp, rtol=1e-3, atol=1e-4)
+        bf, bp = getattr(fused, name).bias.grad, getattr(plain, name).bias.grad
+        assert_close(f"{name}.bias.grad (heads={heads})", bf[perm], bp, rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("heads", [1, 2])
+def test_gt_function_grads_multi_head_fp64(cuda, heads):
+    """dQ / dK / dV of FusedGTFunction_hyper for h >= 1 against fp64 autograd (the reference's own
+    backward is only defined for h == 1, SURVEY.md 8a notes)."""
+    g = graphs.pattern_like(batch=3).to(cuda)
+    A, rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx, smem = preprocess_Hyper_fw_bw(g)
+    n = g.num_nodes()
+    torch.manual_seed(7)
+    Q = (torch.randn(n, heads, 32, device=cuda) * 32 ** -0.5).requires_grad_()
+    K = torch.randn(n, heads, 32, device=cuda, requires_grad=True)
+    V = torch.randn(n, heads, 32, device=cuda, requires_grad=True)
+    out = GTConvFuse_hyper(rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx, smem, Q, K, V)
+    dO = torch.randn_like(out)
+    out.backward(dO)
+    Qd, Kd, Vd = (t.detach().double().requires_grad_() for t in (Q, K, V))
+    r, c = A.row.long(), A.col.long()
+    s = (Qd[r] * Kd[c]).sum(-1)
+    mx = torch.full((n, heads), -1e300, dtype=torch.float64, device=cuda).scatter_reduce(
+        0, r[:, None].expand(-1, heads), s, "amax")
+    ex = torch.exp(s - mx[r])
+    p = ex / torch.zeros(n, heads, dtype=torch.float64, device=cuda).index_add(0, r, ex)[r]
+    ref = torch.zeros_like(Vd).index_add(0, r, p[:, :, None] * Vd[c])
+    ref.backward(dO.double())
+    assert_close("out", out, ref)
+    assert_close("dQ", Q.grad, Qd.grad)
+    assert_close("dK", K.grad, Kd.grad)
+    assert_close("dV", V.grad, Vd.grad)
+
+
+def test_agnn_backward_matches_oracle_and_autograd(cuda):
+    """AGNN training: the GT Function fed Q = K = normalize(H), V = H
+    (layers/AGNN/agnn_layer_forward.py:8-66).  (i) dQ, dK, dV of the conv against the fp64 CPU
+    oracle on the normalised inputs; (ii) the gradient w.r.t. H through F.normalize against fp64
+    autograd of the whole AGNN maths; (iii) the module's weight gradient, fused vs non-fused."""
+    import numpy as np
+    from oracle import cpu_oracle as O
+    torch.manual_seed(5)
+    g = graphs.pattern_like(batch=3)
+    gd = g.to(cuda)
+    params = preprocess_Hyper_fw_bw(gd)
+    A, rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx, smem = params
+    n = g.num_nodes()
+    H = torch.randn(n, 1, 64, device=cuda, requires_grad=True)
+    Hn = torch.nn.functional.normalize(H, p=2, dim=-1)
+    Hn.retain_grad()
+    Hv = H.clone()
+    Hv.retain_grad()
+    out = GTConvFuse_hyper(rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx, smem, Hn, Hn, Hv)
+    dO = torch.randn_like(out)
+    out.backward(dO)
+    # (i) conv gradients vs the oracle: dQ + dK arrive summed in Hn.grad
+    rp, ci = row_ptr.cpu().numpy(), col_ind.cpu().numpy()
+    cp, ri, vi = col_ptr.cpu().numpy(), row_ind.cpu().numpy(), val_idx.cpu().numpy()
+    Hn_c, H_c, dO_c = Hn.detach().cpu(), H.detach().cpu(), dO.cpu()
+    o64, a64 = O.gt_forward(rp, ci, None, Hn_c, Hn_c, H_c, dtype=np.float64)
+    dQ, dK, dV, _ = O.gt_backward(rp, ci, cp, ri, vi, Hn_c, Hn_c, H_c, a64, dO_c, dtype=np.float64)
+    assert_close("agnn out", out, o64)
+    assert_close("agnn dQ + dK", Hn.grad, dQ + dK)
+    assert_close("agnn dV", Hv.grad, dV)
+    # (ii) full chain vs fp64 autograd
+    Hd = H.detach().double().requires_grad_()
+    Hnd = torch.nn.functional.normalize(Hd, p=2, dim=-1)
+    r, c = A.row.long(), A.col.long()
+    s = (Hnd[r] * Hnd[c]).sum(-1)
+    mx = torch.full((n, 1), -1e300, dtype=torch.float64, device=cuda).scatter_reduce(0, r[:, None], s, "amax")
+    ex = torch.exp(s - mx[r])
+    p = ex / torch.zeros(n, 1, dtype=torch.float64, device=cuda).index_add(0, r, ex)[r]
+    ref = torch.zeros_like(Hd).index_add(0, r, p[:, :, None] * Hd[c])
+    ref.backward(dO.double())
+    assert_close("agnn dH", H.grad, Hd.grad)
+    # (iii) module level
+    agnn = AGNNConv_forward(64, 64, 1).to(cuda).train()
+    x = torch.randn(n, 64, device=cuda)
+    w = torch.randn(n, 64, device=cuda)
     grads = []
-    for fuse in (False, True):
-        layer.zero_grad()
-        out = layer(params, x, fuse=fuse)
-        if heads > 1 and not fuse:
-            # non-fused layout is [N, d, nh]; fused is [N, nh, d] (gtconv_layer_forward.py:22-26)
-            out = out.reshape(-1, 64 // heads, heads).transpose(1, 2).reshape(-1, 64)
-        (out * w).sum().backward()
-        grads.append([p.grad.clone() for p in (layer.q_proj.weight, layer.k_proj.weight, layer.v_proj.weight)])
-    if heads == 1:
-        for name, a, b in zip("qkv", grads[1], grads[0]):
-            assert_close(f"{name}_proj.weight.grad", a, b, rtol=1e-3, atol=1e-4)
+    for fuse in (True, False):
+        agnn.zero_grad()
+        (agnn(params, x, fuse=fuse) * w).sum().backward()
+        grads.append((agnn.proj.weight.grad.clone(), agnn.proj.bias.grad.clone()))
+    assert_close("agnn proj.weight.grad", grads[0][0], grads[1][0], rtol=1e-3, atol=1e-4)
+    assert_close("agnn proj.bias.grad", grads[0][1], grads[1][1], rtol=1e-3, atol=1e-4)
 
 
 def test_gt_function_signature_and_grads(cuda):

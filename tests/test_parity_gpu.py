@@ -421,3 +421,63 @@ def test_backward_phases_and_graph_capture(cuda):
     torch.cuda.synchronize()
     for a, b in zip(res, [out] + ref):
         assert torch.equal(a, b)
+
+
+# --------------------------------------------------------------------------- #
+# weighted scores (val != 1): forward AND backward carry val                    #
+# --------------------------------------------------------------------------- #
+
+@pytest.mark.parametrize("gname,dim", [("arxiv", 64), ("pattern", 128), ("holes+super", 32)])
+def test_gt_weighted_scores_forward_and_backward(cuda, gname, dim):
+    """s_e = <Q_i, K_j> * val_e.  The reference's forward multiplies by val
+    (fused_gtconv_hyper.cu:89) and its backward drops it (fused_gtconv_backward.cu:126), which is
+    only consistent for val == 1; here both directions carry val, checked against fp64 autograd."""
+    c = _case(gname, dim)
+    d = to_dev(c, cuda)
+    gen = torch.Generator().manual_seed(5)
+    val = (0.5 + torch.rand(c["nnz"], generator=gen)).to(cuda)
+    out, attn = N.gt_hyper_forward(d["row_ptr"], d["col_ind"], d["rows"], val, d["col_ptr"],
+                                   d["row_ind"], d["val_idx"], 1024, d["Q"], d["K"], d["V"])
+    gq, gk, gv = N.gt_backward(d["row_ptr"], d["col_ind"], d["rows"], val, d["col_ptr"],
+                               d["row_ind"], d["val_idx"], 1024, d["Q"], d["K"], d["V"], attn, d["dO"])
+    n = c["n"]
+    r = torch.from_numpy(np.repeat(np.arange(n), np.diff(c["row_ptr"]))).to(cuda)
+    col = d["col_ind"].long()
+    Qd, Kd, Vd = (d[k][:, 0].double().requires_grad_() for k in ("Q", "K", "V"))
+    s = (Qd[r] * Kd[col]).sum(-1) * val.double()
+    mx = torch.full((n,), -1e300, dtype=torch.float64, device=cuda).scatter_reduce(0, r, s, "amax")
+    ex = torch.exp(s - mx[r])
+    p = ex / torch.zeros(n, dtype=torch.float64, device=cuda).index_add(0, r, ex)[r]
+    ref = torch.zeros_like(Vd).index_add(0, r, p[:, None] * Vd[col])
+    ref.backward(d["dO"][:, 0].double())
+    assert_close("out", out[:, 0], ref.detach())
+    assert_close("attn_edge", attn[0], p.detach())
+    assert_close("grad_Q", gq[:, 0], Qd.grad)
+    assert_close("grad_K", gk[:, 0], Kd.grad)
+    assert_close("grad_V", gv[:, 0], Vd.grad)
+    # the all-ones tensor of the preprocessing is recognised and skips the weight loads: same numbers
+    ones = torch.ones_like(val)
+    o1, a1 = N.gt_hyper_forward(d["row_ptr"], d["col_ind"], d["rows"], ones, d["col_ptr"], d["row_ind"],
+                                d["val_idx"], 1024, d["Q"], d["K"], d["V"])
+    ones._dfgnn_ones = True
+    o2, a2 = N.gt_hyper_forward(d["row_ptr"], d["col_ind"], d["rows"], ones, d["col_ptr"], d["row_ind"],
+                                d["val_idx"], 1024, d["Q"], d["K"], d["V"])
+    assert torch.equal(o1, o2) and torch.equal(a1, a2)
+
+
+def test_empty_graph_returns_empty_tensors(cuda):
+    """m == 0: every entry point returns without touching its (NULL) operands."""
+    z = lambda *s, dt=torch.float32: torch.zeros(s, dtype=dt, device=cuda)
+    rp = z(1, dt=torch.int32)
+    e = z(0, dt=torch.int32)
+    Q = z(0, 1, 64)
+    out, attn = N.gt_hyper_forward(rp, e, e, z(0), rp, e, e, 1024, Q, Q, Q)
+    assert out.shape == (0, 1, 64) and attn.shape == (1, 0)
+    gq, gk, gv = N.gt_backward(rp, e, e, z(0), rp, e, e, 1024, Q, Q, Q, attn, Q)
+    assert gq.shape == gk.shape == gv.shape == (0, 1, 64)
+    o, emax, esum, emask = N.gat_forward(z(0, 1), z(0, 1), rp, e, 0.2, Q, 0.0)
+    assert o.shape == (0, 1, 64) and emax.shape == (0, 1)
+    gf, gr, gc = N.gat_backward(0.2, 0.0, rp, e, rp, e, e, emax, esum, emask, Q, z(0, 1), z(0, 1), Q)
+    assert gf.shape == (0, 1, 64) and gr.shape == gc.shape == (0, 1)
+    assert N.gat_inference(z(0, 1), z(0, 1), rp, e, 0.2, Q).shape == (0, 1, 64)
+    assert N.agnn_forward(rp, e, Q).shape == (0, 1, 64)

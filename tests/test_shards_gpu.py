@@ -1,0 +1,203 @@
+"""Row-partitioned (rectangular) shards through the CUDA kernels.
+
+A shard of a 1-D row partition is an n_rows_local x (world * max_rows) matrix whose column ids
+live in the padded gathered space of dfgnn_b200/dist.py.  Two levels:
+
+* one GPU, every rank's shard in turn: the halo all-gather is emulated by scattering the global
+  operands into the padded buffer (``Partition.padded_index``), the reduce-scatter by summing the
+  ranks' column-side partial gradients -- stitched out / dQ / dK / dV (GT) and out / grad_feat /
+  grad_attn_row / grad_attn_col (GAT) must match the fp64 CPU oracle of the FULL graph and the
+  single-shard CUDA result;
+* two GPUs over NCCL (skipped on a one-GPU box): the public distributed operators
+  ``GTConvFuse_hyper_dist`` / ``GATConvFuse_dist`` under autograd against the same references.
+
+Tolerance 1e-4 relative / 1e-5 absolute (BASELINE.json north_star)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from dfgnn_b200 import dist as ddist
+from dfgnn_b200 import graphs
+from dfgnn_b200.layers import preprocess_gat_fw_bw, preprocess_Hyper_fw_bw
+from dfgnn_b200.operators import _native as N
+from oracle import cpu_oracle as O
+
+from .helpers import assert_close, make_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _graph(kind):
+    if kind == "arxiv":      # mean degree 6.9: staged GAT schedule, sparse columns per shard
+        return graphs.arxiv_like(0.05)
+    if kind == "reddit":     # mean degree ~49: row-block schedule
+        return graphs.reddit_like(0.1)
+    if kind == "long":       # mean degree 300 (> 128): the long-row layout of the GT kernels
+        return graphs.full_graph(2000, 600000, 300.0, 120.0, 1, 1999, 77, "long-rows")
+    raise KeyError(kind)
+
+
+def _oracle(case, conv, dim):
+    X = case["X"]
+    rp, ci, cp, ri, vi = (case[k] for k in ("row_ptr", "col_ind", "col_ptr", "row_ind", "val_idx"))
+    if conv == "gt":
+        out, attn = O.gt_forward(rp, ci, None, X.Q, X.K, X.V, dtype=np.float64)
+        dQ, dK, dV, _ = O.gt_backward(rp, ci, cp, ri, vi, X.Q, X.K, X.V, attn, X.dO, dtype=np.float64)
+        return dict(out=out, g_row=dQ, g_col_a=dK, g_col_b=dV)
+    out, emax, esum = O.gat_forward(X.attn_row, X.attn_col, rp, ci, 0.2, X.V, dtype=np.float64)
+    gf, gr, gc = O.gat_backward(0.2, 0.0, rp, ci, cp, ri, vi, emax, esum, None, X.V, X.attn_row,
+                                X.attn_col, X.dO, dtype=np.float64)
+    return dict(out=out, g_row=gr, g_col_a=gf, g_col_b=gc)
+
+
+def _run_shard(part, conv, X, dev, chunked_cols):
+    """The CUDA kernels on one rectangular shard with emulated gathered operands.
+    Returns out, row-side grad, and the two column-side partial grads over the padded columns."""
+    n = X.Q.shape[0]
+    idx = part.padded_index(torch.arange(n)).to(dev)
+    g = part.local_graph.to(dev)
+    rs = part.row_slice
+
+    def gathered(t):
+        buf = torch.zeros((part.n_cols,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+        buf[idx] = t.to(dev)
+        return buf
+
+    # column chunks exactly as DistGTFunction / DistGATFunction launch them
+    w = part.world * part.q
+    cols = [(c * w, w) for c in range(part.chunks)] if chunked_cols else [None]
+    dO = X.dO[rs].to(dev).contiguous()
+    if conv == "gt":
+        A, rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx, smem = preprocess_Hyper_fw_bw(g)
+        assert col_ptr.numel() == part.n_cols + 1 and row_ptr.numel() == part.n_rows + 1
+        Q, K, V = X.Q[rs].to(dev).contiguous(), gathered(X.K), gathered(X.V)
+        out, attn = N.gt_hyper_forward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V)
+        args = (row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V, attn, dO)
+        bufs = N.gt_backward(*args, _phases=1)
+        bufs[1].fill_(float("nan"))
+        bufs[2].fill_(float("nan"))  # every column must be written by the column-side launches
+        for c in cols:
+            N.gt_backward(*args, _phases=2, _buffers=bufs, _cols=c)
+        return out, bufs[0], bufs[1], bufs[2]
+    row_ptr, col_ind, col_ptr, row_ind, permute = preprocess_gat_fw_bw(g)
+    ar, ac, F = X.attn_row[rs].to(dev).contiguous(), gathered(X.attn_col), gathered(X.V)
+    out, emax, esum, emask = N.gat_forward(ar, ac, row_ptr, col_ind, 0.2, F, 0.0)
+    args = (0.2, 0.0, row_ptr, col_ind, col_ptr, row_ind, permute, emax, esum, emask, F, ar, ac, dO)
+    bufs = N.gat_backward(*args, _phases=1)
+    bufs[0].fill_(float("nan"))
+    bufs[2].fill_(float("nan"))
+    for c in cols:
+        N.gat_backward(*args, _phases=2, _buffers=bufs, _cols=c)
+    return out, bufs[1], bufs[0], bufs[2]
+
+
+@pytest.mark.parametrize("conv,dim", [("gt", 128), ("gat", 64)])
+@pytest.mark.parametrize("kind,world,chunks", [("arxiv", 2, 1), ("arxiv", 8, 2), ("reddit", 2, 2),
+                                               ("reddit", 8, 1), ("long", 4, 4)])
+def test_rectangular_shards_on_one_gpu(cuda, conv, dim, kind, world, chunks):
+    g = _graph(kind)
+    n = g.num_nodes()
+    case = make_case(g, dim, 31)
+    X = case["X"]
+    want = _oracle(case, conv, dim)
+    out = torch.empty((n, 1, dim), dtype=torch.float32, device=cuda)
+    g_row = torch.empty((n, 1, dim) if conv == "gt" else (n, 1), dtype=torch.float32, device=cuda)
+    acc_a = acc_b = None
+    idx = None
+    for r in range(world):
+        part = ddist.make_partition(g, world, r, chunks=chunks)
+        assert part.kind == "row" and part.n_cols == world * part.max_rows
+        o, gr, ga, gb = _run_shard(part, conv, X, cuda, chunked_cols=chunks > 1)
+        out[part.row_slice] = o
+        g_row[part.row_slice] = gr
+        assert bool(torch.isfinite(ga).all()) and bool(torch.isfinite(gb).all()), "unwritten columns"
+        acc_a = ga.double() if acc_a is None else acc_a + ga.double()   # the reduce-scatter's sum
+        acc_b = gb.double() if acc_b is None else acc_b + gb.double()
+        idx = part.padded_index(torch.arange(n)).to(cuda)
+        # padding columns have no entries: their partial gradients are exactly zero
+        pad = torch.ones(part.n_cols, dtype=torch.bool, device=cuda)
+        pad[idx] = False
+        assert float(ga[pad].abs().sum()) == 0.0 and float(gb[pad].abs().sum()) == 0.0
+    names = ("dQ", "dK", "dV") if conv == "gt" else ("d attn_row", "d feat", "d attn_col")
+    assert_close("out", out, want["out"])
+    assert_close(names[0], g_row, want["g_row"])
+    assert_close(names[1], acc_a[idx].float(), want["g_col_a"])
+    assert_close(names[2], acc_b[idx].float(), want["g_col_b"])
+
+
+# ----------------------------------------------------------------------------------------- #
+# two ranks over NCCL                                                                        #
+# ----------------------------------------------------------------------------------------- #
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _nccl_worker(rank, world, port, conv, dim, chunks, out_dir):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        g = graphs.reddit_like(0.1) if conv == "gt" else graphs.arxiv_like(0.05)
+        n = g.num_nodes()
+        X = graphs.conv_inputs(n, dim, 31)
+        part = ddist.make_partition(g, world, rank, chunks=chunks)
+        halo = ddist.HaloExchange(part, dev, world, record=True)
+        gl = part.local_graph.to(dev)
+        rs, own = part.row_slice, part.col_owned
+        dO = X.dO[rs].to(dev)
+        res = {}
+        for it in range(2):  # twice: buffers of the first step must not leak into the second
+            if conv == "gt":
+                A, rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx, smem = preprocess_Hyper_fw_bw(gl)
+                Q = X.Q[rs].to(dev).requires_grad_()
+                K = X.K[own].to(dev).requires_grad_()
+                V = halo.pad(X.V[own].to(dev)).requires_grad_()   # one operand given already padded
+                out = ddist.GTConvFuse_hyper_dist(halo, rows, row_ptr, col_ind, val, col_ptr, row_ind,
+                                                  val_idx, smem, Q, K, V)
+                out.backward(dO)
+                assert K.grad.shape == K.shape and V.grad.shape == V.shape
+                res = dict(out=out.detach(), g_row=Q.grad, g_col_a=K.grad, g_col_b=V.grad[: part.n_rows])
+            else:
+                row_ptr, col_ind, col_ptr, row_ind, permute = preprocess_gat_fw_bw(gl)
+                ar = X.attn_row[rs].to(dev).requires_grad_()
+                ac = X.attn_col[own].to(dev).requires_grad_()
+                F = X.V[own].to(dev).requires_grad_()
+                out = ddist.GATConvFuse_dist(halo, ar, ac, row_ptr, col_ind, col_ptr, row_ind, permute,
+                                             0.2, F, 0.0)
+                out.backward(dO)
+                res = dict(out=out.detach(), g_row=ar.grad, g_col_a=F.grad, g_col_b=ac.grad)
+        times = halo.pop_times()
+        assert times["allgather_ms"] > 0 and times["reduce_scatter_ms"] > 0
+        np.savez(os.path.join(out_dir, f"r{rank}.npz"), lo=rs.start, hi=rs.stop,
+                 **{k: v.cpu().numpy() for k, v in res.items()})
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("conv,dim,chunks", [("gt", 128, 1), ("gt", 128, 2), ("gat", 64, 2)])
+def test_two_rank_nccl_distributed_operators(cuda, tmp_path, conv, dim, chunks):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_nccl_worker, args=(world, _free_port(), conv, dim, chunks, str(tmp_path)), nprocs=world,
+             join=True)
+    g = graphs.reddit_like(0.1) if conv == "gt" else graphs.arxiv_like(0.05)
+    case = make_case(g, dim, 31)
+    want = _oracle(case, conv, dim)
+    covered = 0
+    for r in range(world):
+        z = np.load(tmp_path / f"r{r}.npz")
+        lo, hi = int(z["lo"]), int(z["hi"])
+        covered += hi - lo
+        for k in ("out", "g_row", "g_col_a", "g_col_b"):
+            assert_close(f"{conv} rank {r} {k}", z[k], want[k][lo:hi])
+    assert covered == g.num_nodes()
