@@ -3,24 +3,39 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
 
-One "step" is one fused conv forward + backward over one synthetic graph of the
-named workload (BASELINE.json configs; default = configs[1], GAT d=64 on the
-arxiv-shaped full graph).  Prints ONE JSON line (rank 0).
+One "step" is one fused conv forward + backward over one synthetic graph of the named
+workload (BASELINE.json configs).  Prints ONE JSON line (rank 0).
+
+Headline workload (when --workload is not given):
+  N = 1   arxiv-gat   BASELINE.json configs[1] (GAT d=64, arxiv-shaped full graph), the
+                      configuration the metric is quoted on;
+  N > 1   reddit-gt   BASELINE.json configs[3], ONE graph 1-D row-partitioned over the N ranks
+                      with the NCCL halo all-gather / reduce-scatter (strong scaling) -- the
+                      north-star multi-GPU partition.  Its own 1-GPU point is the `reddit-gt`
+                      entry of `workloads` in the N = 1 line.
+The other GPU workloads ride along in `workloads` (each in its north-star partition: arxiv-gat
+row-partitioned, pattern-gt one global batch sharded by graph, voc-gt 1024 graphs per GPU,
+reddit-gt row-partitioned), so that every line carries configs 2-5 at that N.
 
   value     edges*dim per second, inputs resident in HBM, CUDA-event timed per step,
-            L2 flushed between steps (a 256 MB write), max over ranks.
-  e2e       same metric through the public operator (dfgnn_b200.operators, i.e. the
-            reference's autograd-Function API) with HOST operands: every step copies the
-            node features / logits / upstream gradient from pinned host memory and reads
-            the output and the gradients back.  The graph index (CSR/CSC) is built once
-            and stays resident, like the reference's `params = preprocess_func(g)`.
-  roofline  the forward kernel: algorithmic bytes (SURVEY.md 8d gather model) / its
-            CUDA-event duration inside the timed steps, against MEASURED_PEAKS.json.
+            L2 flushed between steps (a 256 MB write), max over ranks; the step is replayed
+            from a CUDA graph (collectives included) so the region holds kernels, not Python.
+  e2e       same metric through the public operator (dfgnn_b200.operators / dfgnn_b200.dist:
+            the reference's autograd-Function API) with HOST operands: every step copies the
+            node features / logits / upstream gradient from pinned host memory and reads the
+            output and the gradients back.  The graph index (CSR/CSC) is built once and stays
+            resident, like the reference's `params = preprocess_func(g)`.
+  roofline  the slowest kernel of the step on its own: algorithmic bytes (SURVEY.md 8d gather
+            model) / its CUDA-event duration, against MEASURED_PEAKS.json; next to it the
+            compulsory bytes (every array once) and, from the committed ncu capture of the SAME
+            kernel sources (profiles/r02_traffic.json), the DRAM traffic and frac_dram.
   cpu_baseline   the CPU oracle (oracle/dfgnn_oracle.c, OpenMP) on the same workload.
-  gpu_reference  the reference's own CUDA kernels (oracle/_ref, sm_100a) timed the same way.
+  gpu_reference  the reference's own CUDA kernels (oracle/_ref, sm_100a): timed eagerly next to
+                 OUR step timed eagerly too (like for like), plus the graph-replay number.
 
-`--impl reference` times the reference's CPU path: dgl / PyG are not installable
-offline, so it is the oracle port (kind "port") on all host cores.
+`--impl reference` times the reference's CPU path: dgl / PyG are not installable offline, so it
+is the oracle port (kind "port") on all host cores.  `--profile` is the short, eager, conv-only
+run that tools/profile_r02.sh wraps in ncu.
 """
 from __future__ import annotations
 
@@ -39,6 +54,7 @@ if ROOT not in sys.path:
 
 METRIC = "fused_conv_fwd_bwd_edges_x_dim_per_s"
 UNIT = "edges*dim/s"
+TRAFFIC_FILE = os.path.join("profiles", "r02_traffic.json")
 
 WORKLOADS = {
     # name: (conv, dim, graph fn, kwargs, format, BASELINE.json config index)
@@ -49,6 +65,9 @@ WORKLOADS = {
     "cora-gt": ("gt", 128, "cora_like", {}, "hyper", 0),
 }
 SEEDS = {"arxiv-gat": 1002, "pattern-gt": 1003, "reddit-gt": 1004, "voc-gt": 1005, "cora-gt": 1001}
+GPU_WORKLOADS = ["arxiv-gat", "pattern-gt", "voc-gt", "reddit-gt"]
+# north-star partition of every workload at N > 1
+PARTITION = {"arxiv-gat": "row", "reddit-gt": "row", "cora-gt": "row", "pattern-gt": "by-graph", "voc-gt": "weak"}
 
 
 def alg_bytes(conv: str, phase: str, n: int, e: int, d: int) -> float:
@@ -74,12 +93,40 @@ def kernel_alg_bytes(conv: str, n: int, e: int, d: int) -> dict:
             "bwd_col": 4.0 * e * d + 4.0 * n * d + 16.0 * e + 8.0 * n}           # dO rows; grad_feat; row_ind, permute, {de,p}
 
 
+def kernel_compulsory_bytes(conv: str, n: int, nc: int, e: int, d: int) -> dict:
+    """Compulsory HBM bytes per kernel: every array the kernel touches counted ONCE (what an
+    infinite cache would still move).  n rows, nc columns."""
+    if conv == "gt":
+        return {"fwd": 4.0 * d * (2 * n + 2 * nc) + 8.0 * e + 4.0 * n,          # Q, out | K, V; col_ind, attn_edge; row_ptr
+                "bwd_row": 4.0 * d * (2 * n + 2 * nc) + 16.0 * e + 4.0 * n,     # dO, dQ | K, V; col_ind, attn, {dS,p} written
+                "bwd_col": 4.0 * d * (2 * n + 2 * nc) + 16.0 * e + 4.0 * nc}    # dO, Q | dK, dV; row_ind, val_idx, {dS,p} read
+    return {"fwd": 4.0 * d * (n + nc) + 4.0 * e + 12.0 * n + 4.0 * nc + 4.0 * n,  # out | feat; col_ind; ar, emax, esum; ac; row_ptr
+            "bwd_row": 4.0 * d * (n + nc) + 12.0 * e + 20.0 * n + 4.0 * nc,      # dO | feat; col_ind, {de,p} written; ar, emax, esum, d_ar, row_ptr; ac
+            "bwd_col": 4.0 * d * (n + nc) + 16.0 * e + 8.0 * nc}                 # dO | grad_feat; row_ind, permute, {de,p} read; d_ac, col_ptr
+
+
 def hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
             return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic():
+    """profiles/r02_traffic.json (written by tools/make_traffic.py from ncu captures of
+    `bench.py --profile`), only if it was taken from the kernel sources that are running."""
+    from dfgnn_b200 import _lib
+    try:
+        with open(os.path.join(ROOT, TRAFFIC_FILE)) as fh:
+            t = json.load(fh)
+    except Exception:
+        return {}, "no committed ncu capture (%s)" % TRAFFIC_FILE
+    if t.get("source_sha") != _lib.source_sha():
+        return {}, ("%s was captured from kernel sources %s, running %s: not reported"
+                    % (TRAFFIC_FILE, t.get("source_sha"), _lib.source_sha()))
+    return t.get("workloads", {}), ("ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, %s "
+                                    "(kernel sources %s)" % (TRAFFIC_FILE, t.get("source_sha")))
 
 
 class ClockSampler:
@@ -137,6 +184,10 @@ def build_graph(name: str, seed_offset: int = 0):
     return getattr(graphs, fn)(seed=SEEDS[name] + seed_offset, **kw)
 
 
+def default_workload(gpus: int) -> str:
+    return "arxiv-gat" if gpus <= 1 else "reddit-gt"
+
+
 # ----------------------------------------------------------------------------- #
 # reference arm: the CPU path (oracle port) on the host cores                    #
 # ----------------------------------------------------------------------------- #
@@ -175,6 +226,17 @@ def time_cpu(name: str, g, steps: int, warmup: int):
     return e * dim / dt, dt, n, e, dim
 
 
+def cpu_sample_graph(name: str):
+    """The bounded sample the CPU legs run: the full workload, except the reddit-shaped graph
+    (114 M edges), which is shrunk to scale 0.2 (4.6 M edges) so that a step takes about a second."""
+    if name == "reddit-gt":
+        from dfgnn_b200 import graphs
+        g = graphs.reddit_like(0.2)
+        return g, f"reddit-shaped graph at scale 0.2 (N={g.num_nodes()}, E={g.num_edges()})"
+    g = build_graph(name)
+    return g, f"full workload (N={g.num_nodes()}, E={g.num_edges()})"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -182,24 +244,18 @@ def run_reference(args):
     # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm runs on rank 0 alone and
     # may use all host cores (libgomp reads the variable when the oracle library is loaded)
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
-    name = args.workload
-    # bounded sample: the big workloads are shrunk so that K steps finish in minutes
-    scale = {"reddit-gt": 0.05}.get(name, 1.0)
-    if name == "reddit-gt":
-        from dfgnn_b200 import graphs
-        g = graphs.reddit_like(scale)
-        sample = f"reddit-shaped graph at scale {scale} (N={g.num_nodes()}, E={g.num_edges()})"
-    else:
-        g = build_graph(name)
-        sample = f"full workload (N={g.num_nodes()}, E={g.num_edges()})"
+    name = args.workload or default_workload(args.gpus)
+    g, sample = cpu_sample_graph(name)
     steps, warmup = max(1, args.steps), max(1, min(args.warmup, 3))
+    if name == "reddit-gt":
+        steps = min(steps, 10)
     val, dt, n, e, dim = time_cpu(name, g, steps, warmup)
     cores = os.cpu_count() or 1
     conv, _, _, _, fmt, cfg = WORKLOADS[name]
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "weak" if args.gpus <= 1 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": name, "conv": conv, "dim": dim, "format": fmt, "nodes": n, "edges": e,
                    "baseline_config_index": cfg},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
@@ -210,11 +266,27 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def cpu_baseline(name):
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    g, sample = cpu_sample_graph(name)
+    nsteps = 2 if name == "reddit-gt" else 3
+    val, dt, *_ = time_cpu(name, g, nsteps, 1)
+    return {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": sample + f", {nsteps} steps after 1 warm-up", "ms_per_step": dt * 1e3}
+
+
 # ----------------------------------------------------------------------------- #
 # our arm                                                                        #
 # ----------------------------------------------------------------------------- #
 
-def run_ours(args):
+class Env:
+    pass
+
+
+def measure(env, args, name: str, full: bool):
+    """One workload in its partition at env.world ranks.  `full`: headline (e2e, reference and CPU
+    legs, clocks); otherwise the compact record that goes into `workloads`."""
     import torch
     import torch.distributed as dist
 
@@ -224,203 +296,237 @@ def run_ours(args):
     from dfgnn_b200.operators import GATConvFuse, GTConvFuse_hyper
     from dfgnn_b200.operators import _native as N
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    rank, world, dev, local = env.rank, env.world, env.dev, env.local
+    conv, dim, fn, kw, fmt, cfg = WORKLOADS[name]
+    batched = "batch" in kw
+    steps = args.steps if full else max(3, min(args.steps, 10))
+    if args.profile:
+        steps = 2
 
-    def measure(mode: str, light: bool):
-        """One measurement in partition mode `mode` ("weak" | "strong" | "auto"); `light` skips
-        the e2e, per-kernel and baseline legs (used for the secondary row-partition numbers)."""
-        name = args.workload
-        conv, dim, fn, kw, fmt, cfg = WORKLOADS[name]
-        batched = "batch" in kw
-        weak = world > 1 and ((batched and mode != "strong") or mode == "weak")
-        # ---- partition (SURVEY.md 8e) ------------------------------------------------
+    # ---- partition ------------------------------------------------------
+    mode = PARTITION[name] if args.scaling == "auto" else \
+        ("weak" if args.scaling == "weak" else ("by-graph" if batched else "row"))
+    weak = world > 1 and mode == "weak"
+    chunks = args.chunks if args.chunks > 0 else 4
+    if world == 1 or weak:
+        g_full = build_graph(name, seed_offset=1000 * rank if weak else 0)
+        part = ddist.make_partition(g_full, 1, 0)
         if weak:
-            # data-parallel: every rank owns its own batch of graphs, no collective in the conv
-            g_full = build_graph(name, seed_offset=1000 * rank)
-            part = ddist.make_partition(g_full, 1, 0)
             part.describe = (f"{kw['batch']} graphs per GPU" if batched else "one graph per GPU") + \
                 f" on {world} GPUs (weak scaling), no collective"
-        else:
-            g_full = build_graph(name)
-            part = ddist.make_partition(g_full, world, rank)
-        n_total, e_total = g_full.num_nodes(), g_full.num_edges()
-        g = part.local_graph.to(dev)
-        n_rows, n_cols, e_local = part.n_rows, part.n_cols, part.local_graph.num_edges()
+    else:
+        g_full = build_graph(name)
+        part = ddist.make_partition(g_full, world, rank, mode=mode, chunks=chunks)
+    n_total, e_total = g_full.num_nodes(), g_full.num_edges()
+    g = part.local_graph.to(dev)
+    n_rows, n_cols, e_local = part.n_rows, part.n_cols, part.local_graph.num_edges()
+    sha = g_full.sha256()[:16] if (full or name != "reddit-gt") else None
+    halo = ddist.HaloExchange(part, dev, world)
 
-        X = graphs.conv_inputs(n_total, dim, SEEDS[name])
-        rows_sl = part.row_slice
-        pin = lambda t: t.contiguous().pin_memory()
-        if conv == "gt":
-            h_in = {"Q": pin(X.Q[rows_sl]), "K": pin(X.K[part.col_owned]), "V": pin(X.V[part.col_owned]),
-                    "dO": pin(X.dO[rows_sl])}
-        else:
-            h_in = {"ar": pin(X.attn_row[rows_sl]), "ac": pin(X.attn_col[part.col_owned]),
-                    "F": pin(X.V[part.col_owned]), "dO": pin(X.dO[rows_sl])}
-        d_in = {k: v.to(dev) for k, v in h_in.items()}
+    X = graphs.conv_inputs(n_total, dim, SEEDS[name])
+    rows_sl, own = part.row_slice, part.col_owned
+    del g_full
 
-        # resident index formats, built once by the CUDA format kernels
+    def col_side(t):
+        """this rank's slice of a column-side operand, already in the padded layout of the halo
+        exchange (no staging copy inside the step)"""
+        t = t[own].contiguous()
+        if halo.active:
+            p = torch.zeros((part.max_rows,) + tuple(t.shape[1:]), dtype=t.dtype)
+            p[: t.shape[0]] = t
+            t = p
+        return t.pin_memory()
+
+    pin = lambda t: t.contiguous().pin_memory()
+    if conv == "gt":
+        h_in = {"Q": pin(X.Q[rows_sl]), "K": col_side(X.K), "V": col_side(X.V), "dO": pin(X.dO[rows_sl])}
+    else:
+        h_in = {"ar": pin(X.attn_row[rows_sl]), "ac": col_side(X.attn_col), "F": col_side(X.V),
+                "dO": pin(X.dO[rows_sl])}
+    del X
+    d_in = {k: v.to(dev) for k, v in h_in.items()}
+
+    # resident index formats, built once by the CUDA format kernels
+    if conv == "gt":
+        A, rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx, smem = preprocess_Hyper_fw_bw(g)
+        del A
+    else:
+        row_ptr, col_ind, col_ptr, row_ind, val_idx = preprocess_gat_fw_bw(g)
+        rows = val = None
+        smem = 128
+    torch.cuda.synchronize()
+
+    # format construction (SURVEY.md 8a rows a1-a3) timed separately, like the reference's own
+    # `only_preprocess` loop (train_batch_graph_timing.py:115-143): COO -> CSR (+rows, val) -> CSC
+    fmt_ms = []
+    for _ in range(1 if args.profile else 5):
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
         if conv == "gt":
-            A, rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx, smem = preprocess_Hyper_fw_bw(g)
+            preprocess_Hyper_fw_bw(g)
         else:
-            row_ptr, col_ind, col_ptr, row_ind, val_idx = preprocess_gat_fw_bw(g)
-            rows = val = None
-            smem = 128
+            preprocess_gat_fw_bw(g)
+        b_.record()
+        b_.synchronize()
+        fmt_ms.append(a.elapsed_time(b_))
+    fmt_ms = sorted(fmt_ms)[len(fmt_ms) // 2]
+
+    flush = env.flush
+    gt_idx = (rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx, smem)
+    gat_idx = (row_ptr, col_ind, col_ptr, row_ind, val_idx)
+
+    def step_device():
+        """fwd + bwd on resident operands; returns the tensors a caller would keep.  Row-partitioned
+        shards go through the distributed operator's own forward / backward (dfgnn_b200/dist.py)."""
+        if conv == "gt":
+            if halo.active:
+                out, saved = ddist.dist_gt_forward(halo, *gt_idx, d_in["Q"], d_in["K"], d_in["V"])
+                gq, gk, gv = ddist.dist_gt_backward(halo, saved, smem, d_in["dO"])
+                return out, gq, gk, gv
+            out, attn = N.gt_hyper_forward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx,
+                                           smem, d_in["Q"], d_in["K"], d_in["V"])
+            gq, gk, gv = N.gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem,
+                                       d_in["Q"], d_in["K"], d_in["V"], attn, d_in["dO"])
+            return out, gq, gk, gv
+        if halo.active:
+            out, saved = ddist.dist_gat_forward(halo, d_in["ar"], d_in["ac"], *gat_idx, 0.2, d_in["F"], 0.0)
+            gr, gc, gf = ddist.dist_gat_backward(halo, saved, 0.2, 0.0, d_in["dO"])
+            return out, gf, gr, gc
+        out, emax, esum, emask = N.gat_forward(d_in["ar"], d_in["ac"], row_ptr, col_ind, 0.2, d_in["F"], 0.0)
+        gf, gr, gc = N.gat_backward(0.2, 0.0, row_ptr, col_ind, col_ptr, row_ind, val_idx, emax, esum,
+                                    emask, d_in["F"], d_in["ar"], d_in["ac"], d_in["dO"])
+        return out, gf, gr, gc
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize()
 
-        # format construction (SURVEY.md 8a rows a1-a3) timed separately, like the reference's own
-        # `only_preprocess` loop (train_batch_graph_timing.py:115-143): COO -> CSR (+rows, val) -> CSC
-        fmt_ms = []
-        for _ in range(5):
-            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            if conv == "gt":
-                preprocess_Hyper_fw_bw(g)
-            else:
-                preprocess_gat_fw_bw(g)
-            b_.record()
-            b_.synchronize()
-            fmt_ms.append(a.elapsed_time(b_))
-        fmt_ms = sorted(fmt_ms)[len(fmt_ms) // 2]
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    for _ in range(1 if args.profile else max(args.warmup, 3)):
+        step_device()
+    barrier()
+    knames = {"fwd": _lib.last_kernel(0), "bwd_row": _lib.last_kernel(1), "bwd_col": _lib.last_kernel(2)}
 
-        halo = ddist.HaloExchange(part, dev, world)
-        flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
-
-        def step_device(rec=None):
-            """fwd + bwd on resident operands; returns the tensors a caller would keep."""
-            if conv == "gt":
-                K, V = halo.gather_pair(d_in["K"], d_in["V"], rec)
-                if rec is not None:
-                    rec["f0"].record()
-                out, attn = N.gt_hyper_forward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx,
-                                               smem, d_in["Q"], K, V)
-                if rec is not None:
-                    rec["f1"].record()
-                gq, gk, gv = N.gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem,
-                                           d_in["Q"], K, V, attn, d_in["dO"])
-                gk, gv = halo.reduce_pair(gk, gv, rec)
-                return out, gq, gk, gv
-            F, ac = halo.gather_pair(d_in["F"], d_in["ac"], rec)
-            if rec is not None:
-                rec["f0"].record()
-            out, emax, esum, emask = N.gat_forward(d_in["ar"], ac, row_ptr, col_ind, 0.2, F, 0.0)
-            if rec is not None:
-                rec["f1"].record()
-            gf, gr, gc = N.gat_backward(0.2, 0.0, row_ptr, col_ind, col_ptr, row_ind, val_idx, emax, esum,
-                                        emask, F, d_in["ar"], ac, d_in["dO"])
-            gf, gc = halo.reduce_pair(gf, gc, rec)
-            return out, gf, gr, gc
-
-        def barrier():
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-
-        ev = lambda: torch.cuda.Event(enable_timing=True)
-        for _ in range(max(args.warmup, 3)):
+    if args.profile:  # the short eager run tools/profile_r02.sh wraps in ncu
+        for _ in range(steps):
+            flush.fill_(1.0)
             step_device()
         barrier()
+        if args.profile_ref and world == 1:  # the reference's kernels in the same capture
+            time_gpu_reference(name, conv, dim, dict(
+                row_ptr=row_ptr, col_ind=col_ind, rows=rows, val=val, col_ptr=col_ptr, row_ind=row_ind,
+                val_idx=val_idx), d_in, flush, 1, e_total, 0.0, 0.0)
+        return {"workload": name, "profile_steps": steps, "kernels": knames}
 
-        # Single GPU: the step (6 launches + output allocations) is captured once in a CUDA graph and
-        # replayed, so the timed region holds the kernels and not the Python launch path.  With
-        # collectives in the step (N > 1 row partition) it runs eagerly.
-        graph = None
-        if not halo.active and not args.no_graph:
+    # eager timing first (like-for-like partner of the reference-kernel leg and the fallback)
+    def timed(fn_, n_it):
+        ts = []
+        for _ in range(n_it):
+            flush.fill_(1.0)  # L2 flush between timed steps (not timed)
+            s, e = ev(), ev()
+            s.record()
+            fn_()
+            e.record()
+            ts.append((s, e))
+        barrier()
+        return [s.elapsed_time(e) for s, e in ts]
+
+    barrier()
+    n0 = _lib.launch_count()
+    step_device()
+    launches_per_step = _lib.launch_count() - n0
+    barrier()
+    eager_ms = timed(step_device, min(steps, 10))
+
+    # The step (kernel launches + output allocations + the coalesced NCCL groups of a row partition)
+    # is captured once in a CUDA graph and replayed, so the timed region holds device work and not
+    # the Python launch path.
+    graph, graph_note = None, None
+    if not args.no_graph:
+        try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 step_device()
             torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
+            barrier()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 graph_out = step_device()
             for _ in range(2):
                 graph.replay()
+            barrier()
+        except Exception as exc:  # e.g. a collective that cannot be captured on this stack
+            graph, graph_note = None, "graph capture failed (%s); eager launches timed" % repr(exc)[:120]
             torch.cuda.synchronize()
+    ok = torch.tensor([1.0 if graph is not None else 0.0], device=dev)
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if float(ok) == 0.0:
+        graph = None
 
-        clocks = ClockSampler(local) if rank == 0 else None
-        n_launch0 = _lib.launch_count()
-        launches_per_step = None
-        recs = []
-        barrier()
-        for _ in range(args.steps):
-            flush.fill_(1.0)  # L2 flush between timed steps (not timed)
-            rec = {k: ev() for k in ("s", "f0", "f1", "e", "ag0", "ag1", "rs0", "rs1")}
-            rec["s"].record()
-            if graph is not None:
-                graph.replay()
-            else:
-                step_device(rec)
-            rec["e"].record()
-            recs.append(rec)
-        barrier()
-        launches = _lib.launch_count() - n_launch0
-        if graph is not None:
-            # graph replays do not pass through the library's launch counter: count one eager step
-            n0 = _lib.launch_count()
+    clocks = ClockSampler(local) if (rank == 0 and full) else None
+    barrier()
+    step_ms = timed(graph.replay if graph is not None else step_device, steps)
+    ms_local = sum(step_ms) / len(step_ms)
+    launches = launches_per_step * steps
+
+    # collectives on their own streams (eager pass with event brackets; CUDA events cannot be
+    # recorded for timing inside a captured graph)
+    ag_t = rs_t = 0.0
+    if halo.active:
+        halo.record = True
+        n_c = max(3, min(steps, 5))
+        halo.pop_times()
+        for _ in range(n_c):
+            flush.fill_(1.0)
             step_device()
-            launches = (_lib.launch_count() - n0) * args.steps
-        # every kernel of the step on its own (roofline leg): same flush protocol, eager launches,
-        # CUDA events around the single library call that launches it
-        kern_ms = {"fwd": [], "bwd_row": [], "bwd_col": []}
-        if not halo.active and not light:
-            if conv == "gt":
-                out0, attn0 = N.gt_hyper_forward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem,
-                                                 d_in["Q"], d_in["K"], d_in["V"])
-                bargs = (row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, d_in["Q"], d_in["K"],
-                         d_in["V"], attn0, d_in["dO"])
-                bufs = N.gt_backward(*bargs, _phases=1)
-                calls = {"fwd": lambda: N.gt_hyper_forward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx,
-                                                           smem, d_in["Q"], d_in["K"], d_in["V"]),
-                         "bwd_row": lambda: N.gt_backward(*bargs, _phases=1, _buffers=bufs),
-                         "bwd_col": lambda: N.gt_backward(*bargs, _phases=2, _buffers=bufs)}
-            else:
-                o0, emax0, esum0, emask0 = N.gat_forward(d_in["ar"], d_in["ac"], row_ptr, col_ind, 0.2, d_in["F"], 0.0)
-                bargs = (0.2, 0.0, row_ptr, col_ind, col_ptr, row_ind, val_idx, emax0, esum0, emask0, d_in["F"],
-                         d_in["ar"], d_in["ac"], d_in["dO"])
-                bufs = N.gat_backward(*bargs, _phases=1)
-                calls = {"fwd": lambda: N.gat_forward(d_in["ar"], d_in["ac"], row_ptr, col_ind, 0.2, d_in["F"], 0.0),
-                         "bwd_row": lambda: N.gat_backward(*bargs, _phases=1, _buffers=bufs),
-                         "bwd_col": lambda: N.gat_backward(*bargs, _phases=2, _buffers=bufs)}
-            for kname, call in calls.items():
-                call()
-                pairs = []
-                for _ in range(args.steps):
-                    flush.fill_(1.0)
-                    a, b_ = ev(), ev()
-                    a.record()
-                    call()
-                    b_.record()
-                    pairs.append((a, b_))
-                torch.cuda.synchronize()
-                kern_ms[kname] = [a.elapsed_time(b_) for a, b_ in pairs]
-            for r, t in zip(recs, kern_ms["fwd"]):
-                r["fwd_ms"] = t
-        step_ms = [r["s"].elapsed_time(r["e"]) for r in recs]
-        if kern_ms["fwd"]:
-            fwd_ms = kern_ms["fwd"]
-        elif graph is None:
-            fwd_ms = [r["f0"].elapsed_time(r["f1"]) for r in recs]
-        else:
-            fwd_ms = [0.0] * len(recs)  # light pass under graph replay: no per-kernel events
-        timed_coll = world > 1 and graph is None  # collectives only exist in the eager (row partition) step
-        ag_ms = [r["ag0"].elapsed_time(r["ag1"]) for r in recs] if timed_coll else [0.0] * len(recs)
-        rs_ms = [r["rs0"].elapsed_time(r["rs1"]) for r in recs] if timed_coll else [0.0] * len(recs)
-        ms_local = sum(step_ms) / len(step_ms)
+        t = halo.pop_times()
+        halo.record = False
+        ag_t, rs_t = t["allgather_ms"] / n_c, t["reduce_scatter_ms"] / n_c
 
-        # ---- e2e: public autograd API with host operands ------------------------------
+    # every kernel of the step on its own (roofline leg): same flush protocol, eager launches,
+    # CUDA events around the single library call that launches it.  Row-partitioned shards run the
+    # same kernels on their rectangular shard (gathered operands kept from one all-gather).
+    kern_ms = {"fwd": [], "bwd_row": [], "bwd_col": []}
+    if conv == "gt":
+        K_, V_ = halo.all_gather([d_in["K"], d_in["V"]]) if halo.active else (d_in["K"], d_in["V"])
+        out0, attn0 = N.gt_hyper_forward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem,
+                                         d_in["Q"], K_, V_)
+        bargs = (row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, d_in["Q"], K_, V_, attn0, d_in["dO"])
+        bufs = N.gt_backward(*bargs, _phases=1)
+        calls = {"fwd": lambda: N.gt_hyper_forward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx,
+                                                   smem, d_in["Q"], K_, V_),
+                 "bwd_row": lambda: N.gt_backward(*bargs, _phases=1, _buffers=bufs),
+                 "bwd_col": lambda: N.gt_backward(*bargs, _phases=2, _buffers=bufs)}
+    else:
+        F_, ac_ = halo.all_gather([d_in["F"], d_in["ac"]]) if halo.active else (d_in["F"], d_in["ac"])
+        o0, emax0, esum0, emask0 = N.gat_forward(d_in["ar"], ac_, row_ptr, col_ind, 0.2, F_, 0.0)
+        bargs = (0.2, 0.0, row_ptr, col_ind, col_ptr, row_ind, val_idx, emax0, esum0, emask0, F_,
+                 d_in["ar"], ac_, d_in["dO"])
+        bufs = N.gat_backward(*bargs, _phases=1)
+        calls = {"fwd": lambda: N.gat_forward(d_in["ar"], ac_, row_ptr, col_ind, 0.2, F_, 0.0),
+                 "bwd_row": lambda: N.gat_backward(*bargs, _phases=1, _buffers=bufs),
+                 "bwd_col": lambda: N.gat_backward(*bargs, _phases=2, _buffers=bufs)}
+    for kname, call in calls.items():
+        call()
+        kern_ms[kname] = timed(call, min(steps, 10))
+    del calls, bufs, bargs
+
+    # ---- e2e: public autograd API with host operands ------------------------------------
+    e2e_local, h2d, d2h = 0.0, 0, 0
+    if full:
         h_out = {}
-
         up, down = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def _download(t, key, cur):
+            if key not in h_out:
+                h_out[key] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            down.wait_stream(cur)
+            with torch.cuda.stream(down):
+                h_out[key].copy_(t, non_blocking=True)
+            t.record_stream(down)
 
         def step_e2e():
             """Host operands in, host results out, through the public autograd operators.  The
@@ -432,30 +538,26 @@ def run_ours(args):
             with torch.cuda.stream(up):
                 dd["dO"] = h_in["dO"].to(dev, non_blocking=True)
             if conv == "gt":
-                K, V = halo.gather_pair(dd["K"], dd["V"], None)
-                Q = dd["Q"].requires_grad_()
-                K.requires_grad_()
-                V.requires_grad_()
-                out = GTConvFuse_hyper(rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx, smem, Q, K, V)
+                Q, K, V = dd["Q"].requires_grad_(), dd["K"].requires_grad_(), dd["V"].requires_grad_()
+                if halo.active:
+                    out = ddist.GTConvFuse_hyper_dist(halo, *gt_idx, Q, K, V)
+                else:
+                    out = GTConvFuse_hyper(*gt_idx, Q, K, V)
                 _download(out.detach(), "out", cur)
                 cur.wait_stream(up)
                 out.backward(dd["dO"])
-                gk, gv = halo.reduce_pair(K.grad, V.grad, None)
-                res = {"out": out.detach(), "gQ": Q.grad, "gK": gk, "gV": gv}
+                res = {"gQ": Q.grad, "gK": K.grad, "gV": V.grad}
             else:
-                F, ac = halo.gather_pair(dd["F"], dd["ac"], None)
-                ar = dd["ar"].requires_grad_()
-                ac.requires_grad_()
-                F.requires_grad_()
-                out = GATConvFuse(ar, ac, row_ptr, col_ind, col_ptr, row_ind, val_idx, 0.2, F, 0.0)
+                ar, ac, F = dd["ar"].requires_grad_(), dd["ac"].requires_grad_(), dd["F"].requires_grad_()
+                if halo.active:
+                    out = ddist.GATConvFuse_dist(halo, ar, ac, *gat_idx, 0.2, F, 0.0)
+                else:
+                    out = GATConvFuse(ar, ac, *gat_idx, 0.2, F, 0.0)
                 _download(out.detach(), "out", cur)
                 cur.wait_stream(up)
                 out.backward(dd["dO"])
-                gf, gc = halo.reduce_pair(F.grad, ac.grad, None)
-                res = {"out": out.detach(), "gF": gf, "g_ar": ar.grad, "g_ac": gc}
+                res = {"gF": F.grad, "g_ar": ar.grad, "g_ac": ac.grad}
             for k, v in res.items():
-                if k == "out":
-                    continue  # already on its way (download stream)
                 if k not in h_out:
                     h_out[k] = torch.empty(v.shape, dtype=v.dtype).pin_memory()
                 h_out[k].copy_(v, non_blocking=True)
@@ -463,19 +565,11 @@ def run_ours(args):
             dd["dO"].record_stream(cur)
             return res
 
-        def _download(t, key, cur):
-            if key not in h_out:
-                h_out[key] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
-            down.wait_stream(cur)
-            with torch.cuda.stream(down):
-                h_out[key].copy_(t, non_blocking=True)
-            t.record_stream(down)
-
-        for _ in range(1 if light else 3):
+        for _ in range(3):
             step_e2e()
         barrier()
         e2e_ms = []
-        for _ in range(1 if light else args.steps):
+        for _ in range(steps):
             flush.fill_(1.0)
             s, e = ev(), ev()
             s.record()
@@ -484,139 +578,175 @@ def run_ours(args):
             e.synchronize()
             e2e_ms.append(s.elapsed_time(e))
         barrier()
-        clock_info = clocks.stop() if clocks else None
         e2e_local = sum(e2e_ms) / len(e2e_ms)
         h2d = sum(v.numel() * v.element_size() for v in h_in.values())
         d2h = sum(v.numel() * v.element_size() for v in h_out.values())
+    clock_info = clocks.stop() if clocks else None
 
-        # ---- max over ranks -----------------------------------------------------------
-        stats = torch.tensor([ms_local, e2e_local, sum(fwd_ms) / len(fwd_ms), sum(ag_ms) / len(ag_ms),
-                              sum(rs_ms) / len(rs_ms)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-        ms, e2e_t, fwd_t, ag_t, rs_t = (float(x) for x in stats.cpu())
-        fwd_t = max(fwd_t, 1e-9)
-        tot = torch.tensor([float(e_local), float(n_rows)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        e_all, n_all = (float(x) for x in tot.cpu())
-        units = e_all * dim  # edges*dim processed by all ranks per step
-
-        line = None
-        if rank == 0:
-            peak, peak_src = hbm_peak()
-            fwd_bytes = alg_bytes(conv, "fwd", n_rows, e_local, dim)
-            step_bytes = alg_bytes(conv, "fwd+bwd", n_rows, e_local, dim)
-            staged = e_local <= 16 * max(n_rows, 1)  # abi_common.h: want_staged (mean degree <= 16)
-            knames = ({"fwd": "gat_fwd_staged_kernel", "bwd_row": "gat_bwd_row_staged_kernel",
-                       "bwd_col": "gat_bwd_col_staged_kernel"} if staged else
-                      {"fwd": "gat_fwd_kernel", "bwd_row": "gat_bwd_row_kernel", "bwd_col": "gat_bwd_col_kernel"}) \
-                if conv == "gat" else {"fwd": "dot_fwd_kernel", "bwd_row": "gt_bwd_row_kernel",
-                                       "bwd_col": "gt_bwd_col_kernel"}
-            fwd_kernel = knames["fwd"]
-            kbytes = kernel_alg_bytes(conv, n_rows, e_local, dim)
-            traffic = {}
-            try:
-                with open(os.path.join(ROOT, "profiles", "r01i_traffic.json")) as fh:
-                    traffic = json.load(fh).get(name, {})
-            except Exception:
-                pass
-            kernels = {}
-            for k, ts in kern_ms.items():
-                if ts:
-                    t = sum(ts) / len(ts)
-                    kernels[knames[k]] = {"ms": t, "algorithmic_bytes": kbytes[k],
-                                          "achieved": kbytes[k] / (t * 1e-3) / 1e9,
-                                          "frac": kbytes[k] / (t * 1e-3) / 1e9 / peak,
-                                          "traffic": (traffic.get(knames[k]) or {}).get("dram_bytes_per_launch")}
-            dominant = max(kernels, key=lambda k: kernels[k]["ms"]) if kernels else None
-            line = {
-                "metric": METRIC, "value": units / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
-                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
-                "higher_is_better": True, "scaling": "weak" if (weak or world == 1) else "strong", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic",
-                "config": {"workload": name, "conv": conv, "dim": dim, "heads": 1, "format": fmt,
-                           "nodes": int(n_all), "edges": int(e_all), "baseline_config_index": cfg,
-                           "partition": part.describe, "l2": "flushed between timed steps (256 MB fill)",
-                           "launch": "cuda graph replay" if graph is not None else "eager (collectives in the step)",
-                           "graph_sha256": g_full.sha256()[:16]},
-                "e2e": {"value": units / (e2e_t * 1e-3), "unit": UNIT, "ms_per_step": e2e_t,
-                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "api": "dfgnn_b200.operators.%s (autograd Function) with pinned host operands; "
-                               "index formats resident" % ("GTConvFuse_hyper" if conv == "gt" else "GATConvFuse")},
-                "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm",
-                             "kernel": dominant or fwd_kernel,
-                             "achieved": kernels[dominant]["achieved"] if dominant else fwd_bytes / (fwd_t * 1e-3) / 1e9,
-                             "peak": peak, "unit": "GB/s",
-                             "frac": kernels[dominant]["frac"] if dominant else fwd_bytes / (fwd_t * 1e-3) / 1e9 / peak,
-                             "traffic": kernels[dominant]["traffic"] if dominant else None,
-                             "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, "
-                                               "profiles/r01i_traffic.json" if dominant and kernels[dominant]["traffic"] else None,
-                             "peak_source": peak_src,
-                             "kernel_ms": kernels[dominant]["ms"] if dominant else fwd_t,
-                             "algorithmic_bytes": kernels[dominant]["algorithmic_bytes"] if dominant else fwd_bytes,
-                             "kernels": kernels,
-                             "step": {"algorithmic_bytes": step_bytes,
-                                      "achieved": step_bytes / (ms * 1e-3) / 1e9,
-                                      "frac": step_bytes / (ms * 1e-3) / 1e9 / peak}},
-                "format_construction_ms": fmt_ms,
-                "clocks": clock_info,
-                "collectives": {"allgather_ms": ag_t, "reduce_scatter_ms": rs_t} if (world > 1 and halo.active) else None,
-            }
-
-        # ---- GPU reference (the reference's own kernels, sm_100a) + CPU baseline, N = 1 ---
-        if rank == 0 and world == 1 and not args.no_ref and not light:
-            line["gpu_reference"] = time_gpu_reference(name, conv, dim, dict(
-                row_ptr=row_ptr, col_ind=col_ind, rows=rows, val=val, col_ptr=col_ptr, row_ind=row_ind,
-                val_idx=val_idx), d_in, flush, args.steps, e_total)
-        if rank == 0 and world == 1 and not args.no_cpu and not light:
-            line["cpu_baseline"] = cpu_baseline(name, g_full)
-        return line
-
-    name = args.workload
-    full_graph = "batch" not in WORKLOADS[name][3]
-    if world > 1 and full_graph and name != "reddit-gt" and args.scaling == "auto":
-        # A graph of this size is one GPU's worth of work: at N > 1 the headline
-        # is weak scaling -- one such graph per GPU, no collective -- and the row-partitioned
-        # (halo all-gather + reduce-scatter) numbers of ONE graph over N ranks ride along.
-        strong = measure("strong", True)
-        line = measure("weak", False)
-        if rank == 0:
-            line["row_partition"] = {k: strong[k] for k in ("ms_per_step", "value", "collectives", "scaling")}
-            line["row_partition"]["partition"] = strong["config"]["partition"]
-    else:
-        line = measure(args.scaling, False)
-    if rank == 0:
-        print(json.dumps(line), flush=True)
+    # ---- max over ranks -----------------------------------------------------------------
+    mean = lambda ts: sum(ts) / len(ts) if ts else 0.0
+    stats = torch.tensor([ms_local, e2e_local, mean(eager_ms), ag_t, rs_t, mean(kern_ms["fwd"]),
+                          mean(kern_ms["bwd_row"]), mean(kern_ms["bwd_col"])], dtype=torch.float64, device=dev)
     if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    ms, e2e_t, eager_t, ag_t, rs_t, k_fwd, k_row, k_col = (float(x) for x in stats.cpu())
+    tot = torch.tensor([float(e_local), float(n_rows)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    e_all, n_all = (float(x) for x in tot.cpu())
+    units = e_all * dim  # edges*dim processed by all ranks per step
+
+    line = None
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        step_bytes = alg_bytes(conv, "fwd+bwd", n_rows, e_local, dim)
+        kbytes = kernel_alg_bytes(conv, n_rows, e_local, dim)
+        cbytes = kernel_compulsory_bytes(conv, n_rows, n_cols, e_local, dim)
+        traffic, traffic_src = load_traffic()
+        traffic = traffic.get(name, {}) if world == 1 else {}
+        kernels = {}
+        for k, t in (("fwd", k_fwd), ("bwd_row", k_row), ("bwd_col", k_col)):
+            if t <= 0:
+                continue
+            tr = (traffic.get(knames[k]) or {}).get("dram_bytes_per_launch")
+            kernels[knames[k]] = {
+                "ms": t, "algorithmic_bytes": kbytes[k], "achieved": kbytes[k] / (t * 1e-3) / 1e9,
+                "frac": kbytes[k] / (t * 1e-3) / 1e9 / peak,
+                "compulsory_bytes": cbytes[k], "frac_compulsory": cbytes[k] / (t * 1e-3) / 1e9 / peak,
+                "traffic": tr, "frac_dram": (tr / (t * 1e-3) / 1e9 / peak) if tr else None}
+        dominant = max(kernels, key=lambda k: kernels[k]["ms"])
+        dk = kernels[dominant]
+        comp_step = sum(cbytes.values())
+        tr_step = sum(v["traffic"] for v in kernels.values()) if all(v["traffic"] for v in kernels.values()) else None
+        strong = world > 1 and not weak
+        line = {
+            "metric": METRIC, "value": units / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name, "conv": conv, "dim": dim, "heads": 1, "format": fmt,
+                       "nodes": int(n_all), "edges": int(e_all), "baseline_config_index": cfg,
+                       "partition": part.describe, "l2": "flushed between timed steps (256 MB fill)",
+                       "launch": "cuda graph replay" if graph is not None else (graph_note or "eager"),
+                       "graph_sha256": sha},
+            "e2e": {"value": units / (e2e_t * 1e-3) if e2e_t > 0 else None, "unit": UNIT, "ms_per_step": e2e_t,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "pcie_gbs_per_gpu": (h2d + d2h) / (e2e_t * 1e-3) / 1e9 if e2e_t > 0 else None,
+                    "api": ("dfgnn_b200.dist.%s" % ("GTConvFuse_hyper_dist" if conv == "gt" else "GATConvFuse_dist")
+                            if halo.active else
+                            "dfgnn_b200.operators.%s" % ("GTConvFuse_hyper" if conv == "gt" else "GATConvFuse"))
+                    + " (autograd Function) with pinned host operands; index formats resident"} if full else None,
+            "gpu_launches": int(launches),
+            "eager_ms_per_step": eager_t,
+            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": dk["achieved"], "peak": peak,
+                         "unit": "GB/s", "frac": dk["frac"], "traffic": dk["traffic"],
+                         "frac_dram": dk["frac_dram"], "compulsory_bytes": dk["compulsory_bytes"],
+                         "frac_compulsory": dk["frac_compulsory"],
+                         "traffic_source": traffic_src, "peak_source": peak_src,
+                         "kernel_ms": dk["ms"], "algorithmic_bytes": dk["algorithmic_bytes"],
+                         "kernels": kernels,
+                         "step": {"algorithmic_bytes": step_bytes,
+                                  "achieved": step_bytes / (ms * 1e-3) / 1e9,
+                                  "frac": step_bytes / (ms * 1e-3) / 1e9 / peak,
+                                  "compulsory_bytes": comp_step,
+                                  "frac_compulsory": comp_step / (ms * 1e-3) / 1e9 / peak,
+                                  "traffic": tr_step,
+                                  "frac_dram": (tr_step / (ms * 1e-3) / 1e9 / peak) if tr_step else None}},
+            "format_construction_ms": fmt_ms,
+            "clocks": clock_info,
+            "collectives": ({"allgather_ms": ag_t, "reduce_scatter_ms": rs_t,
+                             "share_of_step": (ag_t + rs_t) / ms,
+                             "exposed_ms": max(0.0, ms - (k_fwd + k_row + k_col)),
+                             "note": "durations on their own streams; the reduce-scatter of column chunk c "
+                                     "runs behind the column-side kernel of chunk c+1; exposed_ms = step - "
+                                     "sum of the three kernels timed alone",
+                             "bytes_in_per_rank": (world - 1) * part.max_rows * (2 * dim if conv == "gt" else dim + 1) * 4}
+                            if halo.active else None),
+        }
+
+    # ---- GPU reference (the reference's own kernels, sm_100a) + CPU baseline, N = 1 --------
+    if rank == 0 and world == 1 and not args.no_ref:
+        line["gpu_reference"] = time_gpu_reference(name, conv, dim, dict(
+            row_ptr=row_ptr, col_ind=col_ind, rows=rows, val=val, col_ptr=col_ptr, row_ind=row_ind,
+            val_idx=val_idx), d_in, flush, steps, e_total, eager_t, ms)
+    if rank == 0 and world == 1 and not args.no_cpu and full:
+        line["cpu_baseline"] = cpu_baseline(name)
+    return line
+
+
+def compact(line):
+    """The record of a non-headline workload inside `workloads`."""
+    r = line["roofline"]
+    return {"workload": line["config"]["workload"], "baseline_config_index": line["config"]["baseline_config_index"],
+            "value": line["value"], "unit": UNIT, "ms_per_step": line["ms_per_step"],
+            "eager_ms_per_step": line["eager_ms_per_step"], "scaling": line["scaling"], "steps": line["steps"],
+            "nodes": line["config"]["nodes"], "edges": line["config"]["edges"],
+            "partition": line["config"]["partition"], "launch": line["config"]["launch"],
+            "collectives": line["collectives"], "format_construction_ms": line["format_construction_ms"],
+            "roofline": {"kernel": r["kernel"], "frac": r["frac"], "frac_compulsory": r["frac_compulsory"],
+                         "frac_dram": r["frac_dram"], "traffic": r["traffic"], "step": r["step"],
+                         "kernels": {k: {kk: v[kk] for kk in ("ms", "frac", "frac_compulsory", "frac_dram", "traffic")}
+                                     for k, v in r["kernels"].items()}},
+            "gpu_reference": line.get("gpu_reference")}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    env = Env()
+    env.rank = int(os.environ.get("RANK", "0"))
+    env.world = int(os.environ.get("WORLD_SIZE", "1"))
+    env.local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(env.local)
+    env.dev = torch.device("cuda", env.local)
+    if env.world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=env.dev)
+    env.flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=env.dev)
+
+    head = args.workload or default_workload(env.world)
+    extras = [] if (args.workload or args.no_extras or args.profile) else [w for w in GPU_WORKLOADS if w != head]
+    line = measure(env, args, head, True)
+    if args.profile:
+        if env.rank == 0:
+            print(json.dumps(line), flush=True)
+        return
+    others = []
+    for w in extras:
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        try:
+            rec = measure(env, args, w, False)
+            if env.rank == 0:
+                others.append(compact(rec))
+        except Exception as exc:  # a side workload must not take the headline down
+            if env.rank == 0:
+                others.append({"workload": w, "error": repr(exc)[:300]})
+    if env.rank == 0:
+        line["workloads"] = others
+        print(json.dumps(line), flush=True)
+    if env.world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def cpu_baseline(name, g_full):
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    if name == "reddit-gt":
-        from dfgnn_b200 import graphs
-        g = graphs.reddit_like(0.05)
-        sample = f"reddit-shaped at scale 0.05 (N={g.num_nodes()}, E={g.num_edges()}), 2 steps"
-    else:
-        g = g_full
-        sample = f"full workload (N={g.num_nodes()}, E={g.num_edges()}), 3 steps after 1 warm-up"
-    val, dt, *_ = time_cpu(name, g, 2 if name == "reddit-gt" else 3, 1)
-    return {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-            "ms_per_step": dt * 1e3}
-
-
-def time_gpu_reference(name, conv, dim, idx, d_in, flush, steps, e_total):
-    """The reference's DFGNN CUDA kernels (unchanged, sm_100a) on the same resident inputs."""
+def time_gpu_reference(name, conv, dim, idx, d_in, flush, steps, e_total, ours_eager_ms, ours_graph_ms):
+    """The reference's DFGNN CUDA kernels (unchanged, sm_100a) on the same resident inputs,
+    launched eagerly through their pybind module -- compare with OUR eager step (ours_eager_ms)."""
     import torch
     from oracle import ref_gpu
     if not ref_gpu.available():
         return {"unavailable": "oracle/_ref not built"}
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    res = {}
+    res = {"ours_eager_ms": ours_eager_ms, "ours_graph_replay_ms": ours_graph_ms,
+           "note": "both sides launched eagerly from Python with the same L2-flush protocol; the reference's "
+                   "gat_forward also creates a cuRAND generator and zero-fills its outputs on every call "
+                   "(fused_gatconv_kernel.cu:1073-1081), which is part of its public entry point; the "
+                   "kernel-only sum of the reference is in profiles/r02_traffic.json (reference_kernels)"}
     try:
         if conv == "gt":
             ref = ref_gpu.fused_gtconv()
@@ -633,8 +763,8 @@ def time_gpu_reference(name, conv, dim, idx, d_in, flush, steps, e_total):
                                 idx["row_ptr"], idx["col_ind"], idx["rows"], idx["val"], hs, Q, K, V)}
             else:
                 variants = {}
-                res["note"] = ("hyper/backward kernels need %d floats of smem per 8-row block (> 48 KB): "
-                               "outside the reference's envelope; tiling forward only" % hs)
+                res["envelope"] = ("hyper/backward kernels need %d floats of smem per 8-row block (> 48 KB): "
+                                   "outside the reference's envelope; tiling forward only" % hs)
             variants["fwd (gt_tiling_inference)"] = lambda: ref.gt_tiling_inference(
                 idx["row_ptr"], idx["col_ind"], idx["val"], 128, Q, K, V)
         else:
@@ -678,13 +808,19 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="arxiv-gat", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=list(WORKLOADS),
+                    help="default: arxiv-gat at N=1, reddit-gt (row-partitioned) at N>1, the other GPU "
+                         "workloads in `workloads`; naming one measures only that one")
+    ap.add_argument("--no-extras", action="store_true", help="skip the `workloads` array")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-ref", action="store_true", help="skip the reference-CUDA-kernel timing leg")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
+    ap.add_argument("--profile", action="store_true", help="short eager conv-only run for ncu (tools/profile_r02.sh)")
+    ap.add_argument("--profile-ref", action="store_true", help="with --profile: also launch the reference kernels")
+    ap.add_argument("--chunks", type=int, default=0, help="column chunks of a row partition (default 4)")
     ap.add_argument("--scaling", default="auto", choices=["auto", "weak", "strong"],
-                    help="batched workloads at N>1: weak (own batch per GPU, default) or strong "
-                         "(one global batch sharded by graph); full graphs are always row-partitioned")
+                    help="auto: every workload in its north-star partition (module docstring); weak: own graph / "
+                         "batch per GPU; strong: one global graph / batch split over the ranks")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -38,6 +38,7 @@ _SIGNATURES = {
     "dfgnn_abi_version": (c_int, []),
     "dfgnn_last_error": (ctypes.c_char_p, []),
     "dfgnn_launch_count": (c_uint64, []),
+    "dfgnn_last_kernel": (ctypes.c_char_p, [c_int]),
     "dfgnn_format_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "dfgnn_coo_to_csr": (c_int, [c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "dfgnn_csr_to_csc": (c_int, [c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
@@ -96,3 +97,20 @@ def check(rc: int, what: str) -> None:
 
 def launch_count() -> int:
     return int(lib().dfgnn_launch_count())
+
+
+def last_kernel(slot: int) -> str:
+    """Kernel the last forward (0) / backward row-side (1) / column-side (2) call dispatched to."""
+    return (lib().dfgnn_last_kernel(int(slot)) or b"").decode()
+
+
+def source_sha() -> str:
+    """sha256 over the kernel sources (csrc/*.cu, *.cuh, *.h): ties a committed ncu capture
+    (profiles/*_traffic.json) to the kernels it was taken from."""
+    import hashlib
+    h = hashlib.sha256()
+    for name in sorted(os.listdir(CSRC)):
+        if name.endswith((".cu", ".cuh", ".h")):
+            with open(os.path.join(CSRC, name), "rb") as fh:
+                h.update(name.encode() + b"\0" + fh.read())
+    return h.hexdigest()[:16]

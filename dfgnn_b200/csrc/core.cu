@@ -15,6 +15,12 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static thread_local const char* g_last_kernel[3] = {"", "", ""};
+
+void note_kernel(int slot, const char* name) {
+  if (slot >= 0 && slot < 3) g_last_kernel[slot] = name;
+}
+
 std::atomic<uint64_t>& launch_counter() {
   static std::atomic<uint64_t> c{0};
   return c;
@@ -27,5 +33,8 @@ extern "C" {
 int dfgnn_abi_version(void) { return DFGNN_ABI_VERSION; }
 const char* dfgnn_last_error(void) { return dfgnn::g_err; }
 uint64_t dfgnn_launch_count(void) { return dfgnn::launch_counter().load(); }
+const char* dfgnn_last_kernel(int slot) {
+  return (slot >= 0 && slot < 3) ? dfgnn::g_last_kernel[slot] : "";
+}
 
 }  // extern "C"

@@ -63,6 +63,7 @@ static int gat_backward_impl(int phases, int col0, int n_sub, int nnz_sub, int m
     const dim3 grid_c((n_c + p.rb_col - 1) / p.rb_col, h);
     ensure_smem(gat_bwd_col_kernel<L, C>, slot_bytes<L::NR, L>());
     if (m > 0 && (phases & 1)) {
+      note_kernel(1, staged_r ? "gat_bwd_row_staged_kernel" : "gat_bwd_row_kernel");
       if (staged_r) {
         const size_t sx = stage_x<L>() ? (size_t)p.rb * f * sizeof(float) : 0;
         ensure_smem(gat_bwd_row_staged_kernel<L, StageChunk<L>::kSddmm>, sx, 44 * 1024);
@@ -79,6 +80,7 @@ static int gat_backward_impl(int phases, int col0, int n_sub, int nnz_sub, int m
     }
     if (n_c > 0 && (phases & 2)) {
       p.cap = 0;
+      note_kernel(2, staged_c ? "gat_bwd_col_staged_kernel" : "gat_bwd_col_kernel");
       if (staged_c) {
         ensure_smem(gat_bwd_col_staged_kernel<L, StageChunk<L>::kSpmm>, slot_bytes<L::NR, L>(), 42 * 1024);
         gat_bwd_col_staged_kernel<L, StageChunk<L>::kSpmm><<<grid_c, kNW * 32, slot_bytes<L::NR, L>(), st>>>(p);

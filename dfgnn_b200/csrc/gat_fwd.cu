@@ -30,6 +30,7 @@ int launch_gat_fwd(int m, int nnz, int h, int f, const float* ar, const float* a
     using L = typename decltype(tag)::type;
     constexpr int C = ChunkOf<L>::C1;
     const bool staged = want_staged(m, nnz);
+    note_kernel(0, staged ? "gat_fwd_staged_kernel" : "gat_fwd_kernel");
     p.rb = staged ? pick_rb_staged(m, nnz) : pick_rb(m, nnz, L::G);
     const dim3 grid((m + p.rb - 1) / p.rb, h);
     const size_t smem = slot_bytes<L::NR, L>();

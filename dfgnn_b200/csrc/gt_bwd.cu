@@ -57,11 +57,13 @@ static int gt_backward_impl(int phases, int col0, int n_sub, int nnz_sub, int m,
     if (m > 0 && (phases & 1)) {
       gt_bwd_row_kernel<L, C><<<grid, kNW * 32, smem, st>>>(p);
       rc = check_launch(fn);
+      note_kernel(1, "gt_bwd_row_kernel");
       if (rc) return;
     }
     if (n_c > 0 && (phases & 2)) {
       gt_bwd_col_kernel<L, C><<<grid_c, kNW * 32, smem, st>>>(p);
       rc = check_launch(fn);
+      note_kernel(2, "gt_bwd_col_kernel");
     }
   }, long_rows(m, nnz));
   return rc;

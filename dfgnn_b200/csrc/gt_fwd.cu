@@ -25,6 +25,7 @@ int launch_dot_fwd(bool agnn, int m, int nnz, int h, int f, const int* row_ptr, 
       dot_fwd_kernel<L, C, false><<<grid, kNW * 32, smem, st>>>(p);
     }
     rc = check_launch(fn);
+    note_kernel(0, "dot_fwd_kernel");
   }, long_rows(m, nnz));
   return rc;
 }

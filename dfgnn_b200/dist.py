@@ -161,6 +161,18 @@ class HaloExchange:
         self._comm = torch.cuda.Stream(self.device) if (self.active and self.device.type == "cuda") else None
 
     # -- helpers ---------------------------------------------------------------------------
+    def chunk_nnz(self, col_ptr: torch.Tensor, c: int) -> int:
+        """Entries of column chunk c of the shard's CSC (schedule heuristics of the column-side
+        launches); read back once per col_ptr tensor and cached."""
+        key = (col_ptr.data_ptr(), col_ptr.numel())
+        if getattr(self, "_nnz_key", None) != key:
+            w = self.world * self.part.q
+            cuts = col_ptr[:: w].tolist() if self.part.chunks > 1 else [0, int(col_ptr[-1])]
+            if len(cuts) < self.part.chunks + 1:
+                cuts.append(int(col_ptr[-1]))
+            self._nnz_key, self._nnz = key, [cuts[i + 1] - cuts[i] for i in range(self.part.chunks)]
+        return self._nnz[c]
+
     def pad(self, x: torch.Tensor) -> torch.Tensor:
         """owned slice [n_rows, ...] -> [max_rows, ...] (zero tail); already padded: unchanged."""
         mr = self.part.max_rows
@@ -332,44 +344,88 @@ def _fit_grad(g: torch.Tensor, rows: int) -> torch.Tensor:
     return out
 
 
+def dist_gt_forward(halo, rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx, smem_consume,
+                    Q, K_own, V_own):
+    """Halo all-gather of K, V + fused conv forward on the shard.  -> out, saved (for
+    dist_gt_backward).  Plain function: the autograd Function below and callers that drive the
+    two directions by hand (bench.py's device-timed step) share it."""
+    from .operators import _native as N
+    K, V = halo.all_gather([K_own, V_own])
+    out, attn = N.gt_hyper_forward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx,
+                                   smem_consume, Q, K, V)
+    return out, (row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, Q, K, V, attn)
+
+
+def dist_gt_backward(halo, saved, smem_consume, grad_out, own_rows=None):
+    """Row-side kernel, then the column-side kernel chunk by chunk with the reduce-scatter of
+    dK, dV of chunk c running behind the kernel of chunk c+1.  -> dQ, dK_own, dV_own."""
+    from .operators import _native as N
+    row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, Q, K, V, attn = saved
+    args = (row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem_consume, Q, K, V, attn,
+            grad_out)
+    bufs = N.gt_backward(*args, _phases=1)
+    gq, gk, gv, _ = bufs
+    if not halo.active:
+        N.gt_backward(*args, _phases=2, _buffers=bufs)
+        return gq, gk, gv
+    halo.begin_overlapped_reduce([gk, gv])
+    for c, (c0, nc) in enumerate(_col_chunks(halo)):
+        N.gt_backward(*args, _phases=2, _buffers=bufs, _cols=(c0, nc, halo.chunk_nnz(col_ptr, c)))
+        halo.reduce_chunk_async(c)
+    gk_own, gv_own = halo.end_overlapped_reduce()
+    if own_rows is not None:
+        gk_own, gv_own = _fit_grad(gk_own, own_rows[0]), _fit_grad(gv_own, own_rows[1])
+    return gq, gk_own, gv_own
+
+
+def dist_gat_forward(halo, attn_row, attn_col_own, row_ptr, col_ind, col_ptr, row_ind, permute,
+                     negative_slope, feat_own, attn_drop):
+    from .operators import _native as N
+    feat, ac = halo.all_gather([feat_own, attn_col_own])
+    out, emax, esum, emask = N.gat_forward(attn_row, ac, row_ptr, col_ind, negative_slope, feat,
+                                           attn_drop)
+    return out, (row_ptr, col_ind, col_ptr, row_ind, permute, emax, esum, emask, feat, attn_row, ac)
+
+
+def dist_gat_backward(halo, saved, negative_slope, attn_drop, grad_out, own_rows=None):
+    """-> grad_attn_row, grad_attn_col_own, grad_feat_own."""
+    from .operators import _native as N
+    row_ptr, col_ind, col_ptr, row_ind, permute, emax, esum, emask, feat, attn_row, ac = saved
+    args = (negative_slope, attn_drop, row_ptr, col_ind, col_ptr, row_ind, permute, emax, esum,
+            emask, feat, attn_row, ac, grad_out)
+    bufs = N.gat_backward(*args, _phases=1)
+    gf, gr, gc, _ = bufs
+    if not halo.active:
+        N.gat_backward(*args, _phases=2, _buffers=bufs)
+        return gr, gc, gf
+    halo.begin_overlapped_reduce([gf, gc])
+    for c, (c0, nc) in enumerate(_col_chunks(halo)):
+        N.gat_backward(*args, _phases=2, _buffers=bufs, _cols=(c0, nc, halo.chunk_nnz(col_ptr, c)))
+        halo.reduce_chunk_async(c)
+    gf_own, gc_own = halo.end_overlapped_reduce()
+    if own_rows is not None:
+        gf_own, gc_own = _fit_grad(gf_own, own_rows[0]), _fit_grad(gc_own, own_rows[1])
+    return gr, gc_own, gf_own
+
+
 class DistGTFunction(torch.autograd.Function):
-    """Row-partitioned FusedGTFunction_hyper (operators/fused_gtconv.py:79-158 on a shard):
-    forward = halo all-gather of K, V + fused conv; backward = row-side kernel, then the
-    column-side kernel chunk by chunk with the reduce-scatter of dK, dV of chunk c running
-    behind the kernel of chunk c+1."""
+    """Row-partitioned FusedGTFunction_hyper (operators/fused_gtconv.py:79-158 on a shard)."""
 
     @staticmethod
     def forward(ctx, halo, rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx, smem_consume,
                 Q, K_own, V_own):
-        from .operators import _native as N
-        K, V = halo.all_gather([K_own, V_own])
-        out, attn = N.gt_hyper_forward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx,
-                                       smem_consume, Q, K, V)
+        out, saved = dist_gt_forward(halo, rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx,
+                                     smem_consume, Q, K_own, V_own)
         ctx.halo, ctx.smem = halo, smem_consume
         ctx.own_rows = (K_own.shape[0], V_own.shape[0])
-        ctx.save_for_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, Q, K, V, attn)
+        ctx.save_for_backward(*saved)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        from .operators import _native as N
-        row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, Q, K, V, attn = ctx.saved_tensors
-        halo = ctx.halo
-        grad_out = grad_out.contiguous()
-        bufs = N.gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, ctx.smem,
-                             Q, K, V, attn, grad_out, _phases=1)
-        gq, gk, gv, ge = bufs
-        if not halo.active:
-            N.gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, ctx.smem,
-                          Q, K, V, attn, grad_out, _phases=2, _buffers=bufs)
-            return (None,) * 9 + (gq, gk, gv)
-        halo.begin_overlapped_reduce([gk, gv])
-        for c, (c0, nc) in enumerate(_col_chunks(halo)):
-            N.gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, ctx.smem,
-                          Q, K, V, attn, grad_out, _phases=2, _buffers=bufs, _cols=(c0, nc))
-            halo.reduce_chunk_async(c)
-        gk_own, gv_own = halo.end_overlapped_reduce()
-        return (None,) * 9 + (gq, _fit_grad(gk_own, ctx.own_rows[0]), _fit_grad(gv_own, ctx.own_rows[1]))
+        gq, gk, gv = dist_gt_backward(ctx.halo, ctx.saved_tensors, ctx.smem, grad_out.contiguous(),
+                                      ctx.own_rows)
+        return (None,) * 9 + (gq, gk, gv)
 
 
 class DistGATFunction(torch.autograd.Function):
@@ -378,37 +434,18 @@ class DistGATFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, halo, attn_row, attn_col_own, row_ptr, col_ind, col_ptr, row_ind, permute,
                 negative_slope, feat_own, attn_drop):
-        from .operators import _native as N
-        feat, ac = halo.all_gather([feat_own, attn_col_own])
-        out, emax, esum, emask = N.gat_forward(attn_row, ac, row_ptr, col_ind, negative_slope, feat,
-                                               attn_drop)
+        out, saved = dist_gat_forward(halo, attn_row, attn_col_own, row_ptr, col_ind, col_ptr,
+                                      row_ind, permute, negative_slope, feat_own, attn_drop)
         ctx.halo, ctx.slope, ctx.drop = halo, negative_slope, attn_drop
         ctx.own_rows = (feat_own.shape[0], attn_col_own.shape[0])
-        ctx.save_for_backward(row_ptr, col_ind, col_ptr, row_ind, permute, emax, esum, emask, feat,
-                              attn_row, ac)
+        ctx.save_for_backward(*saved)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        from .operators import _native as N
-        (row_ptr, col_ind, col_ptr, row_ind, permute, emax, esum, emask, feat, attn_row,
-         ac) = ctx.saved_tensors
-        halo = ctx.halo
-        grad_out = grad_out.contiguous()
-        args = (ctx.slope, ctx.drop, row_ptr, col_ind, col_ptr, row_ind, permute, emax, esum, emask,
-                feat, attn_row, ac, grad_out)
-        bufs = N.gat_backward(*args, _phases=1)
-        gf, gr, gc, ge = bufs
-        if not halo.active:
-            N.gat_backward(*args, _phases=2, _buffers=bufs)
-            return (None, gr, gc) + (None,) * 6 + (gf, None)
-        halo.begin_overlapped_reduce([gf, gc])
-        for c, (c0, nc) in enumerate(_col_chunks(halo)):
-            N.gat_backward(*args, _phases=2, _buffers=bufs, _cols=(c0, nc))
-            halo.reduce_chunk_async(c)
-        gf_own, gc_own = halo.end_overlapped_reduce()
-        return (None, gr, _fit_grad(gc_own, ctx.own_rows[1])) + (None,) * 6 + \
-            (_fit_grad(gf_own, ctx.own_rows[0]), None)
+        gr, gc, gf = dist_gat_backward(ctx.halo, ctx.saved_tensors, ctx.slope, ctx.drop,
+                                       grad_out.contiguous(), ctx.own_rows)
+        return (None, gr, gc) + (None,) * 6 + (gf, None)
 
 
 def GTConvFuse_hyper_dist(halo: HaloExchange, rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx,

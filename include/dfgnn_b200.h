@@ -54,6 +54,9 @@ int dfgnn_abi_version(void);
 const char *dfgnn_last_error(void);
 /* Number of kernels this library has launched in this process (all entry points). */
 uint64_t dfgnn_launch_count(void);
+/* Name of the kernel the calling thread's last forward (slot 0), backward row-side (slot 1) or
+ * backward column-side (slot 2) call dispatched to, e.g. "gat_fwd_staged_kernel"; "" if none. */
+const char *dfgnn_last_kernel(int slot);
 
 /* ------------------------------------------------------------------------ */
 /* Index-format construction                                                 */

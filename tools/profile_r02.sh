@@ -1,0 +1,27 @@
+#!/bin/bash
+# ncu evidence of round 2, one gpurun call (all ncu runs of a call count as one):
+#   gpurun --timeout 1500 -- 'bash tools/profile_r02.sh'
+# For every GPU workload: the plain run first (must exit 0), then (a) a metrics pass over every
+# conv kernel launch (duration + DRAM bytes; ours and the reference's), (b) one --set full capture
+# of our kernels.  tools/make_traffic.py turns the CSVs into profiles/r02_traffic.json and the
+# .ncu-rep files into profiles/r02_ncu_full_<workload>.txt.
+set -u
+OUT=gpurun_out
+mkdir -p $OUT
+OURS='regex:gat_fwd|gat_bwd|dot_fwd|gt_bwd|gt_block'
+ALL='regex:gat_fwd|gat_bwd|dot_fwd|gt_bwd|gt_block|fused_|sddmm|spmm|softMax|softmax|mhsddmm|mhspmm|Kernel'
+for W in ${WORKLOADS:-arxiv-gat pattern-gt voc-gt reddit-gt}; do
+  python bench.py --workload $W --profile --profile-ref > $OUT/r02_plain_$W.log 2>&1 || { echo "plain run failed: $W"; tail -5 $OUT/r02_plain_$W.log; continue; }
+  ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
+      -k "$ALL" --csv --log-file $OUT/r02_traffic_$W.csv python bench.py --workload $W --profile --profile-ref > $OUT/r02_ncu1_$W.log 2>&1
+  echo "traffic $W rc=$?"
+  python bench.py --workload $W --profile > $OUT/r02_plain2_$W.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k "$OURS" -c 24 -f -o $OUT/r02_full_$W \
+      python bench.py --workload $W --profile > $OUT/r02_ncu2_$W.log 2>&1
+  echo "full $W rc=$?"
+done
+# launch list of the default bench command (shares of the step)
+python bench.py --steps 3 --warmup 3 --no-cpu --no-ref --no-extras > $OUT/r02_plain_default.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/r02_launches_arxiv-gat.csv \
+    python bench.py --steps 3 --warmup 3 --no-cpu --no-ref --no-extras > $OUT/r02_ncu3.log 2>&1
+echo "launch list rc=$?"
