@@ -184,6 +184,10 @@ def build_graph(name: str, seed_offset: int = 0):
     return getattr(graphs, fn)(seed=SEEDS[name] + seed_offset, **kw)
 
 
+def n_nodes_hint(name: str) -> int:
+    return {"arxiv-gat": 169343, "reddit-gt": 232965, "cora-gt": 2708}.get(name, 0)
+
+
 def default_workload(gpus: int) -> str:
     return "arxiv-gat" if gpus <= 1 else "reddit-gt"
 
@@ -307,7 +311,10 @@ def measure(env, args, name: str, full: bool):
     mode = PARTITION[name] if args.scaling == "auto" else \
         ("weak" if args.scaling == "weak" else ("by-graph" if batched else "row"))
     weak = world > 1 and mode == "weak"
-    chunks = args.chunks if args.chunks > 0 else 4
+    # column chunks of a row partition: enough bytes per reduce-scatter to amortise its launch
+    # latency (~48 MB of column-side gradient per chunk), at most 4
+    grad_bytes = n_nodes_hint(name) * (2 * dim if conv == "gt" else dim + 1) * 4
+    chunks = args.chunks if args.chunks > 0 else int(max(1, min(4, grad_bytes // (48 << 20))))
     if world == 1 or weak:
         g_full = build_graph(name, seed_offset=1000 * rank if weak else 0)
         part = ddist.make_partition(g_full, 1, 0)
@@ -631,7 +638,7 @@ def measure(env, args, name: str, full: bool):
                        "graph_sha256": sha},
             "e2e": {"value": units / (e2e_t * 1e-3) if e2e_t > 0 else None, "unit": UNIT, "ms_per_step": e2e_t,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "pcie_gbs_per_gpu": (h2d + d2h) / (e2e_t * 1e-3) / 1e9 if e2e_t > 0 else None,
+                    "host_bytes_over_step_gbs_per_gpu": (h2d + d2h) / (e2e_t * 1e-3) / 1e9 if e2e_t > 0 else None,
                     "api": ("dfgnn_b200.dist.%s" % ("GTConvFuse_hyper_dist" if conv == "gt" else "GATConvFuse_dist")
                             if halo.active else
                             "dfgnn_b200.operators.%s" % ("GTConvFuse_hyper" if conv == "gt" else "GATConvFuse"))
