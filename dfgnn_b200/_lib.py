@@ -45,6 +45,10 @@ _SIGNATURES = {
     "dfgnn_gt_hyper_forward": (c_int, [c_int] * 4 + [_P] * 7 + [c_int] + [_P] * 5 + [_P]),
     "dfgnn_gt_backward": (c_int, [c_int] * 5 + [_P] * 7 + [c_int] + [_P] * 9 + [_P]),
     "dfgnn_gt_backward_phase": (c_int, [c_int] * 6 + [_P] * 7 + [c_int] + [_P] * 9 + [_P]),
+    "dfgnn_block_plan_check": (c_int, [c_int] * 3 + [_P] * 5 + [_P]),
+    "dfgnn_gt_block_supported": (c_int, [c_int] * 5),
+    "dfgnn_gt_block_forward": (c_int, [c_int, _P] + [c_int] * 5 + [_P] * 8 + [_P]),
+    "dfgnn_gt_block_backward": (c_int, [c_int, c_int, _P] + [c_int] * 5 + [_P] * 15 + [_P]),
     "dfgnn_gt_backward_cols": (c_int, [c_int] * 8 + [_P] * 7 + [c_int] + [_P] * 9 + [_P]),
     "dfgnn_gt_hyper_inference": (c_int, [c_int] * 4 + [_P] * 4 + [c_int] + [_P] * 4 + [_P]),
     "dfgnn_gt_softmax_inference": (c_int, [c_int] * 4 + [_P] * 4 + [c_int] + [_P] * 4 + [_P]),

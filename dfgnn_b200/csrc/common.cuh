@@ -238,6 +238,38 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// ---- TMA bulk copies (1-D cp.async.bulk, SASS UBLKCP) completing on an mbarrier ------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+// makes the barrier initialisation visible to the async proxy (the TMA unit)
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// a contiguous range of `bytes` bytes in pieces of at most 16 KB (several requests in flight);
+// called by ONE thread that has already done mbar_expect_tx for the total
+__device__ __forceinline__ void bulk_g2s_range(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  constexpr uint32_t kPiece = 16 * 1024;
+  for (uint32_t off = 0; off < bytes; off += kPiece)
+    bulk_g2s(static_cast<char*>(smem_dst) + off, static_cast<const char*>(gmem_src) + off,
+             bytes - off < kPiece ? bytes - off : kPiece, bar);
+}
+
 // lets the next kernel on the stream start early if it was launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization (abi_common.h: launch_overlapped)
 __device__ __forceinline__ void allow_dependent_launch() {

@@ -109,3 +109,63 @@ def csr_to_csc(row_ptr: torch.Tensor, col_ind: torch.Tensor, n_cols: int = None,
                                 torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(rc, "csr_to_csc")
     return col_ptr, row_ind, val_idx
+
+
+class BlockPlan:
+    """Node ranges of the graphs of a block-diagonal batch (``g.batch_num_nodes()``), validated
+    against the CSR.  Attached to the ``row_ptr`` tensor the preprocessing returns
+    (``row_ptr._dfgnn_blocks``): the operators then run the graph-resident kernels
+    (csrc/block_gt.cuh) for the sizes they support."""
+
+    def __init__(self, blk_ptr: torch.Tensor, n_blocks: int, max_nodes: int):
+        self.blk_ptr = blk_ptr
+        self.n_blocks = int(n_blocks)
+        self.max_nodes = int(max_nodes)
+        self._ok = {}
+
+    def supported(self, m: int, nnz: int, h: int, f: int) -> bool:
+        key = (m, nnz, h, f)
+        if key not in self._ok:
+            self._ok[key] = bool(_lib.lib().dfgnn_gt_block_supported(self.max_nodes, m, nnz, h, f))
+        return self._ok[key]
+
+
+def block_plan(batch_num_nodes: torch.Tensor, row_ptr: torch.Tensor, col_ind: torch.Tensor):
+    """-> BlockPlan for a batch whose graphs have ``batch_num_nodes`` nodes each, or None when the
+    batch is a single graph.  Raises if the CSR is not block diagonal over those ranges."""
+    import ctypes
+    _require_cuda(row_ptr, "row_ptr")
+    bnn = batch_num_nodes.to(torch.int64).cpu()
+    if bnn.numel() <= 1:
+        return None
+    m = row_ptr.numel() - 1
+    if int(bnn.sum()) != m:
+        raise RuntimeError(f"batch_num_nodes sums to {int(bnn.sum())}, the graph has {m} nodes")
+    dev = row_ptr.device
+    blk = torch.zeros(bnn.numel() + 1, dtype=torch.int32)
+    blk[1:] = torch.cumsum(bnn, 0).to(torch.int32)
+    blk = blk.to(dev)
+    with torch.cuda.device(dev):
+        flag = torch.empty(2, dtype=torch.int32, device=dev)
+        mx = ctypes.c_int32(0)
+        rc = _lib.lib().dfgnn_block_plan_check(
+            bnn.numel(), m, col_ind.numel(), blk.data_ptr(), row_ptr.data_ptr(),
+            col_ind.data_ptr() if col_ind.numel() else None, flag.data_ptr(), ctypes.addressof(mx),
+            torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "block_plan")
+    return BlockPlan(blk, bnn.numel(), mx.value)
+
+
+def attach_block_plan(g, row_ptr: torch.Tensor, col_ind: torch.Tensor):
+    """Preprocessing hook: a batched graph (``g.batch_size > 1``) gets its block plan attached to
+    ``row_ptr``.  Graphs without batch information are left alone."""
+    try:
+        bs = int(getattr(g, "batch_size", 1))
+        if bs <= 1 or getattr(g, "num_cols", g.num_nodes()) != g.num_nodes():
+            return
+        bnn = g.batch_num_nodes()
+    except Exception:
+        return
+    plan = block_plan(bnn, row_ptr, col_ind)
+    if plan is not None:
+        row_ptr._dfgnn_blocks = plan

@@ -6,7 +6,7 @@ from __future__ import annotations
 
 import torch
 
-from ..formats import SparseMatrix, coo_to_csr, csr_to_csc
+from ..formats import SparseMatrix, attach_block_plan, coo_to_csr, csr_to_csc
 
 WARP_SIZE = 32
 
@@ -31,6 +31,7 @@ def preprocess_CSR(g, **args):
     """layers/util.py:66-79 -> (row_ptr, col_ind, val, smem_consume=128)."""
     A, max_neigh = g_to_SPmatrix(g)
     row_ptr, col_ind, _, _, val = coo_to_csr(A.row, A.col, A.shape[0], A.shape[1])
+    attach_block_plan(g, row_ptr, col_ind)
     return row_ptr, col_ind, val, _smem(max_neigh, 1)
 
 
@@ -38,6 +39,7 @@ def preprocess_Hyper(g, **args):
     """layers/util.py:82-100 -> (row_ptr, col_ind, rows, val, smem_consume=1024)."""
     A, max_neigh = g_to_SPmatrix(g)
     row_ptr, col_ind, rows, _, val = coo_to_csr(A.row, A.col, A.shape[0], A.shape[1])
+    attach_block_plan(g, row_ptr, col_ind)
     return row_ptr, col_ind, rows, val, _smem(max_neigh, 8)
 
 
@@ -45,6 +47,7 @@ def preprocess_softmax(g, **args):
     """layers/util.py:145-162 -> (row_ptr, col_ind, rows, val, smem_consume=128)."""
     A, max_neigh = g_to_SPmatrix(g)
     row_ptr, col_ind, rows, _, val = coo_to_csr(A.row, A.col, A.shape[0], A.shape[1])
+    attach_block_plan(g, row_ptr, col_ind)
     return row_ptr, col_ind, rows, val, _smem(max_neigh, 1)
 
 
@@ -56,6 +59,7 @@ def preprocess_Hyper_fw_bw(g, fused=True):
         return A, None, None, None, None, None, None, None, None
     row_ptr, col_ind, rows, _, val = coo_to_csr(A.row, A.col, A.shape[0], A.shape[1])
     col_ptr, row_ind, val_idx = csr_to_csc(row_ptr, col_ind, A.shape[1], rows)
+    attach_block_plan(g, row_ptr, col_ind)
     return A, rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx, _smem(max_neigh, 8)
 
 

@@ -43,6 +43,15 @@ def _val_ptr(val):
     return None if (val is None or getattr(val, "_dfgnn_ones", False)) else _ptr(val)
 
 
+def _blocks(row_ptr, m, nnz, h, f):
+    """The block plan the preprocessing attached to row_ptr (formats.attach_block_plan), if the
+    graph-resident kernels support this size; else None (general kernels)."""
+    plan = getattr(row_ptr, "_dfgnn_blocks", None)
+    if plan is None or plan.blk_ptr.device != row_ptr.device or not plan.supported(m, nnz, h, f):
+        return None
+    return plan
+
+
 def _stream(ref: torch.Tensor):
     return torch.cuda.current_stream(ref.device).cuda_stream
 
@@ -80,9 +89,16 @@ def gt_hyper_forward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, sme
     """fused_gtconv.cpp:79-116 -> [out_feat (m,h,f), attn_edge (h,nnz)]."""
     fn = "gt_hyper_forward"
     m, nnz, h, f = _check_gt(fn, row_ptr, col_ind, Q, K, V, rows, val)
+    plan = _blocks(row_ptr, m, nnz, h, f) if K.shape[0] == m else None
     with torch.cuda.device(Q.device):
         out = torch.empty_like(Q)
         attn = torch.empty((h, nnz), dtype=torch.float32, device=Q.device)
+        if plan is not None:
+            rc = _lib.lib().dfgnn_gt_block_forward(
+                plan.n_blocks, _ptr(plan.blk_ptr), plan.max_nodes, m, nnz, h, f, _ptr(row_ptr), _ptr(col_ind),
+                _val_ptr(val), _ptr(Q), _ptr(K), _ptr(V), _ptr(out), _ptr(attn), _stream(Q))
+            _lib.check(rc, fn)
+            return [out, attn]
         rc = _lib.lib().dfgnn_gt_hyper_forward(
             m, nnz, h, f, _ptr(row_ptr), _ptr(col_ind), _ptr(rows), _val_ptr(val), _ptr(col_ptr),
             _ptr(row_ind), _ptr(val_idx), int(smem_consume), _ptr(Q), _ptr(K), _ptr(V),
@@ -123,7 +139,13 @@ def gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem_con
         tail = (m, n, nnz, h, f, _ptr(row_ptr), _ptr(col_ind), _ptr(rows), _val_ptr(val), _ptr(col_ptr),
                 _ptr(row_ind), _ptr(val_idx), int(smem_consume), _ptr(Q), _ptr(K), _ptr(V),
                 _ptr(attn_edge), _ptr(grad), _ptr(gq), _ptr(gk), _ptr(gv), _ptr(ge), _stream(Q))
-        if _cols is not None:
+        plan = _blocks(row_ptr, m, nnz, h, f) if (n == m and _cols is None) else None
+        if plan is not None:
+            rc = _lib.lib().dfgnn_gt_block_backward(
+                int(_phases), plan.n_blocks, _ptr(plan.blk_ptr), plan.max_nodes, m, nnz, h, f, _ptr(row_ptr),
+                _ptr(col_ind), _val_ptr(val), _ptr(col_ptr), _ptr(row_ind), _ptr(val_idx), _ptr(Q), _ptr(K),
+                _ptr(V), _ptr(attn_edge), _ptr(grad), _ptr(gq), _ptr(gk), _ptr(gv), _ptr(ge), _stream(Q))
+        elif _cols is not None:
             if _buffers is None or _phases != 2:
                 raise RuntimeError(f"{fn}: _cols needs _phases=2 and _buffers")
             c0, nc = int(_cols[0]), int(_cols[1])
@@ -138,8 +160,15 @@ def gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem_con
 
 def _gt_inference(cname, fn, indptr, indices, rows, val, smem_consume, Q, K, V, has_rows, has_smem):
     m, nnz, h, f = _check_gt(fn, indptr, indices, Q, K, V, rows, val)
+    plan = _blocks(indptr, m, nnz, h, f) if K.shape[0] == m else None
     with torch.cuda.device(Q.device):
         out = torch.empty_like(Q)
+        if plan is not None:
+            rc = _lib.lib().dfgnn_gt_block_forward(
+                plan.n_blocks, _ptr(plan.blk_ptr), plan.max_nodes, m, nnz, h, f, _ptr(indptr), _ptr(indices),
+                _val_ptr(val), _ptr(Q), _ptr(K), _ptr(V), _ptr(out), None, _stream(Q))
+            _lib.check(rc, fn)
+            return out
         args = [m, nnz, h, f, _ptr(indptr), _ptr(indices)]
         if has_rows:
             args.append(_ptr(rows))

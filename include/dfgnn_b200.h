@@ -159,6 +159,39 @@ int dfgnn_gt_backward_cols(int col_begin, int n_sub, int nnz_sub, int m, int n, 
                            const float *attn_edge, const float *grad_out, float *grad_Q,
                            float *grad_K, float *grad_V, float *grad_edge, void *stream);
 
+/* ------------------------------------------------------------------------ */
+/* Block-diagonal batches of small graphs (graph-resident kernels)            */
+/* ------------------------------------------------------------------------ */
+/*
+ * The reference batches small graphs with dgl.batch (block-diagonal adjacency; the node ranges
+ * are g.batch_num_nodes(), used by its preprocessing at DFGNN/layers/util.py:116-142 only
+ * implicitly) and runs the same kernels as on a full graph.  Here a block plan -- blk_ptr
+ * [n_blocks + 1], the first node of every graph -- selects kernels that keep one graph's operand
+ * blocks in shared memory (csrc/block_gt.cuh).  Results are those of the entry points above.
+ *
+ * dfgnn_block_plan_check validates that every column id of a block's rows lies inside the block
+ * (one small device -> host readback; flag_ws = 2 ints of device scratch) and returns the largest
+ * block in *max_nodes_out (host).  dfgnn_gt_block_supported tells whether the block kernels would
+ * be used for this size (h == 1, f in {32, 64, 128}, both operand blocks of the largest graph fit
+ * shared memory, mean degree >= 8); callers fall back to the general entry points otherwise.
+ */
+int dfgnn_block_plan_check(int n_blocks, int m, int nnz, const int32_t *blk_ptr,
+                           const int32_t *row_ptr, const int32_t *col_ind, int32_t *flag_ws,
+                           int32_t *max_nodes_out, void *stream);
+int dfgnn_gt_block_supported(int max_nodes, int m, int nnz, int h, int f);
+/* = dfgnn_gt_hyper_forward (attn_edge may be NULL: inference). */
+int dfgnn_gt_block_forward(int n_blocks, const int32_t *blk_ptr, int max_nodes, int m, int nnz,
+                           int h, int f, const int32_t *row_ptr, const int32_t *col_ind,
+                           const float *val, const float *Q, const float *K, const float *V,
+                           float *out_feat, float *attn_edge, void *stream);
+/* = dfgnn_gt_backward_phase on a square block-diagonal adjacency (n == m). */
+int dfgnn_gt_block_backward(int phases, int n_blocks, const int32_t *blk_ptr, int max_nodes, int m,
+                            int nnz, int h, int f, const int32_t *row_ptr, const int32_t *col_ind,
+                            const float *val, const int32_t *col_ptr, const int32_t *row_ind,
+                            const int32_t *val_idx, const float *Q, const float *K, const float *V,
+                            const float *attn_edge, const float *grad_out, float *grad_Q,
+                            float *grad_K, float *grad_V, float *grad_edge, void *stream);
+
 /*
  * Inference entry points; all compute the same function, the name selects the
  * schedule heuristics.  Replace gt_hyper_inference (fused_gtconv.cpp:278-314),

@@ -1,0 +1,136 @@
+"""Graph-resident GT kernels (csrc/block_gt.cuh) for block-diagonal batches: one CTA per graph,
+K/V (dO/Q) of the graph staged in shared memory by TMA bulk copies.  Checked against the fp64 CPU
+oracle and against the general row-block kernels on the same inputs; tolerance 1e-4 relative /
+1e-5 absolute (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from dfgnn_b200 import _lib, formats, graphs
+from dfgnn_b200.layers import preprocess_Hyper, preprocess_Hyper_fw_bw
+from dfgnn_b200.operators import GTConvFuse_hyper
+from dfgnn_b200.operators import _native as N
+from oracle import cpu_oracle as O
+
+from .helpers import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(kind):
+    if kind == "pattern":      # largest graph <= 159 nodes: 16 warps per CTA in all three kernels
+        return graphs.batched_graph(8, 110.0, 20.0, 50, 150, 51.0, 11.0, 1, None, 3, "pattern-small")
+    if kind == "pattern-max":  # graphs of up to 186 nodes: the backward kernels run with 8 warps
+        return graphs.batched_graph(6, 170.0, 20.0, 120, 186, 51.0, 11.0, 1, None, 4, "pattern-max")
+    if kind == "ragged":       # 1-node graphs, rows without edges, sparse and dense graphs mixed
+        g = graphs.batched_graph(40, 30.0, 40.0, 1, 186, 9.0, 8.0, 0, None, 5, "ragged")
+        return g
+    raise KeyError(kind)
+
+
+def _oracle(g, X):
+    src, dst = g.edges()
+    n = g.num_nodes()
+    rp, ci, rows, perm = O.coo_to_csr(src, dst, n)
+    cp, ri, vi = O.csr_to_csc(rp, ci, n)
+    out, attn = O.gt_forward(rp, ci, None, X.Q, X.K, X.V, dtype=np.float64)
+    dQ, dK, dV, _ = O.gt_backward(rp, ci, cp, ri, vi, X.Q, X.K, X.V, attn, X.dO, dtype=np.float64)
+    return out, attn, dQ, dK, dV
+
+
+@pytest.mark.parametrize("kind,dim", [("pattern", 128), ("pattern", 64), ("pattern", 32), ("pattern-max", 128),
+                                      ("ragged", 128), ("ragged", 64)])
+def test_block_kernels_match_oracle_and_general_kernels(cuda, kind, dim):
+    g = _batch(kind)
+    n = g.num_nodes()
+    X = graphs.conv_inputs(n, dim, 17)
+    A, rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx, smem = preprocess_Hyper_fw_bw(g.to(cuda))
+    plan = getattr(row_ptr, "_dfgnn_blocks", None)
+    assert plan is not None and plan.n_blocks == g.batch_size
+    assert plan.max_nodes == int(g.batch_num_nodes().max())
+    assert plan.supported(n, col_ind.numel(), 1, dim), "the batch should run on the block kernels"
+    Q, K, V, dO = (t.to(cuda) for t in (X.Q, X.K, X.V, X.dO))
+    out, attn = N.gt_hyper_forward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V)
+    assert _lib.last_kernel(0) == "gt_block_fwd_kernel"
+    gq, gk, gv = N.gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V, attn, dO)
+    assert _lib.last_kernel(1) == "gt_block_bwd_row_kernel" and _lib.last_kernel(2) == "gt_block_bwd_col_kernel"
+    inf = N.gt_hyper_inference(row_ptr, col_ind, rows, val, smem, Q, K, V)[0]
+    assert torch.equal(inf, out)
+    o64, a64, dQ, dK, dV = _oracle(g, X)
+    assert_close("out", out, o64)
+    assert_close("attn_edge", attn, a64)
+    assert_close("grad_Q", gq, dQ)
+    assert_close("grad_K", gk, dK)
+    assert_close("grad_V", gv, dV)
+    # the same CSR without the plan runs the general kernels: same numbers within tolerance
+    rp2 = row_ptr.clone()
+    out2, attn2 = N.gt_hyper_forward(rp2, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V)
+    assert _lib.last_kernel(0) == "dot_fwd_kernel"
+    gq2, gk2, gv2 = N.gt_backward(rp2, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V, attn2, dO)
+    for name, a, b in (("out", out, out2), ("attn", attn, attn2), ("gq", gq, gq2), ("gk", gk, gk2), ("gv", gv, gv2)):
+        assert_close("block vs general " + name, a, b)
+
+
+def test_block_path_under_autograd_and_weighted_scores(cuda):
+    g = _batch("pattern")
+    n = g.num_nodes()
+    A, rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx, smem = preprocess_Hyper_fw_bw(g.to(cuda))
+    X = graphs.conv_inputs(n, 128, 19)
+    Q, K, V = (t.to(cuda).requires_grad_() for t in (X.Q, X.K, X.V))
+    out = GTConvFuse_hyper(rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx, smem, Q, K, V)
+    out.backward(X.dO.to(cuda))
+    # the plan travels with row_ptr through save_for_backward
+    assert _lib.last_kernel(1) == "gt_block_bwd_row_kernel"
+    o64, a64, dQ, dK, dV = _oracle(g, X)
+    assert_close("out", out, o64)
+    assert_close("dQ", Q.grad, dQ)
+    assert_close("dK", K.grad, dK)
+    assert_close("dV", V.grad, dV)
+    # weighted scores through the block kernels vs fp64 autograd
+    gen = torch.Generator().manual_seed(3)
+    w = (0.5 + torch.rand(col_ind.numel(), generator=gen)).to(cuda)
+    Qd, Kd, Vd = (t.detach() for t in (Q, K, V))
+    o, attn = N.gt_hyper_forward(row_ptr, col_ind, rows, w, col_ptr, row_ind, val_idx, smem, Qd, Kd, Vd)
+    assert _lib.last_kernel(0) == "gt_block_fwd_kernel"
+    gq, gk, gv = N.gt_backward(row_ptr, col_ind, rows, w, col_ptr, row_ind, val_idx, smem, Qd, Kd, Vd, attn,
+                               X.dO.to(cuda))
+    r, c = A.row.long(), A.col.long()   # sorted by (row, col): CSR order
+    Q6, K6, V6 = (t[:, 0].double().requires_grad_() for t in (Qd, Kd, Vd))
+    s = (Q6[r] * K6[c]).sum(-1) * w.double()
+    mx = torch.full((n,), -1e300, dtype=torch.float64, device=cuda).scatter_reduce(0, r, s, "amax")
+    ex = torch.exp(s - mx[r])
+    p = ex / torch.zeros(n, dtype=torch.float64, device=cuda).index_add(0, r, ex)[r]
+    ref = torch.zeros_like(V6).index_add(0, r, p[:, None] * V6[c])
+    ref.backward(X.dO.to(cuda)[:, 0].double())
+    assert_close("weighted out", o[:, 0], ref.detach())
+    assert_close("weighted dQ", gq[:, 0], Q6.grad)
+    assert_close("weighted dK", gk[:, 0], K6.grad)
+    assert_close("weighted dV", gv[:, 0], V6.grad)
+
+
+def test_block_plan_validation_and_fallbacks(cuda):
+    g = _batch("pattern")
+    gd = g.to(cuda)
+    row_ptr, col_ind, rows, val, smem = preprocess_Hyper(gd)
+    assert getattr(row_ptr, "_dfgnn_blocks", None) is not None
+    # wrong node ranges: an edge leaves its block
+    bnn = g.batch_num_nodes().clone()
+    bnn[0] -= 5
+    bnn[1] += 5
+    with pytest.raises(RuntimeError, match="not block diagonal"):
+        formats.block_plan(bnn, row_ptr, col_ind)
+    with pytest.raises(RuntimeError, match="sums to"):
+        formats.block_plan(bnn[:-1], row_ptr, col_ind)
+    # sizes the stage cannot hold (VOC-shaped graphs: ~480 nodes x 128 floats x 2 > 227 KB), several
+    # heads, or short rows fall back to the general kernels
+    plan = row_ptr._dfgnn_blocks
+    n, nnz = g.num_nodes(), col_ind.numel()
+    assert plan.supported(n, nnz, 1, 128) and not plan.supported(n, nnz, 2, 64)
+    assert not plan.supported(n, nnz, 1, 48)
+    big = formats.BlockPlan(plan.blk_ptr, plan.n_blocks, 480)
+    assert not big.supported(n, nnz, 1, 128) and big.supported(n, nnz, 1, 32)
+    gv = graphs.pascalvoc_like(batch=2).to(cuda)
+    rp, ci, rws, vl, sm = preprocess_Hyper(gv)
+    X = graphs.conv_inputs(gv.num_nodes(), 128, 1)
+    N.gt_hyper_inference(rp, ci, rws, vl, sm, X.Q.to(cuda), X.K.to(cuda), X.V.to(cuda))
+    assert _lib.last_kernel(0) == "dot_fwd_kernel"
