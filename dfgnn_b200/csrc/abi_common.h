@@ -27,7 +27,7 @@ namespace dfgnn {
 
 void set_error(const char* fmt, ...);
 // which kernel family the last forward (slot 0) / backward row side (1) / column side (2) call of
-// this thread dispatched to (dfgnn_last_kernel; bench.py labels its per-kernel numbers with it)
+// this process dispatched to (dfgnn_last_kernel; bench.py labels its per-kernel numbers with it)
 void note_kernel(int slot, const char* name);
 std::atomic<uint64_t>& launch_counter();
 

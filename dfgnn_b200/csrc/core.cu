@@ -15,10 +15,11 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-static thread_local const char* g_last_kernel[3] = {"", "", ""};
+// process-wide (autograd runs the backward on its own thread, the caller asks from another)
+static std::atomic<const char*> g_last_kernel[3] = {{""}, {""}, {""}};
 
 void note_kernel(int slot, const char* name) {
-  if (slot >= 0 && slot < 3) g_last_kernel[slot] = name;
+  if (slot >= 0 && slot < 3) g_last_kernel[slot].store(name, std::memory_order_relaxed);
 }
 
 std::atomic<uint64_t>& launch_counter() {
@@ -34,7 +35,7 @@ int dfgnn_abi_version(void) { return DFGNN_ABI_VERSION; }
 const char* dfgnn_last_error(void) { return dfgnn::g_err; }
 uint64_t dfgnn_launch_count(void) { return dfgnn::launch_counter().load(); }
 const char* dfgnn_last_kernel(int slot) {
-  return (slot >= 0 && slot < 3) ? dfgnn::g_last_kernel[slot] : "";
+  return (slot >= 0 && slot < 3) ? dfgnn::g_last_kernel[slot].load(std::memory_order_relaxed) : "";
 }
 
 }  // extern "C"

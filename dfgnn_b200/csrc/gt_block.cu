@@ -6,15 +6,17 @@
 namespace dfgnn {
 
 // The block kernels pay when a staged row is reused often enough: mean degree >= kBlockMinDegree.
-// DFGNN_B200_BLOCK=0 disables them, =1 uses them whenever they fit (developer / test knob).
+// Mode (dfgnn_set_block_mode; initial value from DFGNN_B200_BLOCK=0|1): 0 auto, 1 off, 2 whenever
+// they fit.
 constexpr double kBlockMinDegree = 8.0;
-static int block_override() {
-  static const int v = [] {
+static std::atomic<int>& block_mode() {
+  static std::atomic<int> v{[] {
     const char* e = getenv("DFGNN_B200_BLOCK");
     return e ? (e[0] == '0' ? 1 : 2) : 0;
-  }();
+  }()};
   return v;
 }
+static int block_override() { return block_mode().load(std::memory_order_relaxed); }
 
 static size_t smem_limit() {
   static const size_t lim = [] {
@@ -89,6 +91,11 @@ int dfgnn_block_plan_check(int n_blocks, int m, int nnz, const int32_t* blk_ptr,
   }
   *max_nodes_out = h_flag[1];
   return DFGNN_OK;
+}
+
+int dfgnn_set_block_mode(int mode) {
+  if (mode < 0 || mode > 2) return block_override();
+  return block_mode().exchange(mode);
 }
 
 int dfgnn_gt_block_supported(int max_nodes, int m, int nnz, int h, int f) {

@@ -124,7 +124,7 @@ class BlockPlan:
         self._ok = {}
 
     def supported(self, m: int, nnz: int, h: int, f: int) -> bool:
-        key = (m, nnz, h, f)
+        key = (m, nnz, h, f, _lib.lib().dfgnn_set_block_mode(-1))
         if key not in self._ok:
             self._ok[key] = bool(_lib.lib().dfgnn_gt_block_supported(self.max_nodes, m, nnz, h, f))
         return self._ok[key]
@@ -169,3 +169,31 @@ def attach_block_plan(g, row_ptr: torch.Tensor, col_ind: torch.Tensor):
     plan = block_plan(bnn, row_ptr, col_ind)
     if plan is not None:
         row_ptr._dfgnn_blocks = plan
+        _register_plan(row_ptr, plan)
+
+
+# Tensors that come back from autograd's save_for_backward are new Python objects over the same
+# memory: the plan is also findable by address for as long as the tensor it was attached to lives
+# (its memory cannot be reused before that).
+_PLANS = {}
+
+
+def _register_plan(row_ptr: torch.Tensor, plan) -> None:
+    import weakref
+    dead = [k for k, (ref, _) in _PLANS.items() if ref() is None]
+    for k in dead:
+        del _PLANS[k]
+    _PLANS[(row_ptr.data_ptr(), row_ptr.numel())] = (weakref.ref(row_ptr), plan)
+
+
+def find_block_plan(row_ptr: torch.Tensor):
+    plan = getattr(row_ptr, "_dfgnn_blocks", None)
+    if plan is not None:
+        return plan
+    hit = _PLANS.get((row_ptr.data_ptr(), row_ptr.numel()))
+    if hit is None:
+        return None
+    owner = hit[0]()
+    if owner is None or owner.data_ptr() != row_ptr.data_ptr() or owner.device != row_ptr.device:
+        return None
+    return hit[1]

@@ -46,7 +46,8 @@ def _val_ptr(val):
 def _blocks(row_ptr, m, nnz, h, f):
     """The block plan the preprocessing attached to row_ptr (formats.attach_block_plan), if the
     graph-resident kernels support this size; else None (general kernels)."""
-    plan = getattr(row_ptr, "_dfgnn_blocks", None)
+    from ..formats import find_block_plan
+    plan = find_block_plan(row_ptr)
     if plan is None or plan.blk_ptr.device != row_ptr.device or not plan.supported(m, nnz, h, f):
         return None
     return plan

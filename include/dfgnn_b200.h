@@ -54,7 +54,7 @@ int dfgnn_abi_version(void);
 const char *dfgnn_last_error(void);
 /* Number of kernels this library has launched in this process (all entry points). */
 uint64_t dfgnn_launch_count(void);
-/* Name of the kernel the calling thread's last forward (slot 0), backward row-side (slot 1) or
+/* Name of the kernel the process's last forward (slot 0), backward row-side (slot 1) or
  * backward column-side (slot 2) call dispatched to, e.g. "gat_fwd_staged_kernel"; "" if none. */
 const char *dfgnn_last_kernel(int slot);
 
@@ -179,6 +179,9 @@ int dfgnn_block_plan_check(int n_blocks, int m, int nnz, const int32_t *blk_ptr,
                            const int32_t *row_ptr, const int32_t *col_ind, int32_t *flag_ws,
                            int32_t *max_nodes_out, void *stream);
 int dfgnn_gt_block_supported(int max_nodes, int m, int nnz, int h, int f);
+/* 0 = automatic choice (default), 1 = never use the block kernels, 2 = use them whenever the
+ * stage fits; returns the previous mode (an out-of-range argument only queries). */
+int dfgnn_set_block_mode(int mode);
 /* = dfgnn_gt_hyper_forward (attn_edge may be NULL: inference). */
 int dfgnn_gt_block_forward(int n_blocks, const int32_t *blk_ptr, int max_nodes, int m, int nnz,
                            int h, int f, const int32_t *row_ptr, const int32_t *col_ind,

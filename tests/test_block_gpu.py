@@ -17,6 +17,15 @@ from .helpers import assert_close
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _force_block_kernels():
+    """Mode 2: the block kernels run whenever the stage fits (the automatic choice is tuned for
+    speed, these tests are about correctness)."""
+    prev = _lib.lib().dfgnn_set_block_mode(2)
+    yield
+    _lib.lib().dfgnn_set_block_mode(prev)
+
+
 def _batch(kind):
     if kind == "pattern":      # largest graph <= 159 nodes: 16 warps per CTA in all three kernels
         return graphs.batched_graph(8, 110.0, 20.0, 50, 150, 51.0, 11.0, 1, None, 3, "pattern-small")
