@@ -2,17 +2,19 @@
 // batches of small graphs, and the block-plan validation.
 #include "abi_common.h"
 #include "block_gt.cuh"
+#include "dense_gt.cuh"
 
 namespace dfgnn {
 
-// The block kernels pay when a staged row is reused often enough: mean degree >= kBlockMinDegree.
-// Mode (dfgnn_set_block_mode; initial value from DFGNN_B200_BLOCK=0|1): 0 auto, 1 off, 2 whenever
-// they fit.
-constexpr double kBlockMinDegree = 8.0;
+// Mode (dfgnn_set_block_mode; initial value from DFGNN_B200_BLOCK=0|1|2): 0 auto, 1 off, 2 the
+// shared-memory-staged sparse kernels (block_gt.cuh) whenever they fit, 3 the dense tensor-core
+// kernels (dense_gt.cuh) whenever they fit.  Auto: dense kernels for dense batches (the caller
+// checks the density), never the staged sparse ones (measured slower than the row-block kernels on
+// the PATTERN-shaped batch: both are instruction-issue bound).
 static std::atomic<int>& block_mode() {
   static std::atomic<int> v{[] {
     const char* e = getenv("DFGNN_B200_BLOCK");
-    return e ? (e[0] == '0' ? 1 : 2) : 0;
+    return e ? (e[0] == '0' ? 1 : (e[0] == '2' ? 3 : 2)) : 0;
   }()};
   return v;
 }
@@ -48,15 +50,20 @@ static int pick_nw(int max_nodes, int f) {
 }
 
 static bool block_supported(int max_nodes, int m, int nnz, int h, int f) {
-  if (block_override() == 1 || h != 1 || m <= 0 || nnz <= 0 || max_nodes <= 0) return false;
+  if (block_override() != 2 || h != 1 || m <= 0 || nnz <= 0 || max_nodes <= 0) return false;
   bool fits = false;
   if (!dispatch_block_layout(f, [&](auto tag) {
         using L = typename decltype(tag)::type;
         fits = pick_nw<L, 1>(max_nodes, f) > 0 && pick_nw<L, 2>(max_nodes, f) > 0;
       }))
     return false;
-  if (!fits) return false;
-  return block_override() == 2 || (double)nnz / (double)m >= kBlockMinDegree;
+  return fits;
+}
+
+// dense tensor-core kernels: f in {64, 128}, unweighted scores, stage fits
+static bool dense_supported(int max_nodes, int h, int f) {
+  if (h != 1 || (f != 64 && f != 128) || max_nodes < 1) return false;
+  return DenseSmem(max_nodes, f).bytes <= smem_limit() - 64;
 }
 
 template <class K, class P>
@@ -94,12 +101,40 @@ int dfgnn_block_plan_check(int n_blocks, int m, int nnz, const int32_t* blk_ptr,
 }
 
 int dfgnn_set_block_mode(int mode) {
-  if (mode < 0 || mode > 2) return block_override();
+  if (mode < 0 || mode > 3) return block_override();
   return block_mode().exchange(mode);
 }
 
 int dfgnn_gt_block_supported(int max_nodes, int m, int nnz, int h, int f) {
   return block_supported(max_nodes, m, nnz, h, f) ? 1 : 0;
+}
+
+int dfgnn_gt_dense_supported(int max_nodes, int h, int f) {
+  const int mode = block_override();
+  return ((mode == 0 || mode == 3) && dense_supported(max_nodes, h, f)) ? 1 : 0;
+}
+
+int dfgnn_gt_dense_forward(int n_blocks, const int32_t* blk_ptr, int max_nodes, int m, int nnz, int h, int f,
+                           const int32_t* row_ptr, const int32_t* col_ind, const float* Q, const float* K,
+                           const float* V, float* out_feat, float* attn_edge, void* stream) {
+  const char* fn = "dfgnn_gt_dense_forward";
+  if (int rc = check_common(fn, m, nnz, h, f)) return rc;
+  if (m == 0) return DFGNN_OK;
+  DFGNN_REQUIRE(blk_ptr, fn); DFGNN_REQUIRE(row_ptr, fn);
+  if (nnz > 0) DFGNN_REQUIRE(col_ind, fn);
+  DFGNN_REQUIRE(Q, fn); DFGNN_REQUIRE(K, fn); DFGNN_REQUIRE(V, fn); DFGNN_REQUIRE(out_feat, fn);
+  if (n_blocks < 1 || !dense_supported(max_nodes, h, f)) {
+    set_error("%s: needs h == 1, f in {64, 128} and a stage that fits (h=%d, f=%d, max_nodes=%d)", fn, h, f, max_nodes);
+    return DFGNN_ERR_UNSUPPORTED_DIM;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  GtBlockFwdParams p{{m, nnz, h, f, 0, row_ptr, col_ind, nullptr, Q, K, V, nullptr, out_feat, nnz > 0 ? attn_edge : nullptr},
+                     {blk_ptr, n_blocks, max_nodes}};
+  const size_t smem = DenseSmem(max_nodes, f).bytes;
+  if (f == 128) launch_block(gt_dense_fwd_kernel<128, 8>, n_blocks, 8, smem, st, p);
+  else launch_block(gt_dense_fwd_kernel<64, 8>, n_blocks, 8, smem, st, p);
+  note_kernel(0, "gt_dense_fwd_kernel");
+  return check_launch(fn);
 }
 
 int dfgnn_gt_block_forward(int n_blocks, const int32_t* blk_ptr, int max_nodes, int m, int nnz, int h, int f,

@@ -117,11 +117,32 @@ class BlockPlan:
     (``row_ptr._dfgnn_blocks``): the operators then run the graph-resident kernels
     (csrc/block_gt.cuh) for the sizes they support."""
 
-    def __init__(self, blk_ptr: torch.Tensor, n_blocks: int, max_nodes: int):
+    # dense tensor-core kernels from this fill ratio of the diagonal blocks on (automatic mode)
+    DENSE_MIN_FILL = 0.15
+
+    def __init__(self, blk_ptr: torch.Tensor, n_blocks: int, max_nodes: int, sum_sq_nodes: int = 0):
         self.blk_ptr = blk_ptr
         self.n_blocks = int(n_blocks)
         self.max_nodes = int(max_nodes)
+        self.sum_sq_nodes = int(sum_sq_nodes)   # sum over graphs of nodes^2 = entries of the dense blocks
         self._ok = {}
+
+    def algorithm(self, m: int, nnz: int, h: int, f: int, unweighted: bool) -> int:
+        """0 general kernels, 1 shared-memory-staged sparse kernels, 2 dense tensor-core kernels
+        (forward); see dfgnn_set_block_mode."""
+        L = _lib.lib()
+        mode = L.dfgnn_set_block_mode(-1)
+        key = ("algo", m, nnz, h, f, unweighted, mode)
+        if key not in self._ok:
+            algo = 0
+            if unweighted and L.dfgnn_gt_dense_supported(self.max_nodes, h, f):
+                fill = nnz / self.sum_sq_nodes if self.sum_sq_nodes > 0 else 0.0
+                if mode == 3 or fill >= self.DENSE_MIN_FILL:
+                    algo = 2
+            if algo == 0 and L.dfgnn_gt_block_supported(self.max_nodes, m, nnz, h, f):
+                algo = 1
+            self._ok[key] = algo
+        return self._ok[key]
 
     def supported(self, m: int, nnz: int, h: int, f: int) -> bool:
         key = (m, nnz, h, f, _lib.lib().dfgnn_set_block_mode(-1))
@@ -153,7 +174,7 @@ def block_plan(batch_num_nodes: torch.Tensor, row_ptr: torch.Tensor, col_ind: to
             col_ind.data_ptr() if col_ind.numel() else None, flag.data_ptr(), ctypes.addressof(mx),
             torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(rc, "block_plan")
-    return BlockPlan(blk, bnn.numel(), mx.value)
+    return BlockPlan(blk, bnn.numel(), mx.value, int((bnn * bnn).sum()))
 
 
 def attach_block_plan(g, row_ptr: torch.Tensor, col_ind: torch.Tensor):

@@ -43,14 +43,19 @@ def _val_ptr(val):
     return None if (val is None or getattr(val, "_dfgnn_ones", False)) else _ptr(val)
 
 
-def _blocks(row_ptr, m, nnz, h, f):
-    """The block plan the preprocessing attached to row_ptr (formats.attach_block_plan), if the
-    graph-resident kernels support this size; else None (general kernels)."""
+def _blocks(row_ptr, m, nnz, h, f, val=None, backward=False):
+    """-> (plan, algo): the block plan the preprocessing attached to row_ptr
+    (formats.attach_block_plan) and the kernel family for this call -- 0 general, 1 shared-memory
+    staged (block_gt.cuh), 2 dense tensor-core (dense_gt.cuh, forward only)."""
     from ..formats import find_block_plan
     plan = find_block_plan(row_ptr)
-    if plan is None or plan.blk_ptr.device != row_ptr.device or not plan.supported(m, nnz, h, f):
-        return None
-    return plan
+    if plan is None or plan.blk_ptr.device != row_ptr.device:
+        return None, 0
+    unweighted = val is None or getattr(val, "_dfgnn_ones", False)
+    algo = plan.algorithm(m, nnz, h, f, unweighted)
+    if backward and algo == 2:
+        algo = 1 if plan.supported(m, nnz, h, f) else 0
+    return (plan, algo) if algo else (None, 0)
 
 
 def _stream(ref: torch.Tensor):
@@ -85,19 +90,28 @@ def _check_gt(fn, indptr, indices, Q, K, V, rows=None, val=None):
 # module `fused_gtconv`                                                         #
 # ----------------------------------------------------------------------------- #
 
+def _block_forward(plan, algo, m, nnz, h, f, row_ptr, col_ind, val, Q, K, V, out, attn):
+    L = _lib.lib()
+    if algo == 2:
+        return L.dfgnn_gt_dense_forward(plan.n_blocks, _ptr(plan.blk_ptr), plan.max_nodes, m, nnz, h, f,
+                                        _ptr(row_ptr), _ptr(col_ind), _ptr(Q), _ptr(K), _ptr(V), _ptr(out),
+                                        _ptr(attn), _stream(Q))
+    return L.dfgnn_gt_block_forward(plan.n_blocks, _ptr(plan.blk_ptr), plan.max_nodes, m, nnz, h, f,
+                                    _ptr(row_ptr), _ptr(col_ind), _val_ptr(val), _ptr(Q), _ptr(K), _ptr(V),
+                                    _ptr(out), _ptr(attn), _stream(Q))
+
+
 def gt_hyper_forward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem_consume,
                      Q, K, V) -> List[torch.Tensor]:
     """fused_gtconv.cpp:79-116 -> [out_feat (m,h,f), attn_edge (h,nnz)]."""
     fn = "gt_hyper_forward"
     m, nnz, h, f = _check_gt(fn, row_ptr, col_ind, Q, K, V, rows, val)
-    plan = _blocks(row_ptr, m, nnz, h, f) if K.shape[0] == m else None
+    plan, algo = _blocks(row_ptr, m, nnz, h, f, val) if K.shape[0] == m else (None, 0)
     with torch.cuda.device(Q.device):
         out = torch.empty_like(Q)
         attn = torch.empty((h, nnz), dtype=torch.float32, device=Q.device)
         if plan is not None:
-            rc = _lib.lib().dfgnn_gt_block_forward(
-                plan.n_blocks, _ptr(plan.blk_ptr), plan.max_nodes, m, nnz, h, f, _ptr(row_ptr), _ptr(col_ind),
-                _val_ptr(val), _ptr(Q), _ptr(K), _ptr(V), _ptr(out), _ptr(attn), _stream(Q))
+            rc = _block_forward(plan, algo, m, nnz, h, f, row_ptr, col_ind, val, Q, K, V, out, attn)
             _lib.check(rc, fn)
             return [out, attn]
         rc = _lib.lib().dfgnn_gt_hyper_forward(
@@ -140,7 +154,7 @@ def gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem_con
         tail = (m, n, nnz, h, f, _ptr(row_ptr), _ptr(col_ind), _ptr(rows), _val_ptr(val), _ptr(col_ptr),
                 _ptr(row_ind), _ptr(val_idx), int(smem_consume), _ptr(Q), _ptr(K), _ptr(V),
                 _ptr(attn_edge), _ptr(grad), _ptr(gq), _ptr(gk), _ptr(gv), _ptr(ge), _stream(Q))
-        plan = _blocks(row_ptr, m, nnz, h, f) if (n == m and _cols is None) else None
+        plan, _algo = _blocks(row_ptr, m, nnz, h, f, val, backward=True) if (n == m and _cols is None) else (None, 0)
         if plan is not None:
             rc = _lib.lib().dfgnn_gt_block_backward(
                 int(_phases), plan.n_blocks, _ptr(plan.blk_ptr), plan.max_nodes, m, nnz, h, f, _ptr(row_ptr),
@@ -161,13 +175,11 @@ def gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem_con
 
 def _gt_inference(cname, fn, indptr, indices, rows, val, smem_consume, Q, K, V, has_rows, has_smem):
     m, nnz, h, f = _check_gt(fn, indptr, indices, Q, K, V, rows, val)
-    plan = _blocks(indptr, m, nnz, h, f) if K.shape[0] == m else None
+    plan, algo = _blocks(indptr, m, nnz, h, f, val) if K.shape[0] == m else (None, 0)
     with torch.cuda.device(Q.device):
         out = torch.empty_like(Q)
         if plan is not None:
-            rc = _lib.lib().dfgnn_gt_block_forward(
-                plan.n_blocks, _ptr(plan.blk_ptr), plan.max_nodes, m, nnz, h, f, _ptr(indptr), _ptr(indices),
-                _val_ptr(val), _ptr(Q), _ptr(K), _ptr(V), _ptr(out), None, _stream(Q))
+            rc = _block_forward(plan, algo, m, nnz, h, f, indptr, indices, val, Q, K, V, out, None)
             _lib.check(rc, fn)
             return out
         args = [m, nnz, h, f, _ptr(indptr), _ptr(indices)]

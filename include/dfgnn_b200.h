@@ -172,21 +172,32 @@ int dfgnn_gt_backward_cols(int col_begin, int n_sub, int nnz_sub, int m, int n, 
  * dfgnn_block_plan_check validates that every column id of a block's rows lies inside the block
  * (one small device -> host readback; flag_ws = 2 ints of device scratch) and returns the largest
  * block in *max_nodes_out (host).  dfgnn_gt_block_supported tells whether the block kernels would
- * be used for this size (h == 1, f in {32, 64, 128}, both operand blocks of the largest graph fit
- * shared memory, mean degree >= 8); callers fall back to the general entry points otherwise.
+ * be used for this size in the current mode (h == 1, f in {32, 64, 128}, both operand blocks of
+ * the largest graph fit shared memory); callers fall back to the general entry points otherwise.
  */
 int dfgnn_block_plan_check(int n_blocks, int m, int nnz, const int32_t *blk_ptr,
                            const int32_t *row_ptr, const int32_t *col_ind, int32_t *flag_ws,
                            int32_t *max_nodes_out, void *stream);
 int dfgnn_gt_block_supported(int max_nodes, int m, int nnz, int h, int f);
-/* 0 = automatic choice (default), 1 = never use the block kernels, 2 = use them whenever the
- * stage fits; returns the previous mode (an out-of-range argument only queries). */
+/* 0 = automatic choice (default: the dense kernels below for dense batches), 1 = general kernels
+ * only, 2 = the shared-memory-staged sparse kernels whenever they fit, 3 = the dense kernels
+ * whenever they fit; returns the previous mode (an out-of-range argument only queries). */
 int dfgnn_set_block_mode(int mode);
 /* = dfgnn_gt_hyper_forward (attn_edge may be NULL: inference). */
 int dfgnn_gt_block_forward(int n_blocks, const int32_t *blk_ptr, int max_nodes, int m, int nnz,
                            int h, int f, const int32_t *row_ptr, const int32_t *col_ind,
                            const float *val, const float *Q, const float *K, const float *V,
                            float *out_feat, float *attn_edge, void *stream);
+/*
+ * Dense tensor-core variant for batches of DENSE small graphs (csrc/dense_gt.cuh: masked
+ * 16-row tiles, mma.sync TF32 with the 3xTF32 split): unweighted scores (val == all ones), h == 1,
+ * f in {64, 128}.  Same outputs as dfgnn_gt_hyper_forward.
+ */
+int dfgnn_gt_dense_supported(int max_nodes, int h, int f);
+int dfgnn_gt_dense_forward(int n_blocks, const int32_t *blk_ptr, int max_nodes, int m, int nnz,
+                           int h, int f, const int32_t *row_ptr, const int32_t *col_ind,
+                           const float *Q, const float *K, const float *V, float *out_feat,
+                           float *attn_edge, void *stream);
 /* = dfgnn_gt_backward_phase on a square block-diagonal adjacency (n == m). */
 int dfgnn_gt_block_backward(int phases, int n_blocks, const int32_t *blk_ptr, int max_nodes, int m,
                             int nnz, int h, int f, const int32_t *row_ptr, const int32_t *col_ind,

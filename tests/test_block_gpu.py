@@ -57,7 +57,7 @@ def test_block_kernels_match_oracle_and_general_kernels(cuda, kind, dim):
     plan = getattr(row_ptr, "_dfgnn_blocks", None)
     assert plan is not None and plan.n_blocks == g.batch_size
     assert plan.max_nodes == int(g.batch_num_nodes().max())
-    assert plan.supported(n, col_ind.numel(), 1, dim), "the batch should run on the block kernels"
+    assert plan.algorithm(n, col_ind.numel(), 1, dim, True) == 1, "the batch should run on the block kernels"
     Q, K, V, dO = (t.to(cuda) for t in (X.Q, X.K, X.V, X.dO))
     out, attn = N.gt_hyper_forward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V)
     assert _lib.last_kernel(0) == "gt_block_fwd_kernel"
@@ -138,8 +138,43 @@ def test_block_plan_validation_and_fallbacks(cuda):
     assert not plan.supported(n, nnz, 1, 48)
     big = formats.BlockPlan(plan.blk_ptr, plan.n_blocks, 480)
     assert not big.supported(n, nnz, 1, 128) and big.supported(n, nnz, 1, 32)
+    _lib.lib().dfgnn_set_block_mode(3)
+    assert plan.algorithm(n, nnz, 1, 128, True) == 2 and plan.algorithm(n, nnz, 1, 128, False) == 0
+    assert plan.algorithm(n, nnz, 1, 32, True) == 0 and big.algorithm(n, nnz, 1, 128, True) == 0
+    _lib.lib().dfgnn_set_block_mode(2)
     gv = graphs.pascalvoc_like(batch=2).to(cuda)
     rp, ci, rws, vl, sm = preprocess_Hyper(gv)
     X = graphs.conv_inputs(gv.num_nodes(), 128, 1)
     N.gt_hyper_inference(rp, ci, rws, vl, sm, X.Q.to(cuda), X.K.to(cuda), X.V.to(cuda))
     assert _lib.last_kernel(0) == "dot_fwd_kernel"
+
+
+@pytest.mark.parametrize("kind,dim", [("pattern", 128), ("pattern", 64), ("pattern-max", 128), ("ragged", 128),
+                                      ("ragged", 64)])
+def test_dense_tensor_core_forward(cuda, kind, dim):
+    """dense_gt.cuh: masked 16-row tiles on the tensor cores (mma.sync TF32, 3xTF32 split) --
+    out and attn_edge against the fp64 oracle, training and inference entry points."""
+    _lib.lib().dfgnn_set_block_mode(3)
+    g = _batch(kind)
+    n = g.num_nodes()
+    X = graphs.conv_inputs(n, dim, 23)
+    A, rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx, smem = preprocess_Hyper_fw_bw(g.to(cuda))
+    Q, K, V, dO = (t.to(cuda) for t in (X.Q, X.K, X.V, X.dO))
+    out, attn = N.gt_hyper_forward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V)
+    assert _lib.last_kernel(0) == "gt_dense_fwd_kernel"
+    o64, a64, dQ, dK, dV = _oracle(g, X)
+    assert_close("out", out, o64)
+    assert_close("attn_edge", attn, a64)
+    inf = N.gt_hyper_inference(row_ptr, col_ind, rows, val, smem, Q, K, V)[0]
+    assert _lib.last_kernel(0) == "gt_dense_fwd_kernel"
+    assert torch.equal(inf, out)
+    # the backward (general or staged kernels) consumes the dense forward's attn_edge
+    gq, gk, gv = N.gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V, attn, dO)
+    assert_close("grad_Q", gq, dQ)
+    assert_close("grad_K", gk, dK)
+    assert_close("grad_V", gv, dV)
+    # automatic mode picks the dense kernels from the fill ratio of the blocks
+    _lib.lib().dfgnn_set_block_mode(0)
+    plan = row_ptr._dfgnn_blocks
+    fill = col_ind.numel() / plan.sum_sq_nodes
+    assert plan.algorithm(n, col_ind.numel(), 1, dim, True) == (2 if fill >= plan.DENSE_MIN_FILL else 0)
