@@ -17,13 +17,15 @@
 // One CTA per graph: K and V rows are staged in shared memory by per-row TMA bulk copies into a
 // row stride of f + 4 floats (conflict-free B-fragment reads); the adjacency becomes a bit mask
 // (n x n bits) built from the CSR; each warp owns 16-row tiles of Q and runs a flash-style online
-// softmax over 64-column blocks.  The C fragment of S is reused as the A fragment of the second
+// softmax over 32-column blocks.  The C fragment of S is reused as the A fragment of the second
 // product by permuting the summation index (C holds columns {2t, 2t+1}, A wants {t, t+4}: read V
 // rows 2t and 2t+1 instead), so P never leaves registers.
 //
 // Maths and outputs are those of dot_fwd_kernel (out, attn_edge); the reference counterpart is
 // fused_gtconv_hyper.cu:31-163.
 #pragma once
+
+#include <type_traits>
 
 #include "block_gt.cuh"
 
@@ -35,10 +37,11 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
-// x = hi + lo with hi = x rounded to TF32 (10 mantissa bits); lo is exact in fp32 and is
-// truncated to TF32 by the tensor core (error <= 2^-21 |x|)
+// x = hi + lo with hi = x truncated to TF32 (10 mantissa bits, one LOP3 -- cvt.rna.tf32.f32 is a
+// seven-instruction sequence on sm_100a); lo = x - hi is exact in fp32 and is truncated to TF32 by
+// the tensor core (error <= 2^-20 |x|, like the dropped lo * lo term)
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  hi = __float_as_uint(x) & 0xffffe000u;
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
 // d += a * b in 3xTF32
@@ -49,7 +52,10 @@ __device__ __forceinline__ void mma_3x(float (&d)[4], const uint32_t (&ah)[4], c
   mma_tf32(d, ah, bh);
 }
 
-constexpr int kDenseCB = 64;  // columns per softmax block (8 n8-tiles)
+#ifndef DFGNN_DENSE_CB
+#define DFGNN_DENSE_CB 32
+#endif
+constexpr int kDenseCB = DFGNN_DENSE_CB;  // columns per softmax block (measured: 32 -> 0.354 ms, 64 -> 0.379 ms inference on PATTERN)
 
 // shared-memory carve of the dense kernels
 struct DenseSmem {
@@ -113,10 +119,27 @@ __device__ __forceinline__ void dense_stage(const DenseSmem& L, unsigned char* s
   for (int i = threadIdx.x; i <= n; i += NW * 32) s_rp[i] = __ldg(seg_ptr + lb + i);
   for (int i = threadIdx.x; i < n16 * L.W; i += NW * 32) s_mask[i] = 0u;
   __syncthreads();
-  for (int r = w; r < n; r += NW) {
-    for (int e = s_rp[r] + lane; e < s_rp[r + 1]; e += 32) {
-      const int j = __ldg(idx + e) - lb;
-      atomicOr(s_mask + r * L.W + (j >> 5), 1u << (j & 31));
+  // adjacency bits: a warp per row, four rows (eight coalesced index loads) in flight per warp
+  for (int r0 = w; r0 < n; r0 += 4 * NW) {
+    int j[4][2];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u * NW;
+      const int b = r < n ? s_rp[r] : 0, e = r < n ? s_rp[r + 1] : 0;
+      j[u][0] = b + lane < e ? __ldg(idx + b + lane) - lb : -1;
+      j[u][1] = b + lane + 32 < e ? __ldg(idx + b + lane + 32) - lb : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u * NW;
+#pragma unroll
+      for (int v = 0; v < 2; ++v)
+        if (j[u][v] >= 0) atomicOr(s_mask + r * L.W + (j[u][v] >> 5), 1u << (j[u][v] & 31));
+      if (r < n)
+        for (int e = s_rp[r] + 64 + lane; e < s_rp[r + 1]; e += 32) {  // rows of more than 64 entries
+          const int jj = __ldg(idx + e) - lb;
+          atomicOr(s_mask + r * L.W + (jj >> 5), 1u << (jj & 31));
+        }
     }
   }
   __syncthreads();
@@ -179,8 +202,9 @@ __global__ void __launch_bounds__(NW * 32, 1) gt_dense_fwd_kernel(const GtBlockF
     const uint32_t* mrow_a = s_mask + ra * W;  // rows < mn16: always inside the mask array
     const uint32_t* mrow_b = s_mask + rb * W;
 
-    for (int jb = 0; jb < n8; jb += CB) {
-      const int ntile = min(NB, (n8 - jb) >> 3);  // n8-tiles of this column block (warp-uniform)
+    // one 64-column block; FULL = all 8 n8-tiles present (branch-free inner loops)
+    auto column_block = [&](int jb, int ntile, auto full_tag) {
+      constexpr bool FULL = decltype(full_tag)::value;
       float s[NB][4];
 #pragma unroll
       for (int i = 0; i < NB; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
@@ -192,7 +216,7 @@ __global__ void __launch_bounds__(NW * 32, 1) gt_dense_fwd_kernel(const GtBlockF
         for (int i = 0; i < 4; ++i) split_tf32(qf[ks][i], ah[i], al[i]);
 #pragma unroll
         for (int nt = 0; nt < NB; ++nt) {
-          if (nt < ntile) {
+          if (FULL || nt < ntile) {
             const float* kp = sK + (size_t)(jb + 8 * nt + g) * LD + 8 * ks + t4;
             uint32_t bh[2], bl[2];
             split_tf32(kp[0], bh[0], bl[0]);
@@ -205,7 +229,7 @@ __global__ void __launch_bounds__(NW * 32, 1) gt_dense_fwd_kernel(const GtBlockF
       float bm_a = kNeg, bm_b = kNeg;
 #pragma unroll
       for (int nt = 0; nt < NB; ++nt) {
-        if (nt < ntile) {
+        if (FULL || nt < ntile) {
           const int c0 = jb + 8 * nt + 2 * t4, wd = c0 >> 5, bit = c0 & 31;
           const uint32_t ma = mrow_a[wd], mb = mrow_b[wd];
           const bool v0 = (ma >> bit) & 1u, v1 = (ma >> (bit + 1)) & 1u;
@@ -249,7 +273,7 @@ __global__ void __launch_bounds__(NW * 32, 1) gt_dense_fwd_kernel(const GtBlockF
       // every entry masked)
 #pragma unroll
       for (int nt = 0; nt < NB; ++nt) {
-        if (nt < ntile) {
+        if (FULL || nt < ntile) {
           s[nt][0] = s[nt][0] > 0.5f * kNeg ? fast_exp2(s[nt][0] - mn_a) : 0.f;
           s[nt][1] = s[nt][1] > 0.5f * kNeg ? fast_exp2(s[nt][1] - mn_a) : 0.f;
           s[nt][2] = s[nt][2] > 0.5f * kNeg ? fast_exp2(s[nt][2] - mn_b) : 0.f;
@@ -261,7 +285,7 @@ __global__ void __launch_bounds__(NW * 32, 1) gt_dense_fwd_kernel(const GtBlockF
       // ---- O += P V : the C fragment of S is the A fragment over the permuted k index -------
 #pragma unroll
       for (int kk = 0; kk < NB; ++kk) {
-        if (kk < ntile) {
+        if (FULL || kk < ntile) {
           uint32_t ah[4], al[4];
           split_tf32(s[kk][0], ah[0], al[0]);  // (row a, k-slot t)     = column 2t
           split_tf32(s[kk][2], ah[1], al[1]);  // (row b, k-slot t)
@@ -277,6 +301,11 @@ __global__ void __launch_bounds__(NW * 32, 1) gt_dense_fwd_kernel(const GtBlockF
           }
         }
       }
+    };
+    for (int jb = 0; jb < n8; jb += CB) {
+      const int ntile = min(NB, (n8 - jb) >> 3);  // n8-tiles of this column block (warp-uniform)
+      if (ntile == NB) column_block(jb, NB, std::true_type{});
+      else column_block(jb, ntile, std::false_type{});
     }
     // ---- finish the tile ----------------------------------------------------------------------
     l_a += __shfl_xor_sync(kFull, l_a, 1);
@@ -298,10 +327,9 @@ __global__ void __launch_bounds__(NW * 32, 1) gt_dense_fwd_kernel(const GtBlockF
   }
   if (train) {  // scores -> probabilities (attn_edge of fused_gtconv_hyper.cu:146-149)
     __syncthreads();
-    const int E0 = s_rp[0], E1 = s_rp[n];
-    for (int i = E0 + threadIdx.x; i < E1; i += NW * 32) {
-      const int rr = find_row(s_rp, n, i);
-      p.attn[i] = fast_exp2(p.attn[i] - s_m[rr]) * s_inv[rr];
+    for (int r = w; r < n; r += NW) {  // a warp per row: coalesced, no search
+      const float mr = s_m[r], ir = s_inv[r];
+      for (int i = s_rp[r] + lane; i < s_rp[r + 1]; i += 32) p.attn[i] = fast_exp2(p.attn[i] - mr) * ir;
     }
   }
 }

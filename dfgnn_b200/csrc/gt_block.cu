@@ -131,8 +131,11 @@ int dfgnn_gt_dense_forward(int n_blocks, const int32_t* blk_ptr, int max_nodes, 
   GtBlockFwdParams p{{m, nnz, h, f, 0, row_ptr, col_ind, nullptr, Q, K, V, nullptr, out_feat, nnz > 0 ? attn_edge : nullptr},
                      {blk_ptr, n_blocks, max_nodes}};
   const size_t smem = DenseSmem(max_nodes, f).bytes;
-  if (f == 128) launch_block(gt_dense_fwd_kernel<128, 8>, n_blocks, 8, smem, st, p);
-  else launch_block(gt_dense_fwd_kernel<64, 8>, n_blocks, 8, smem, st, p);
+#ifndef DFGNN_DENSE_NW
+#define DFGNN_DENSE_NW 8
+#endif
+  if (f == 128) launch_block(gt_dense_fwd_kernel<128, DFGNN_DENSE_NW>, n_blocks, DFGNN_DENSE_NW, smem, st, p);
+  else launch_block(gt_dense_fwd_kernel<64, DFGNN_DENSE_NW>, n_blocks, DFGNN_DENSE_NW, smem, st, p);
   note_kernel(0, "gt_dense_fwd_kernel");
   return check_launch(fn);
 }

@@ -127,17 +127,19 @@ class BlockPlan:
         self.sum_sq_nodes = int(sum_sq_nodes)   # sum over graphs of nodes^2 = entries of the dense blocks
         self._ok = {}
 
-    def algorithm(self, m: int, nnz: int, h: int, f: int, unweighted: bool) -> int:
+    def algorithm(self, m: int, nnz: int, h: int, f: int, unweighted: bool, training: bool = False) -> int:
         """0 general kernels, 1 shared-memory-staged sparse kernels, 2 dense tensor-core kernels
-        (forward); see dfgnn_set_block_mode."""
+        (forward); see dfgnn_set_block_mode.  Automatic mode picks the dense kernels for INFERENCE on
+        dense batches (measured on the PATTERN-shaped batch: 0.35 ms vs 0.41 ms); the training forward
+        also scatters attn_edge, which costs the dense tiles more than it gains (0.47 vs 0.44 ms)."""
         L = _lib.lib()
         mode = L.dfgnn_set_block_mode(-1)
-        key = ("algo", m, nnz, h, f, unweighted, mode)
+        key = ("algo", m, nnz, h, f, unweighted, training, mode)
         if key not in self._ok:
             algo = 0
             if unweighted and L.dfgnn_gt_dense_supported(self.max_nodes, h, f):
                 fill = nnz / self.sum_sq_nodes if self.sum_sq_nodes > 0 else 0.0
-                if mode == 3 or fill >= self.DENSE_MIN_FILL:
+                if mode == 3 or (fill >= self.DENSE_MIN_FILL and not training):
                     algo = 2
             if algo == 0 and L.dfgnn_gt_block_supported(self.max_nodes, m, nnz, h, f):
                 algo = 1

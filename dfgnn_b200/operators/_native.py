@@ -43,7 +43,7 @@ def _val_ptr(val):
     return None if (val is None or getattr(val, "_dfgnn_ones", False)) else _ptr(val)
 
 
-def _blocks(row_ptr, m, nnz, h, f, val=None, backward=False):
+def _blocks(row_ptr, m, nnz, h, f, val=None, backward=False, training=False):
     """-> (plan, algo): the block plan the preprocessing attached to row_ptr
     (formats.attach_block_plan) and the kernel family for this call -- 0 general, 1 shared-memory
     staged (block_gt.cuh), 2 dense tensor-core (dense_gt.cuh, forward only)."""
@@ -52,7 +52,7 @@ def _blocks(row_ptr, m, nnz, h, f, val=None, backward=False):
     if plan is None or plan.blk_ptr.device != row_ptr.device:
         return None, 0
     unweighted = val is None or getattr(val, "_dfgnn_ones", False)
-    algo = plan.algorithm(m, nnz, h, f, unweighted)
+    algo = plan.algorithm(m, nnz, h, f, unweighted, training or backward)
     if backward and algo == 2:
         algo = 1 if plan.supported(m, nnz, h, f) else 0
     return (plan, algo) if algo else (None, 0)
@@ -106,7 +106,7 @@ def gt_hyper_forward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, sme
     """fused_gtconv.cpp:79-116 -> [out_feat (m,h,f), attn_edge (h,nnz)]."""
     fn = "gt_hyper_forward"
     m, nnz, h, f = _check_gt(fn, row_ptr, col_ind, Q, K, V, rows, val)
-    plan, algo = _blocks(row_ptr, m, nnz, h, f, val) if K.shape[0] == m else (None, 0)
+    plan, algo = _blocks(row_ptr, m, nnz, h, f, val, training=True) if K.shape[0] == m else (None, 0)
     with torch.cuda.device(Q.device):
         out = torch.empty_like(Q)
         attn = torch.empty((h, nnz), dtype=torch.float32, device=Q.device)

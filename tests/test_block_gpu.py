@@ -178,3 +178,7 @@ def test_dense_tensor_core_forward(cuda, kind, dim):
     plan = row_ptr._dfgnn_blocks
     fill = col_ind.numel() / plan.sum_sq_nodes
     assert plan.algorithm(n, col_ind.numel(), 1, dim, True) == (2 if fill >= plan.DENSE_MIN_FILL else 0)
+    assert plan.algorithm(n, col_ind.numel(), 1, dim, True, training=True) == 0
+    inf2 = N.gt_hyper_inference(row_ptr, col_ind, rows, val, smem, Q, K, V)[0]
+    assert _lib.last_kernel(0) == ("gt_dense_fwd_kernel" if fill >= plan.DENSE_MIN_FILL else "dot_fwd_kernel")
+    assert_close("automatic mode inference", inf2, o64)
