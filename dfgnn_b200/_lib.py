@@ -52,6 +52,9 @@ _SIGNATURES = {
     "dfgnn_gt_dense_forward": (c_int, [c_int, _P] + [c_int] * 5 + [_P] * 7 + [_P]),
     "dfgnn_gt_block_forward": (c_int, [c_int, _P] + [c_int] * 5 + [_P] * 8 + [_P]),
     "dfgnn_gt_block_backward": (c_int, [c_int, c_int, _P] + [c_int] * 5 + [_P] * 15 + [_P]),
+    "dfgnn_proj_weight_image_floats": (c_size_t, [c_int, c_int]),
+    "dfgnn_proj_pack_weights": (c_int, [c_int, c_int, _P, _P, _P]),
+    "dfgnn_proj_forward": (c_int, [c_int] * 4 + [_P] * 8 + [c_int] + [_P] * 4 + [_P]),
     "dfgnn_gt_backward_cols": (c_int, [c_int] * 8 + [_P] * 7 + [c_int] + [_P] * 9 + [_P]),
     "dfgnn_gt_hyper_inference": (c_int, [c_int] * 4 + [_P] * 4 + [c_int] + [_P] * 4 + [_P]),
     "dfgnn_gt_softmax_inference": (c_int, [c_int] * 4 + [_P] * 4 + [c_int] + [_P] * 4 + [_P]),

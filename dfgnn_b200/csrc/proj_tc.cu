@@ -1,0 +1,374 @@
+// proj_tc.cu -- the dense projection in front of the conv on the 5th-generation tensor cores.
+//
+// Reference: q, k, v = Linear(h) (+ q *= d^-0.5) then reshape / transpose to [N, heads, d]
+// (DFGNN/layers/GT/gtconv_layer.py:19-27, gtconv_layer_fused.py:20-22), and for GAT
+// feat = W(x), attn_row = <a_l, feat>, attn_col = <a_r, feat> (layers/GAT/gatconv_layer_fused.py:
+// 121-123; fused logits kernel fused_gatconv_hyper_v2.cu:212-250): three fp32 cuBLAS GEMMs, a
+// scale, transposes and two reductions.  Measured on B200 for the PATTERN-shaped batch (121.8 k
+// nodes, 128 -> 3 x 128): 0.49 ms in fp32 (SIMT SGEMM), longer than the fused conv forward itself.
+//
+// Here: ONE kernel, Y = (X W^T + b) * scale written straight into the operands of the conv
+// ([N, heads * d] per part, i.e. [N, heads, d]), fp32-grade accuracy from TF32 tensor cores by the
+// 3xTF32 split (x = hi + lo; x w ~ hi*hi + hi*lo + lo*hi, fp32 accumulation in tensor memory), and
+// the GAT logits reduced in the epilogue from the accumulator rows.
+//
+//   tcgen05.mma.cta_group::1.kind::tf32, M = 128 (a tile of node rows), N = 64 (a slice of the
+//   output columns), K = 8 per instruction; operands in shared memory in the canonical K-major
+//   no-swizzle layout ("chunk major": 16-byte k-chunk c of row r at c * rows * 16 + r * 16, so
+//   SBO = 128 B between 8-row groups and LBO = rows * 16 B between the two chunks of one MMA);
+//   accumulator 128 lanes x 64 columns of tensor memory, read back with tcgen05.ld.32x32b.x32.
+//
+// A persistent CTA owns one 64-column slice of W for its lifetime -- the pre-split hi / lo images
+// of the slice (prepared once per weight update, dfgnn_proj_pack_weights) arrive by two TMA bulk
+// copies -- and walks over node tiles: all threads load the X tile (coalesced float4), split it
+// into hi / lo in registers and store both images to shared memory; one thread issues the
+// 3 * K/8 MMAs and commits to an mbarrier; the epilogue (bias, scale, logits) of tile t overlaps
+// the global loads of tile t+1.
+#include "abi_common.h"
+
+namespace dfgnn {
+
+constexpr int kProjM = 128;      // node rows per tile (UMMA M)
+constexpr int kProjN = 64;       // output columns per slice (UMMA N)
+constexpr int kProjThreads = 256;
+constexpr int kProjMaxK = 128;
+
+struct ProjParams {
+  int n, k, n_out;        // rows, input width, total output columns (multiple of 64)
+  int part_width;         // columns of one output tensor (q | k | v are three parts); multiple of 64
+  const float* x;         // [n, k]
+  const float* w_img;     // [2][n_out / 64][k / 4][64][4]: hi images then lo images
+  const float* bias;      // [n_out] or null
+  const float* scale;     // [n_out] or null
+  float* out[4];          // one [n, part_width] tensor per part
+  // GAT logits (optional): per head of width head_dim, attn_row = <a_l, y>, attn_col = <a_r, y>
+  int head_dim;           // 0: no logits
+  const float* a_l;       // [n_out]
+  const float* a_r;       // [n_out]
+  float* attn_row;        // [n, n_out / head_dim]
+  float* attn_col;
+};
+
+// ---- tcgen05 wrappers (PTX ISA; syntax as in CUTLASS cute/arch/mma_sm100_umma.hpp, copy_sm100.hpp) ----
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  // shared-memory matrix descriptor, SWIZZLE_NONE: start address, leading / stride byte offsets in
+  // 16-byte units, version 1 (Blackwell) at bits [46, 48)
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
+  // c = F32 (1 << 4), a = b = TF32 (2 << 7, 2 << 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy writes to shared memory -> visible to the async proxy (tensor core operand reads)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// x = hi + lo, hi = x truncated to TF32 (the tensor core ignores the 13 low mantissa bits anyway;
+// the mask makes hi exact whatever it does with them), lo exact in fp32
+__device__ __forceinline__ void split4(const float4 x, float4& hi, float4& lo) {
+  hi.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+  hi.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+  hi.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+  hi.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+  lo = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+}
+
+template <int K>
+__global__ void __launch_bounds__(kProjThreads, 1) proj_tf32x3_kernel(const ProjParams p) {
+  constexpr int CH = K / 4;                         // 16-byte k-chunks per row
+  constexpr int XV = kProjM * CH / kProjThreads;    // float4 of the X tile per thread
+  constexpr uint32_t A_LBO = kProjM * 16, B_LBO = kProjN * 16, SBO = 128;
+  constexpr uint32_t A_BYTES = kProjM * K * 4, B_BYTES = kProjN * K * 4;
+  static_assert(K % 8 == 0 && K <= kProjMaxK && (kProjM * CH) % kProjThreads == 0, "tile shape");
+  extern __shared__ __align__(128) unsigned char smem[];
+  float4* sA_hi = reinterpret_cast<float4*>(smem);
+  float4* sA_lo = reinterpret_cast<float4*>(smem + A_BYTES);
+  unsigned char* sB_hi = smem + 2 * A_BYTES;
+  unsigned char* sB_lo = sB_hi + B_BYTES;
+  __shared__ uint64_t s_bar_w, s_bar_mma;
+  __shared__ uint32_t s_tmem;
+
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int n_slices = p.n_out / kProjN;
+  const int slice = blockIdx.x % n_slices;
+  const int tiles = (p.n + kProjM - 1) / kProjM;
+  const int t_step = gridDim.x / n_slices;
+
+  // ---- one-time setup: barriers, tensor memory, the W slice images --------------------------
+  if (tid == 0) {
+    mbar_init(&s_bar_w, 1);
+    mbar_init(&s_bar_mma, 1);
+    mbar_fence_init();
+  }
+  if (w == 0) {  // 64 columns of tensor memory for the 128 x 64 fp32 accumulator
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(&s_tmem)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = s_tmem;
+  if (tid == 0) {
+    const size_t img = (size_t)kProjN * K;  // floats of one slice image
+    mbar_expect_tx(&s_bar_w, 2 * B_BYTES);
+    bulk_g2s_range(sB_hi, p.w_img + (size_t)slice * img, B_BYTES, &s_bar_w);
+    bulk_g2s_range(sB_lo, p.w_img + ((size_t)n_slices + slice) * img, B_BYTES, &s_bar_w);
+  }
+
+  // this thread's pieces of an X tile: float4 i = tid + u * threads covers row (i % 8) + 8 * (i / (8 * CH))
+  // and chunk (i / 8) % CH: a warp reads 8 rows x 64 contiguous bytes and writes 512 contiguous bytes
+  auto piece = [&](int u, int& r, int& c) {
+    const int i = tid + u * kProjThreads;
+    r = (i & 7) + 8 * (i / (8 * CH));
+    c = (i >> 3) % CH;
+  };
+  float4 xv[XV];
+  auto load_tile = [&](int t) {
+#pragma unroll
+    for (int u = 0; u < XV; ++u) {
+      int r, c;
+      piece(u, r, c);
+      const int row = t * kProjM + r;
+      xv[u] = row < p.n ? __ldg(reinterpret_cast<const float4*>(p.x + (size_t)row * K) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto store_tile = [&]() {
+#pragma unroll
+    for (int u = 0; u < XV; ++u) {
+      int r, c;
+      piece(u, r, c);
+      float4 hi, lo;
+      split4(xv[u], hi, lo);
+      sA_hi[c * kProjM + r] = hi;
+      sA_lo[c * kProjM + r] = lo;
+    }
+    fence_proxy_async();
+  };
+
+  // epilogue role of this warp: rows of TMEM lane quarter (w % 4), column half (w / 4)
+  const int q4 = w & 3, ch = w >> 2;
+  const int col0 = slice * kProjN + ch * 32;               // first output column of this thread
+  const int part = col0 / p.part_width, pcol = col0 % p.part_width;
+  float* outp = p.out[part];
+  float bia[32], scl[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    bia[i] = p.bias ? __ldg(p.bias + col0 + i) : 0.f;
+    scl[i] = p.scale ? __ldg(p.scale + col0 + i) : 1.f;
+  }
+
+  int t = blockIdx.x / n_slices;
+  if (t < tiles) load_tile(t);
+  mbar_wait(&s_bar_w, 0);
+  uint32_t phase = 0;
+  for (; t < tiles; t += t_step) {
+    store_tile();            // X(t): registers -> hi / lo images in shared memory
+    tc_fence_before();
+    __syncthreads();         // images complete; the previous tile's accumulator has been read by everyone
+    if (tid == 0) {
+      tc_fence_after();
+      constexpr uint32_t idesc = umma_idesc_tf32(kProjM, kProjN);
+      const uint32_t a_hi = smem_u32(sA_hi), a_lo = smem_u32(sA_lo), b_hi = smem_u32(sB_hi), b_lo = smem_u32(sB_lo);
+#pragma unroll
+      for (int ks = 0; ks < K / 8; ++ks) {
+        const uint64_t dah = umma_desc_kmajor(a_hi + ks * 2 * A_LBO, A_LBO, SBO);
+        const uint64_t dal = umma_desc_kmajor(a_lo + ks * 2 * A_LBO, A_LBO, SBO);
+        const uint64_t dbh = umma_desc_kmajor(b_hi + ks * 2 * B_LBO, B_LBO, SBO);
+        const uint64_t dbl = umma_desc_kmajor(b_lo + ks * 2 * B_LBO, B_LBO, SBO);
+        umma_tf32(tmem_d, dal, dbh, idesc, ks > 0 ? 1u : 0u);
+        umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+        umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+      }
+      umma_commit(&s_bar_mma);  // arrives when every MMA above has completed
+    }
+    const int t_next = t + t_step;
+    if (t_next < tiles) load_tile(t_next);  // global loads of the next tile fly during MMA + epilogue
+    mbar_wait(&s_bar_mma, phase);
+    phase ^= 1u;
+    tc_fence_after();
+    // ---- epilogue: accumulator row -> (y + bias) * scale -> out; GAT logits ---------------------
+    float y[32];
+    tmem_ld32(tmem_d + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(ch * 32), y);
+    const int row = t * kProjM + q4 * 32 + lane;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) y[i] = (y[i] + bia[i]) * scl[i];
+    if (row < p.n) {
+      float4* o = reinterpret_cast<float4*>(outp + (size_t)row * p.part_width + pcol);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+      if (p.head_dim > 0) {
+        // heads narrower than 32 columns lie inside this thread's 32 columns; wider heads are
+        // finished with one atomicAdd per thread (attn arrays zeroed by the launcher: at most
+        // head_dim / 32 addends per element, added in a fixed pairwise-commutative order for 2)
+        const int hd = p.head_dim, heads = p.n_out / hd;
+        if (hd <= 32) {  // hd in {8, 16, 32}: static reduction tree over the 32 columns
+          float pl[32], pr[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            pl[j] = y[j] * __ldg(p.a_l + col0 + j);
+            pr[j] = y[j] * __ldg(p.a_r + col0 + j);
+          }
+          float l8[4], r8[4];
+#pragma unroll
+          for (int k8 = 0; k8 < 4; ++k8) {
+            float a = 0.f, b = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { a += pl[8 * k8 + j]; b += pr[8 * k8 + j]; }
+            l8[k8] = a;
+            r8[k8] = b;
+          }
+          const size_t at = (size_t)row * heads + col0 / hd;
+          if (hd == 8) {
+#pragma unroll
+            for (int k8 = 0; k8 < 4; ++k8) { p.attn_row[at + k8] = l8[k8]; p.attn_col[at + k8] = r8[k8]; }
+          } else if (hd == 16) {
+            p.attn_row[at] = l8[0] + l8[1]; p.attn_row[at + 1] = l8[2] + l8[3];
+            p.attn_col[at] = r8[0] + r8[1]; p.attn_col[at + 1] = r8[2] + r8[3];
+          } else {
+            p.attn_row[at] = (l8[0] + l8[1]) + (l8[2] + l8[3]);
+            p.attn_col[at] = (r8[0] + r8[1]) + (r8[2] + r8[3]);
+          }
+        } else {
+          float ar = 0.f, ac = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            ar = fmaf(y[j], __ldg(p.a_l + col0 + j), ar);
+            ac = fmaf(y[j], __ldg(p.a_r + col0 + j), ac);
+          }
+          const int head = col0 / hd;
+          atomicAdd(p.attn_row + (size_t)row * heads + head, ar);
+          atomicAdd(p.attn_col + (size_t)row * heads + head, ac);
+        }
+      }
+    }
+  }
+  // ---- teardown ------------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem_d) : "memory");
+}
+
+// W [n_out, k] row major -> hi / lo images in the chunk-major layout of a 64-row slice
+static __global__ void proj_pack_kernel(int n_out, int k, const float* __restrict__ W, float* __restrict__ img) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // one float4 (row o, chunk c)
+  const int ch = k / 4;
+  if (i >= n_out * ch) return;
+  const int o = i / ch, c = i % ch;
+  const float4 x = __ldg(reinterpret_cast<const float4*>(W + (size_t)o * k) + c);
+  float4 hi, lo;
+  split4(x, hi, lo);
+  const int slice = o / kProjN, r = o % kProjN;
+  const size_t at = ((size_t)slice * ch + c) * kProjN + r;  // float4 index inside the hi images
+  reinterpret_cast<float4*>(img)[at] = hi;
+  reinterpret_cast<float4*>(img)[(size_t)n_out * ch + at] = lo;
+}
+
+}  // namespace dfgnn
+
+using namespace dfgnn;
+
+extern "C" {
+
+size_t dfgnn_proj_weight_image_floats(int n_out, int k) { return (size_t)2 * n_out * k; }
+
+int dfgnn_proj_pack_weights(int n_out, int k, const float* W, float* w_img, void* stream) {
+  const char* fn = "dfgnn_proj_pack_weights";
+  if (n_out < 64 || n_out % 64 != 0 || k < 8 || k % 8 != 0 || k > kProjMaxK) {
+    set_error("%s: n_out=%d must be a multiple of 64 and k=%d a multiple of 8 in [8, %d]", fn, n_out, k, kProjMaxK);
+    return DFGNN_ERR_UNSUPPORTED_DIM;
+  }
+  DFGNN_REQUIRE(W, fn); DFGNN_REQUIRE(w_img, fn);
+  const int n4 = n_out * (k / 4);
+  proj_pack_kernel<<<(n4 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n_out, k, W, w_img);
+  return check_launch(fn);
+}
+
+int dfgnn_proj_forward(int n, int k, int n_out, int part_width, const float* x, const float* w_img,
+                       const float* bias, const float* scale, float* out0, float* out1, float* out2, float* out3,
+                       int head_dim, const float* a_l, const float* a_r, float* attn_row, float* attn_col,
+                       void* stream) {
+  const char* fn = "dfgnn_proj_forward";
+  if (n < 0 || n_out < 64 || n_out % 64 != 0 || part_width < 64 || part_width % 64 != 0 || n_out % part_width != 0 ||
+      n_out / part_width > 4) {
+    set_error("%s: n_out=%d / part_width=%d must be multiples of 64 with at most 4 parts", fn, n_out, part_width);
+    return DFGNN_ERR_UNSUPPORTED_DIM;
+  }
+  if (k != 32 && k != 64 && k != 128) {
+    set_error("%s: input width k=%d is not supported (32, 64, 128)", fn, k);
+    return DFGNN_ERR_UNSUPPORTED_DIM;
+  }
+  if (n == 0) return DFGNN_OK;
+  DFGNN_REQUIRE(x, fn); DFGNN_REQUIRE(w_img, fn); DFGNN_REQUIRE(out0, fn);
+  float* outs[4] = {out0, out1, out2, out3};
+  for (int i = 0; i < n_out / part_width; ++i)
+    if (outs[i] == nullptr) { set_error("%s: output %d is NULL", fn, i); return DFGNN_ERR_INVALID_ARGUMENT; }
+  if (head_dim > 0) {
+    DFGNN_REQUIRE(a_l, fn); DFGNN_REQUIRE(a_r, fn); DFGNN_REQUIRE(attn_row, fn); DFGNN_REQUIRE(attn_col, fn);
+    if (n_out % head_dim != 0 || !(head_dim == 8 || head_dim == 16 || head_dim % 32 == 0)) {
+      set_error("%s: head_dim=%d must be 8, 16 or a multiple of 32", fn, head_dim);
+      return DFGNN_ERR_UNSUPPORTED_DIM;
+    }
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  ProjParams p{n, k, n_out, part_width, x, w_img, bias, scale, {out0, out1, out2, out3},
+               head_dim, a_l, a_r, attn_row, attn_col};
+  if (head_dim > 32) {  // wider heads are summed from several 32-column pieces
+    const size_t bytes = (size_t)n * (n_out / head_dim) * sizeof(float);
+    cudaMemsetAsync(attn_row, 0, bytes, st);
+    cudaMemsetAsync(attn_col, 0, bytes, st);
+  }
+  static const int sms = [] {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  const int n_slices = n_out / kProjN, tiles = (n + kProjM - 1) / kProjM;
+  int per_slice = sms / n_slices;               // CTAs working on the same slice
+  if (per_slice < 1) per_slice = 1;
+  if (per_slice > tiles) per_slice = tiles;
+  const int grid = per_slice * n_slices;
+  const size_t smem = (size_t)2 * kProjM * k * 4 + (size_t)2 * kProjN * k * 4;
+  auto launch = [&](auto kernel) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kernel<<<grid, kProjThreads, smem, st>>>(p);
+  };
+  if (k == 128) launch(proj_tf32x3_kernel<128>);
+  else if (k == 64) launch(proj_tf32x3_kernel<64>);
+  else launch(proj_tf32x3_kernel<32>);
+  return check_launch(fn);
+}
+
+}  // extern "C"

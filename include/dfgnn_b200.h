@@ -356,6 +356,31 @@ int dfgnn_gat_inference_hyper_v2(int smem_consume, int m, int nnz, int h, int f,
 int dfgnn_gat_attn_weight(int m, int h, int f, const float *a_l, const float *a_r,
                           const float *in_feat, float *attn_row, float *attn_col, void *stream);
 
+/* ------------------------------------------------------------------------ */
+/* The dense projection in front of the conv (tcgen05 tensor cores, 3xTF32)   */
+/* ------------------------------------------------------------------------ */
+/*
+ * Replaces the three nn.Linear GEMMs + scale + reshape of SparseMHA.prep_qkv
+ * (DFGNN/layers/GT/gtconv_layer.py:19-27; fused branch gtconv_layer_fused.py:20-22) and, for GAT,
+ * feat = W x plus the logits attn_row = <a_l, feat>, attn_col = <a_r, feat>
+ * (layers/GAT/gatconv_layer_fused.py:121-123, fused_gatconv_hyper_v2.cu:212-250) with one kernel:
+ *     Y[n, n_out] = (X[n, k] W[n_out, k]^T + bias) * scale
+ * at fp32-grade accuracy (TF32 tensor cores, x = hi + lo split, fp32 accumulation in tensor
+ * memory).  Y is written as n_out / part_width tensors [n, part_width] (out0..out3; q | k | v are
+ * three parts of width heads * d, i.e. already [N, heads, d]).  k in {32, 64, 128}; n_out and
+ * part_width multiples of 64; bias / scale [n_out] or NULL.  head_dim > 0 also writes the logits
+ * [n, n_out / head_dim] (head_dim 8, 16 or a multiple of 32; a_l, a_r [n_out]).
+ *
+ * dfgnn_proj_pack_weights splits W into the hi / lo operand images the kernel loads by TMA
+ * (w_img: dfgnn_proj_weight_image_floats(n_out, k) floats); call it once per weight update.
+ */
+size_t dfgnn_proj_weight_image_floats(int n_out, int k);
+int dfgnn_proj_pack_weights(int n_out, int k, const float *W, float *w_img, void *stream);
+int dfgnn_proj_forward(int n, int k, int n_out, int part_width, const float *x, const float *w_img,
+                       const float *bias, const float *scale, float *out0, float *out1, float *out2,
+                       float *out3, int head_dim, const float *a_l, const float *a_r,
+                       float *attn_row, float *attn_col, void *stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif
