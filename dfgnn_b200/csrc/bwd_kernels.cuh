@@ -129,14 +129,10 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_GT_WARPS_SMALL :
           float kk[C][NR], vv[C][NR], dA[C];
 #pragma unroll
           for (int c = 0; c < C; ++c) {
-            const int col = group_bcast<LPR>(my_col, s + c);
-            if (s + c < cnt) {
-              L::load(vv[c], ra.at(Vb, col), gl, f);
-              L::load(kk[c], ra.at(Kb, col), gl, f);
-            } else {
-              zero(vv[c]);
-              zero(kk[c]);
-            }
+            // beyond cnt: the chunk's first neighbour again (valid, cached; probability 0)
+            const int col = group_bcast<LPR>(my_col, s + c < cnt ? s + c : 0);
+            L::load(vv[c], ra.at(Vb, col), gl, f);
+            L::load(kk[c], ra.at(Kb, col), gl, f);
           }
 #pragma unroll
           for (int c = 0; c < C; ++c) dA[c] = group_sum<LPR>(dot<NR>(g, vv[c]));
@@ -279,14 +275,10 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_GT_WARPS_SMALL :
           float go[C][NR], qq[C][NR];
 #pragma unroll
           for (int c = 0; c < C; ++c) {
-            const int rid = group_bcast<LPR>(my_rid, s + c);
-            if (s + c < cnt) {
-              L::load(go[c], ra.at(Gb, rid), gl, f);
-              L::load(qq[c], ra.at(Qb, rid), gl, f);
-            } else {
-              zero(go[c]);
-              zero(qq[c]);
-            }
+            // beyond cnt: the chunk's first entry again (valid, cached; weights 0)
+            const int rid = group_bcast<LPR>(my_rid, s + c < cnt ? s + c : 0);
+            L::load(go[c], ra.at(Gb, rid), gl, f);
+            L::load(qq[c], ra.at(Qb, rid), gl, f);
           }
 #pragma unroll
           for (int c = 0; c < C; ++c) {

@@ -138,14 +138,11 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? DFGNN_GT_WARPS_SMALL :
 #pragma unroll
           for (int c = 0; c < C; ++c) {
             ok[c] = s + c < cnt;
-            const int col = group_bcast<LPR>(my_col, s + c);
-            if (ok[c]) {
-              if (!AGNN) L::load(kk[c], ra.at(Kb, col), gl, f);
-              L::load(vv[c], ra.at(Vb, col), gl, f);
-            } else {
-              if (!AGNN) zero(kk[c]);
-              zero(vv[c]);
-            }
+            // beyond cnt: the chunk's first neighbour again (a valid, cached row; its weight is 0) --
+            // cheaper than zeroing the registers and branching around the loads
+            const int col = group_bcast<LPR>(my_col, ok[c] ? s + c : 0);
+            if (!AGNN) L::load(kk[c], ra.at(Kb, col), gl, f);
+            L::load(vv[c], ra.at(Vb, col), gl, f);
           }
           float cm = kNeg;
 #pragma unroll

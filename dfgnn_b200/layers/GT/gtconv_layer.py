@@ -10,12 +10,17 @@ from ...operators.fused_gtconv import (GTConvFuse_hyper, GTConvFuse_inference_cs
                                        GTConvFuse_inference_softmax,
                                        GTConvFuse_inference_softmax_gm,
                                        GTConvFuse_inference_tiling)
+from ...operators import projection
 from ...utils import benchmark
 from .._dglsp import bsddmm, bspmm, edge_softmax
 
 
 class SparseMHA(nn.Module):
     """Sparse Multi-head Attention Module (layers/GT/gtconv_layer.py:6-33)."""
+
+    # fused branches: q, k, v by ONE tensor-core kernel (operators/projection.py) instead of three
+    # fp32 GEMMs + scale + transposes, for the sizes it supports; set False for the literal path
+    fused_projection = True
 
     def __init__(self, in_size, out_size, num_heads):
         super().__init__()
@@ -26,6 +31,17 @@ class SparseMHA(nn.Module):
         self.q_proj = nn.Linear(in_size, out_size)
         self.k_proj = nn.Linear(in_size, out_size)
         self.v_proj = nn.Linear(in_size, out_size)
+
+    def _fused_qkv(self, h, interleaved_heads):
+        """q, k, v as contiguous [N, heads, head_dim] from the fused projection, or None when the
+        sizes are outside what it supports (or it is switched off)."""
+        out_size = self.head_dim * self.num_heads
+        if not (self.fused_projection and h.is_cuda and h.dtype == self.q_proj.weight.dtype and
+                projection.supported(self.in_size, out_size, 3)):
+            return None
+        cache = self.__dict__.setdefault("_proj_cache", projection.PackedWeights())
+        return projection.fused_qkv(h, self.q_proj, self.k_proj, self.v_proj, self.scaling, self.num_heads,
+                                    cache, interleaved_heads)
 
     def prep_qkv(self, h):
         """gtconv_layer.py:19-27: q, k, v as [N, head_dim, heads], q pre-scaled."""
@@ -43,10 +59,14 @@ class SparseMHA(nn.Module):
 
     def _fused(self, op, h, *op_args):
         """Shared body of the fused inference branches (gtconv_layer_fused.py:18-35)."""
-        q, k, v = self.prep_qkv(h)
-        q = q.transpose(1, 2).contiguous()
-        k = k.transpose(1, 2).contiguous()
-        v = v.transpose(1, 2).contiguous()
+        qkv = self._fused_qkv(h, interleaved_heads=True)
+        if qkv is not None:
+            q, k, v = qkv
+        else:
+            q, k, v = self.prep_qkv(h)
+            q = q.transpose(1, 2).contiguous()
+            k = k.transpose(1, 2).contiguous()
+            v = v.transpose(1, 2).contiguous()
         out, elapsed_time = benchmark(op, *op_args, q, k, v)
         return out.transpose(1, 2), elapsed_time
 
@@ -144,10 +164,14 @@ class SparseMHA_forward(SparseMHA):
         N = len(h)
         A, rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx, smem_consume = params
         if fuse:
-            q = self.q_proj(h).reshape(N, self.num_heads, self.head_dim)
-            q = q * self.scaling
-            k = self.k_proj(h).reshape(N, self.num_heads, self.head_dim)
-            v = self.v_proj(h).reshape(N, self.num_heads, self.head_dim)
+            qkv = self._fused_qkv(h, interleaved_heads=False)
+            if qkv is not None:
+                q, k, v = qkv
+            else:
+                q = self.q_proj(h).reshape(N, self.num_heads, self.head_dim)
+                q = q * self.scaling
+                k = self.k_proj(h).reshape(N, self.num_heads, self.head_dim)
+                v = self.v_proj(h).reshape(N, self.num_heads, self.head_dim)
             if self.training:
                 out = GTConvFuse_hyper(rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx,
                                        smem_consume, q, k, v)

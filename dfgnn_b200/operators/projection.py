@@ -30,10 +30,19 @@ class PackedWeights:
         self.img = None
         self.bias = None
 
-    def get(self, weights: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]]):
+    def get(self, weights: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]],
+            row_perm: Optional[torch.Tensor] = None):
+        """``row_perm``: output-column permutation applied to every part (row i of the packed part is
+        row row_perm[i] of the weight) -- the reference's inference modules split the projection
+        output as [N, head_dim, heads] and transpose (gtconv_layer.py:19-27, gtconv_layer_fused.py:
+        20-22); permuting the weight rows yields [N, heads, head_dim] directly."""
         key = tuple((w.data_ptr(), w._version, tuple(w.shape)) for w in weights) + \
-            tuple((b.data_ptr(), b._version) if b is not None else None for b in biases)
+            tuple((b.data_ptr(), b._version) if b is not None else None for b in biases) + \
+            (None if row_perm is None else int(row_perm.numel()),)
         if key != self.key:
+            if row_perm is not None:
+                weights = [w[row_perm] for w in weights]
+                biases = [b[row_perm] if b is not None else None for b in biases]
             W = torch.cat([w.detach() for w in weights], 0).contiguous().float()
             n_out, k = W.shape
             L = _lib.lib()
@@ -76,8 +85,10 @@ class FusedQKVFunction(torch.autograd.Function):
     """q, k, v = ((x Wq^T + bq) * scaling, x Wk^T + bk, x Wv^T + bv), each [N, heads, d]."""
 
     @staticmethod
-    def forward(ctx, x, wq, bq, wk, bk, wv, bv, scaling: float, heads: int, cache: PackedWeights):
-        img, bias = cache.get((wq, wk, wv), (bq, bk, bv))
+    def forward(ctx, x, wq, bq, wk, bk, wv, bv, scaling: float, heads: int, cache: PackedWeights,
+                row_perm=None):
+        img, bias = cache.get((wq, wk, wv), (bq, bk, bv), row_perm)
+        ctx.row_perm = row_perm
         d_out = wq.shape[0]
         scale = torch.ones(3 * d_out, dtype=torch.float32, device=x.device)
         scale[:d_out] = scaling
@@ -93,9 +104,13 @@ class FusedQKVFunction(torch.autograd.Function):
         n = x.shape[0]
         gq = gq.reshape(n, -1) * ctx.scaling
         gk, gv = gk.reshape(n, -1), gv.reshape(n, -1)
+        if ctx.row_perm is not None:  # packed column i is weight row row_perm[i]
+            inv = torch.empty_like(ctx.row_perm)
+            inv[ctx.row_perm] = torch.arange(ctx.row_perm.numel(), device=inv.device)
+            gq, gk, gv = gq[:, inv], gk[:, inv], gv[:, inv]
         gx = gq @ wq + gk @ wk + gv @ wv if ctx.needs_input_grad[0] else None
         gb = [g.sum(0) if hb else None for g, hb in zip((gq, gk, gv), ctx.has_bias)]
-        return gx, gq.t() @ x, gb[0], gk.t() @ x, gb[1], gv.t() @ x, gb[2], None, None, None
+        return gx, gq.t() @ x, gb[0], gk.t() @ x, gb[1], gv.t() @ x, gb[2], None, None, None, None
 
 
 class FusedGATProjFunction(torch.autograd.Function):
@@ -127,7 +142,16 @@ class FusedGATProjFunction(torch.autograd.Function):
         return gx, g2.t() @ x, (g2.sum(0) if ctx.has_bias else None), gal, gar_, None, None
 
 
-def fused_qkv(x, q_proj, k_proj, v_proj, scaling: float, heads: int, cache: PackedWeights):
-    """The three ``nn.Linear`` modules of SparseMHA in one tensor-core kernel -> q, k, v [N, heads, d]."""
+def fused_qkv(x, q_proj, k_proj, v_proj, scaling: float, heads: int, cache: PackedWeights,
+              interleaved_heads: bool = False):
+    """The three ``nn.Linear`` modules of SparseMHA in one tensor-core kernel -> q, k, v [N, heads, d].
+    ``interleaved_heads``: the projection output is split as [N, d, heads] (prep_qkv) rather than
+    [N, heads, d] (the training module); same values, transposed for the conv."""
+    perm = None
+    d_out = q_proj.weight.shape[0]
+    if interleaved_heads and heads > 1:
+        hd = d_out // heads
+        o = torch.arange(d_out, device=x.device)
+        perm = (o % hd) * heads + o // hd     # packed column h * hd + d  <-  weight row d * heads + h
     return FusedQKVFunction.apply(x, q_proj.weight, q_proj.bias, k_proj.weight, k_proj.bias,
-                                  v_proj.weight, v_proj.bias, scaling, heads, cache)
+                                  v_proj.weight, v_proj.bias, scaling, heads, cache, perm)
