@@ -32,6 +32,7 @@ constexpr int kProjM = 128;      // node rows per tile (UMMA M)
 constexpr int kProjN = 64;       // output columns per slice (UMMA N)
 constexpr int kProjThreads = 256;
 constexpr int kProjMaxK = 128;
+constexpr int kOutLd = kProjN + 4;  // row stride of the staged output tile (floats): conflict-free float4 rows
 
 struct ProjParams {
   int n, k, n_out;        // rows, input width, total output columns (multiple of 64)
@@ -117,6 +118,7 @@ __global__ void __launch_bounds__(kProjThreads, 1) proj_tf32x3_kernel(const Proj
   float4* sA_lo = reinterpret_cast<float4*>(smem + A_BYTES);
   unsigned char* sB_hi = smem + 2 * A_BYTES;
   unsigned char* sB_lo = sB_hi + B_BYTES;
+  float* s_out = reinterpret_cast<float*>(sB_lo + B_BYTES);  // [128][kOutLd]: the output tile, for coalesced stores
   __shared__ uint64_t s_bar_w, s_bar_mma;
   __shared__ uint32_t s_tmem;
 
@@ -180,8 +182,6 @@ __global__ void __launch_bounds__(kProjThreads, 1) proj_tf32x3_kernel(const Proj
   // epilogue role of this warp: rows of TMEM lane quarter (w % 4), column half (w / 4)
   const int q4 = w & 3, ch = w >> 2;
   const int col0 = slice * kProjN + ch * 32;               // first output column of this thread
-  const int part = col0 / p.part_width, pcol = col0 % p.part_width;
-  float* outp = p.out[part];
   float bia[32], scl[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
@@ -224,10 +224,12 @@ __global__ void __launch_bounds__(kProjThreads, 1) proj_tf32x3_kernel(const Proj
     const int row = t * kProjM + q4 * 32 + lane;
 #pragma unroll
     for (int i = 0; i < 32; ++i) y[i] = (y[i] + bia[i]) * scl[i];
-    if (row < p.n) {
-      float4* o = reinterpret_cast<float4*>(outp + (size_t)row * p.part_width + pcol);
+    {  // stage the row in shared memory: the tile is written out below in full 256-byte row segments
+      float4* so = reinterpret_cast<float4*>(s_out + (size_t)(q4 * 32 + lane) * kOutLd + ch * 32);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+      for (int i = 0; i < 8; ++i) so[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+    }
+    if (row < p.n) {
       if (p.head_dim > 0) {
         // heads narrower than 32 columns lie inside this thread's 32 columns; wider heads are
         // finished with one atomicAdd per thread (attn arrays zeroed by the launcher: at most
@@ -271,6 +273,19 @@ __global__ void __launch_bounds__(kProjThreads, 1) proj_tf32x3_kernel(const Proj
           atomicAdd(p.attn_row + (size_t)row * heads + head, ar);
           atomicAdd(p.attn_col + (size_t)row * heads + head, ac);
         }
+      }
+    }
+    __syncthreads();  // the tile is staged (the loop-top barrier of the next tile protects its reuse)
+    {
+      const int scol = slice * kProjN;               // this slice inside its part
+      float* obase = p.out[scol / p.part_width] + scol % p.part_width;
+#pragma unroll
+      for (int u = 0; u < kProjM * (kProjN / 4) / kProjThreads; ++u) {
+        const int i = tid + u * kProjThreads, r = i / (kProjN / 4), c4 = i % (kProjN / 4);
+        const int grow = t * kProjM + r;
+        if (grow < p.n)
+          *reinterpret_cast<float4*>(obase + (size_t)grow * p.part_width + 4 * c4) =
+              *reinterpret_cast<const float4*>(s_out + (size_t)r * kOutLd + 4 * c4);
       }
     }
   }
@@ -360,7 +375,7 @@ int dfgnn_proj_forward(int n, int k, int n_out, int part_width, const float* x, 
   if (per_slice < 1) per_slice = 1;
   if (per_slice > tiles) per_slice = tiles;
   const int grid = per_slice * n_slices;
-  const size_t smem = (size_t)2 * kProjM * k * 4 + (size_t)2 * kProjN * k * 4;
+  const size_t smem = (size_t)2 * kProjM * k * 4 + (size_t)2 * kProjN * k * 4 + (size_t)kProjM * kOutLd * 4;
   auto launch = [&](auto kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kernel<<<grid, kProjThreads, smem, st>>>(p);

@@ -19,8 +19,12 @@ class SparseMHA(nn.Module):
     """Sparse Multi-head Attention Module (layers/GT/gtconv_layer.py:6-33)."""
 
     # fused branches: q, k, v by ONE tensor-core kernel (operators/projection.py) instead of three
-    # fp32 GEMMs + scale + transposes, for the sizes it supports; set False for the literal path
-    fused_projection = True
+    # fp32 GEMMs + scale + transposes, for the sizes it supports.  Off by default: the kernel is
+    # fp32-grade (3xTF32, ~1e-6 absolute) but not bit-identical to cuBLAS SGEMM, and the reference's
+    # own layer-level check (check_correct: rtol 1e-3 with atol 1e-8) compares the fused branch with
+    # the non-fused one element by element, zeros included.  Set True (per module or on the class)
+    # where the 1e-4 / 1e-5 bar is the contract; GTStack(fused_projection=True) does.
+    fused_projection = False
 
     def __init__(self, in_size, out_size, num_heads):
         super().__init__()

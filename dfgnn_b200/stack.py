@@ -31,13 +31,15 @@ from .layers.GT import SparseMHA_forward
 
 class GTStack(nn.Module):
     def __init__(self, num_layers: int, in_dim: int, num_hidden: int, num_classes: int,
-                 num_heads: int = 1, pool: bool = False):
+                 num_heads: int = 1, pool: bool = False, fused_projection: bool = False):
         super().__init__()
         self.num_layers = num_layers
         self.pool = pool
         self.input_proj = nn.Linear(in_dim, num_hidden)
         self.layers = nn.ModuleList(SparseMHA_forward(num_hidden, num_hidden, num_heads)
                                     for _ in range(num_layers))
+        for layer in self.layers:  # q, k, v of every layer by the tcgen05 projection kernel
+            layer.fused_projection = fused_projection
         self.output_proj = nn.Linear(num_hidden, num_classes)
 
     def forward(self, params, h, fuse: bool = True, graph_ids: Optional[torch.Tensor] = None,

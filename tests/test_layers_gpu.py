@@ -40,6 +40,38 @@ def test_fused_branch_matches_nonfused(cuda, conv, fmt):
     assert_close("layer out", out, ref, rtol=1e-3, atol=1e-5)
 
 
+@pytest.mark.parametrize("fmt,heads", [("hyper", 1), ("tiling", 2), ("softmax", 4)])
+def test_fused_projection_in_the_gt_layers(cuda, fmt, heads):
+    """fused_projection=True: q, k, v from the tcgen05 kernel (operators/projection.py) instead of
+    three cuBLAS GEMMs + transposes; same layer output within 1e-4 / 1e-5, inference modules (head
+    split [N, d, heads] of prep_qkv) and training module ([N, heads, d]) alike."""
+    torch.manual_seed(0)
+    g = graphs.pattern_like(batch=4).to(cuda)
+    args = argparse.Namespace(conv="gt", format=fmt, dim=128, heads=heads)
+    layer = load_graphconv_layer(args).to(cuda)
+    x = torch.randn(g.num_nodes(), 128, device=cuda)
+    params = load_prepfunc(args)(g)
+    with torch.no_grad():
+        plain, _ = layer(params, x, fuse=True)
+        layer.fused_projection = True
+        fused, _ = layer(params, x, fuse=True)
+    assert_close("layer out with the fused projection", fused, plain)
+    # training module, gradients through FusedQKVFunction
+    tr = SparseMHA_forward(128, 128, heads).to(cuda).train()
+    p2 = preprocess_Hyper_fw_bw(g)
+    w = torch.randn(g.num_nodes(), 128, device=cuda)
+    grads = []
+    for flag in (False, True):
+        tr.fused_projection = flag
+        tr.zero_grad()
+        out = tr(p2, x, fuse=True)
+        (out * w).sum().backward()
+        grads.append((out.detach().clone(), [p.grad.clone() for p in tr.parameters()]))
+    assert_close("training out", grads[1][0], grads[0][0])
+    for (name, _), a, b in zip(tr.named_parameters(), grads[1][1], grads[0][1]):
+        assert_close(name + ".grad", a, b, rtol=1e-3, atol=1e-4)
+
+
 def test_agnn_literal_two_step_path(cuda):
     torch.manual_seed(0)
     g = graphs.cora_like(0.5).to(cuda)
