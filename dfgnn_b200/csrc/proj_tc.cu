@@ -41,7 +41,8 @@ struct ProjParams {
   const float* w_img;     // [2][n_out / 64][k / 4][64][4]: hi images then lo images
   const float* bias;      // [n_out] or null
   const float* scale;     // [n_out] or null
-  float* out[4];          // one [n, part_width] tensor per part
+  float *out0, *out1, *out2, *out3;  // one [n, part_width] tensor per part (separate members: a
+                                     // dynamically indexed array would move the whole block to local memory)
   // GAT logits (optional): per head of width head_dim, attn_row = <a_l, y>, attn_col = <a_r, y>
   int head_dim;           // 0: no logits
   const float* a_l;       // [n_out]
@@ -278,7 +279,8 @@ __global__ void __launch_bounds__(kProjThreads, 1) proj_tf32x3_kernel(const Proj
     __syncthreads();  // the tile is staged (the loop-top barrier of the next tile protects its reuse)
     {
       const int scol = slice * kProjN;               // this slice inside its part
-      float* obase = p.out[scol / p.part_width] + scol % p.part_width;
+      const int part = scol / p.part_width;
+      float* obase = (part == 0 ? p.out0 : part == 1 ? p.out1 : part == 2 ? p.out2 : p.out3) + scol % p.part_width;
 #pragma unroll
       for (int u = 0; u < kProjM * (kProjN / 4) / kProjThreads; ++u) {
         const int i = tid + u * kProjThreads, r = i / (kProjN / 4), c4 = i % (kProjN / 4);
@@ -357,7 +359,7 @@ int dfgnn_proj_forward(int n, int k, int n_out, int part_width, const float* x, 
     }
   }
   cudaStream_t st = (cudaStream_t)stream;
-  ProjParams p{n, k, n_out, part_width, x, w_img, bias, scale, {out0, out1, out2, out3},
+  ProjParams p{n, k, n_out, part_width, x, w_img, bias, scale, out0, out1, out2, out3,
                head_dim, a_l, a_r, attn_row, attn_col};
   if (head_dim > 32) {  // wider heads are summed from several 32-column pieces
     const size_t bytes = (size_t)n * (n_out / head_dim) * sizeof(float);
