@@ -10,6 +10,7 @@ from ...operators.fused_gatconv import (GATConvFuse, GATConvFuse_inference,
                                         GATConvFuse_inference_softmax,
                                         GATConvFuse_inference_softmax_gm,
                                         GATConvFuse_inference_tiling)
+from ...operators import projection
 from ...utils import benchmark
 from .._dglsp import bspmm, edge_softmax
 
@@ -153,18 +154,33 @@ class GATConv_hyper_v2(GATConvDGL):
 class GATConv_forward(GATConvDGL):
     """Training module over FusedGATFunction (the layer the reference's
     script/train/train_gatconv.py:10 imports but does not ship).
-    params = preprocess_gat_fw_bw(g) = (row_ptr, col_ind, col_ptr, row_ind, permute)."""
+    params = preprocess_gat_fw_bw(g) = (row_ptr, col_ind, col_ptr, row_ind, permute).
+    ``fused_projection = True``: feat = W x and both logit vectors come from ONE tensor-core kernel
+    (operators/projection.py; the GEMM epilogue reduces <a_l, feat>, <a_r, feat> from the accumulator
+    rows) instead of a cuBLAS GEMM + two elementwise-reduce kernels."""
+
+    fused_projection = False
 
     def __init__(self, in_size, out_size, num_heads, dropout=0, negative_slope=0.2):
         super().__init__(in_size, out_size, num_heads, dropout, negative_slope)
         self.attn_drop = float(dropout)
 
+    def _project(self, feat):
+        n_out = self.out_size * self.num_heads
+        hd = self.out_size
+        if (self.fused_projection and feat.is_cuda and projection.supported(self.in_size, n_out, 1)
+                and (hd in (8, 16) or hd % 32 == 0)):
+            cache = self.__dict__.setdefault("_proj_cache", projection.PackedWeights())
+            return projection.FusedGATProjFunction.apply(
+                feat, self.W.weight, self.W.bias, self.a_l.transpose(1, 2), self.a_r.transpose(1, 2),
+                self.num_heads, cache)
+        h = self.W(feat).view(-1, self.num_heads, self.out_size).contiguous()
+        return h, (self.a_l.transpose(1, 2) * h).sum(dim=-1), (self.a_r.transpose(1, 2) * h).sum(dim=-1)
+
     def forward(self, params, feat, fuse=True):
         N = len(feat)
         row_ptr, col_ind, col_ptr, row_ind, permute = params
-        h = self.W(feat).view(-1, self.num_heads, self.out_size).contiguous()
-        attn_row = (self.a_l.transpose(1, 2) * h).sum(dim=-1)
-        attn_col = (self.a_r.transpose(1, 2) * h).sum(dim=-1)
+        h, attn_row, attn_col = self._project(feat)
         drop = self.attn_drop if self.training else 0.0
         out = GATConvFuse(attn_row.contiguous(), attn_col.contiguous(), row_ptr, col_ind, col_ptr,
                           row_ind, permute, self.negative_slope, h, drop)

@@ -72,6 +72,25 @@ def test_fused_projection_in_the_gt_layers(cuda, fmt, heads):
         assert_close(name + ".grad", a, b, rtol=1e-3, atol=1e-4)
 
 
+def test_fused_projection_in_the_gat_training_layer(cuda):
+    torch.manual_seed(2)
+    g = graphs.arxiv_like(0.02).to(cuda)
+    params = preprocess_gat_fw_bw(g)
+    layer = GATConv_forward(128, 64, 1).to(cuda).train()
+    x = torch.randn(g.num_nodes(), 128, device=cuda)
+    w = torch.randn(g.num_nodes(), 64, device=cuda)
+    res = []
+    for flag in (False, True):
+        layer.fused_projection = flag
+        layer.zero_grad()
+        out = layer(params, x)
+        (out * w).sum().backward()
+        res.append((out.detach().clone(), [p.grad.clone() for p in layer.parameters()]))
+    assert_close("gat layer out", res[1][0], res[0][0])
+    for (name, _), a, b in zip(layer.named_parameters(), res[1][1], res[0][1]):
+        assert_close(name + ".grad", a, b, rtol=1e-3, atol=1e-4)
+
+
 def test_agnn_literal_two_step_path(cuda):
     torch.manual_seed(0)
     g = graphs.cora_like(0.5).to(cuda)
