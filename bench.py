@@ -184,10 +184,6 @@ def build_graph(name: str, seed_offset: int = 0):
     return getattr(graphs, fn)(seed=SEEDS[name] + seed_offset, **kw)
 
 
-def n_nodes_hint(name: str) -> int:
-    return {"arxiv-gat": 169343, "reddit-gt": 232965, "cora-gt": 2708}.get(name, 0)
-
-
 def default_workload(gpus: int) -> str:
     return "arxiv-gat" if gpus <= 1 else "reddit-gt"
 
@@ -311,10 +307,11 @@ def measure(env, args, name: str, full: bool):
     mode = PARTITION[name] if args.scaling == "auto" else \
         ("weak" if args.scaling == "weak" else ("by-graph" if batched else "row"))
     weak = world > 1 and mode == "weak"
-    # column chunks of a row partition: enough bytes per reduce-scatter to amortise its launch
-    # latency (~48 MB of column-side gradient per chunk), at most 4
-    grad_bytes = n_nodes_hint(name) * (2 * dim if conv == "gt" else dim + 1) * 4
-    chunks = args.chunks if args.chunks > 0 else int(max(1, min(4, grad_bytes // (48 << 20))))
+    # column chunks of a row partition (reduce-scatter of chunk c behind the column-side kernel of
+    # chunk c+1).  Measured on 8 B200 for the reddit-shaped graph: 1 chunk 5.59 ms, 2 chunks 5.66 ms,
+    # 4 chunks 5.71 ms per step -- the smaller NCCL messages and the SMs NCCL takes from the
+    # column-side kernel cost more than the overlap hides -- so the default is 1.
+    chunks = args.chunks if args.chunks > 0 else 1
     if world == 1 or weak:
         g_full = build_graph(name, seed_offset=1000 * rank if weak else 0)
         part = ddist.make_partition(g_full, 1, 0)
@@ -824,7 +821,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
     ap.add_argument("--profile", action="store_true", help="short eager conv-only run for ncu (tools/profile_r02.sh)")
     ap.add_argument("--profile-ref", action="store_true", help="with --profile: also launch the reference kernels")
-    ap.add_argument("--chunks", type=int, default=0, help="column chunks of a row partition (default 4)")
+    ap.add_argument("--chunks", type=int, default=0, help="column chunks of a row partition (default 1)")
     ap.add_argument("--scaling", default="auto", choices=["auto", "weak", "strong"],
                     help="auto: every workload in its north-star partition (module docstring); weak: own graph / "
                          "batch per GPU; strong: one global graph / batch split over the ranks")

@@ -32,6 +32,7 @@ differentiable too (its backward is the reduce-scatter).
 """
 from __future__ import annotations
 
+import math
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
@@ -149,7 +150,9 @@ class HaloExchange:
     ``record=True`` brackets every collective with CUDA events on the stream it runs on;
     ``pop_times()`` returns the accumulated {"allgather_ms", "reduce_scatter_ms"}."""
 
-    def __init__(self, part: Partition, device, world: int, record: bool = False):
+    def __init__(self, part: Partition, device, world: int, record: bool = False, backend: str = "auto"):
+        import os
+
         import torch.distributed as dist
         self.part = part
         self.active = part.kind == "row" and world > 1
@@ -159,6 +162,83 @@ class HaloExchange:
         self._events = {"allgather_ms": [], "reduce_scatter_ms": []}
         self._nccl = self.active and dist.get_backend() == "nccl"
         self._comm = torch.cuda.Stream(self.device) if (self.active and self.device.type == "cuda") else None
+        # "p2p": pull-based exchange over NVLink peer memory (torch symmetric memory: every rank maps
+        # the others' buffers; the copies run on the copy engines, no SM is taken from the kernels
+        # and no NCCL launch latency is paid); "nccl": the coalesced NCCL collectives.  "auto" = p2p
+        # where symmetric memory can be set up, else nccl.  DFGNN_B200_HALO overrides.
+        backend = os.environ.get("DFGNN_B200_HALO", backend)
+        self.backend = "nccl"
+        self.backend_note = None
+        self._sym = {}
+        if self._nccl and backend in ("auto", "p2p") and part.chunks == 1:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                self._symm_mem = symm_mem
+                probe = symm_mem.empty((1024,), dtype=torch.float32, device=self.device)
+                symm_mem.rendezvous(probe, dist.group.WORLD.group_name).barrier()
+                self.backend = "p2p"
+            except Exception as exc:  # no peer mapping on this system: NCCL
+                self.backend_note = "symmetric memory unavailable (%s)" % repr(exc)[:120]
+                if backend == "p2p":
+                    raise
+
+    # -- peer-memory exchange (backend "p2p") -----------------------------------------------------
+    def _sym_buf(self, key, shape, dtype):
+        """A persistent symmetric buffer (same shape on every rank) and its rendezvous handle."""
+        import torch.distributed as dist
+        ent = self._sym.get(key)
+        if ent is None or ent[0].shape != torch.Size(shape) or ent[0].dtype != dtype:
+            t = self._symm_mem.empty(tuple(shape), dtype=dtype, device=self.device)
+            ent = (t, self._symm_mem.rendezvous(t, dist.group.WORLD.group_name))
+            self._sym[key] = ent
+        return ent
+
+    def _p2p_all_gather(self, xs):
+        mr, W, r = self.part.max_rows, self.world, self.part.rank
+        outs = []
+        hdls = []
+        for i, x in enumerate(xs):  # own slice -> symmetric memory (one local copy)
+            buf, hdl = self._sym_buf(("ag", i), x.shape, x.dtype)
+            buf.copy_(x)
+            hdls.append((buf, hdl))
+            outs.append(x.new_empty((W * mr,) + tuple(x.shape[1:])))
+        hdls[0][1].barrier()  # every rank's slices are in place
+        for step in range(W):  # pull, starting with the own slice, every rank from a different peer
+            peer = (r - step) % W
+            for (buf, hdl), x, o in zip(hdls, xs, outs):
+                src = buf if peer == r else hdl.get_buffer(peer, x.shape, x.dtype)
+                o[peer * mr:(peer + 1) * mr].copy_(src)
+        hdls[0][1].barrier()  # nobody overwrites a slice that is still being read
+        return outs
+
+    def p2p_grad_buffers(self, likes):
+        """Persistent symmetric buffers for the column-side partial gradients ([world*max_rows, ...]
+        each): the column-side kernels write them in place and the peers pull their blocks."""
+        return [self._sym_buf(("rs", i), (self.world * self.part.max_rows,) + tuple(t.shape[1:]), t.dtype)[0]
+                for i, t in enumerate(likes)]
+
+    def _p2p_reduce_scatter(self, gs):
+        mr, W, r = self.part.max_rows, self.world, self.part.rank
+        ents = []
+        for i, g in enumerate(gs):
+            buf, hdl = self._sym_buf(("rs", i), g.shape, g.dtype)
+            if g.data_ptr() != buf.data_ptr():
+                buf.copy_(g)  # a caller that did not write into p2p_grad_buffers(): one local copy
+            ents.append((buf, hdl))
+        ents[0][1].barrier()
+        outs = []
+        stage = [g.new_empty((W, mr) + tuple(g.shape[1:])) for g in gs]
+        for step in range(W):
+            peer = (r - step) % W
+            for (buf, hdl), g, st in zip(ents, gs, stage):
+                blk = (mr,) + tuple(g.shape[1:])
+                n_blk = mr * math.prod(g.shape[1:])
+                src = buf[r * mr:(r + 1) * mr] if peer == r else hdl.get_buffer(peer, blk, g.dtype, n_blk * r)
+                st[peer].copy_(src)
+        ents[0][1].barrier()
+        for st in stage:
+            outs.append(st.sum(dim=0))
+        return outs
 
     # -- helpers ---------------------------------------------------------------------------
     def chunk_nnz(self, col_ptr: torch.Tensor, c: int) -> int:
@@ -210,6 +290,12 @@ class HaloExchange:
             return list(xs)
         C, q, W = self.part.chunks, self.part.q, self.world
         xs = [self.pad(x.detach()).contiguous() for x in xs]
+        if self.backend == "p2p":
+            pair = self._ev("allgather_ms")
+            outs = self._p2p_all_gather(xs)
+            if pair:
+                pair[1].record()
+            return outs
         outs = [x.new_empty((C, W * q) + tuple(x.shape[1:])) for x in xs]
         pair = self._ev("allgather_ms")
         if self._nccl:
@@ -252,6 +338,12 @@ class HaloExchange:
             return list(gs)
         mr = self.part.max_rows
         gs = [g.contiguous() for g in gs]
+        if self.backend == "p2p":
+            pair = self._ev("reduce_scatter_ms")
+            outs = self._p2p_reduce_scatter(gs)
+            if pair:
+                pair[1].record()
+            return [o[: self.part.n_rows] for o in outs]
         outs = [g.new_empty((mr,) + tuple(g.shape[1:])) for g in gs]
         for c in range(self.part.chunks):
             self.reduce_scatter_chunk(c, gs, outs)
@@ -364,10 +456,17 @@ def dist_gt_backward(halo, saved, smem_consume, grad_out, own_rows=None):
     args = (row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem_consume, Q, K, V, attn,
             grad_out)
     bufs = N.gt_backward(*args, _phases=1)
-    gq, gk, gv, _ = bufs
+    gq, gk, gv, ge = bufs
     if not halo.active:
         N.gt_backward(*args, _phases=2, _buffers=bufs)
         return gq, gk, gv
+    if halo.backend == "p2p":  # the column side writes straight into peer-visible memory
+        gk, gv = halo.p2p_grad_buffers([gk, gv])
+        N.gt_backward(*args, _phases=2, _buffers=(gq, gk, gv, ge))
+        gk_own, gv_own = halo.reduce_scatter([gk, gv])
+        if own_rows is not None:
+            gk_own, gv_own = _fit_grad(gk_own, own_rows[0]), _fit_grad(gv_own, own_rows[1])
+        return gq, gk_own, gv_own
     halo.begin_overlapped_reduce([gk, gv])
     for c, (c0, nc) in enumerate(_col_chunks(halo)):
         N.gt_backward(*args, _phases=2, _buffers=bufs, _cols=(c0, nc, halo.chunk_nnz(col_ptr, c)))
@@ -394,10 +493,17 @@ def dist_gat_backward(halo, saved, negative_slope, attn_drop, grad_out, own_rows
     args = (negative_slope, attn_drop, row_ptr, col_ind, col_ptr, row_ind, permute, emax, esum,
             emask, feat, attn_row, ac, grad_out)
     bufs = N.gat_backward(*args, _phases=1)
-    gf, gr, gc, _ = bufs
+    gf, gr, gc, ge = bufs
     if not halo.active:
         N.gat_backward(*args, _phases=2, _buffers=bufs)
         return gr, gc, gf
+    if halo.backend == "p2p":
+        gf, gc = halo.p2p_grad_buffers([gf, gc])
+        N.gat_backward(*args, _phases=2, _buffers=(gf, gr, gc, ge))
+        gf_own, gc_own = halo.reduce_scatter([gf, gc])
+        if own_rows is not None:
+            gf_own, gc_own = _fit_grad(gf_own, own_rows[0]), _fit_grad(gc_own, own_rows[1])
+        return gr, gc_own, gf_own
     halo.begin_overlapped_reduce([gf, gc])
     for c, (c0, nc) in enumerate(_col_chunks(halo)):
         N.gat_backward(*args, _phases=2, _buffers=bufs, _cols=(c0, nc, halo.chunk_nnz(col_ptr, c)))
