@@ -658,12 +658,14 @@ def measure(env, args, name: str, full: bool):
                                   "frac_dram": (tr_step / (ms * 1e-3) / 1e9 / peak) if tr_step else None}},
             "format_construction_ms": fmt_ms,
             "clocks": clock_info,
-            "collectives": ({"allgather_ms": ag_t, "reduce_scatter_ms": rs_t,
+            "collectives": ({"backend": halo.backend + (" (%s)" % halo.backend_note if halo.backend_note else ""),
+                             "allgather_ms": ag_t, "reduce_scatter_ms": rs_t,
                              "share_of_step": (ag_t + rs_t) / ms,
                              "exposed_ms": max(0.0, ms - (k_fwd + k_row + k_col)),
-                             "note": "durations on their own streams; the reduce-scatter of column chunk c "
-                                     "runs behind the column-side kernel of chunk c+1; exposed_ms = step - "
-                                     "sum of the three kernels timed alone",
+                             "note": "backend p2p = pull-based exchange over NVLink peer memory (symmetric memory, "
+                                     "copy engines), nccl = coalesced NCCL all-gather / reduce-scatter; durations "
+                                     "bracketed by CUDA events in an eager pass; exposed_ms = step - sum of the three "
+                                     "kernels timed alone",
                              "bytes_in_per_rank": (world - 1) * part.max_rows * (2 * dim if conv == "gt" else dim + 1) * 4}
                             if halo.active else None),
         }
