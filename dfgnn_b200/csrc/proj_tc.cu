@@ -12,27 +12,25 @@
 // 3xTF32 split (x = hi + lo; x w ~ hi*hi + hi*lo + lo*hi, fp32 accumulation in tensor memory), and
 // the GAT logits reduced in the epilogue from the accumulator rows.
 //
-//   tcgen05.mma.cta_group::1.kind::tf32, M = 128 (a tile of node rows), N = 64 (a slice of the
+//   tcgen05.mma.cta_group::1.kind::tf32, M = 128 (a tile of node rows), N = 32 (a slice of the
 //   output columns), K = 8 per instruction; operands in shared memory in the canonical K-major
 //   no-swizzle layout ("chunk major": 16-byte k-chunk c of row r at c * rows * 16 + r * 16, so
 //   SBO = 128 B between 8-row groups and LBO = rows * 16 B between the two chunks of one MMA);
-//   accumulator 128 lanes x 64 columns of tensor memory, read back with tcgen05.ld.32x32b.x32.
+//   accumulators: two stages of 128 lanes x 32 columns of tensor memory, read back with
+//   tcgen05.ld.32x32b.x32.
 //
-// A persistent CTA owns one 64-column slice of W for its lifetime -- the pre-split hi / lo images
-// of the slice (prepared once per weight update, dfgnn_proj_pack_weights) arrive by two TMA bulk
-// copies -- and walks over node tiles: all threads load the X tile (coalesced float4), split it
-// into hi / lo in registers and store both images to shared memory; one thread issues the
-// 3 * K/8 MMAs and commits to an mbarrier; the epilogue (bias, scale, logits) of tile t overlaps
-// the global loads of tile t+1.
+// A persistent CTA walks over node tiles.  Per tile the X images are built ONCE (producer warps:
+// coalesced float4 loads prefetched a tile ahead, hi / lo split in registers, stores into the
+// canonical layout) and the pre-split W slice images (prepared once per weight update,
+// dfgnn_proj_pack_weights) stream through a two-stage ring by TMA bulk copies; one thread issues
+// 3 * K/8 MMAs per slice; the epilogue warps drain accumulator stage s while the MMAs of slice s+1
+// run.  Roles synchronise through mbarriers only (see the kernel).
 #include "abi_common.h"
 
 namespace dfgnn {
 
 constexpr int kProjM = 128;      // node rows per tile (UMMA M)
-constexpr int kProjN = 64;       // output columns per slice (UMMA N)
-constexpr int kProjThreads = 256;
 constexpr int kProjMaxK = 128;
-constexpr int kOutLd = kProjN + 4;  // row stride of the staged output tile (floats): conflict-free float4 rows
 
 struct ProjParams {
   int n, k, n_out;        // rows, input width, total output columns (multiple of 64)
@@ -107,35 +105,59 @@ __device__ __forceinline__ void split4(const float4 x, float4& hi, float4& lo) {
   lo = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
 }
 
+// Warp-specialised, persistent: CTA = one SM, walks node tiles; per tile the X images are built once
+// and the W slice images (32 output columns each, hi + lo) stream through a 2-stage ring.
+//   warps 0-3   epilogue: TMEM lane quarter w, tcgen05.ld 32 columns, bias / scale / logits, the
+//               128 x 32 tile through shared memory, 128-byte row segments to global
+//   warp  4     MMA issue (one lane): 3 * K/8 tcgen05.mma per slice into accumulator stage it % 2
+//   warp  5     TMA producer (one lane): W slice images -> ring, mbarrier complete_tx
+//   warps 6-13  X producers: global float4 -> registers (prefetched one tile ahead) -> hi / lo split
+//               -> canonical shared-memory images
+// mbarriers: a_full / a_empty (X images), b_full / b_empty [2] (W ring), t_full / t_empty [2]
+// (accumulator stages); tcgen05.commit arrives on the "empty" / "full" barriers when the MMAs that
+// read the operands / wrote the accumulator have completed.
+constexpr int kEpiWarps = 4, kProdWarps = 8;
+constexpr int kProjThreads2 = (kEpiWarps + 2 + kProdWarps) * 32;  // 448
+constexpr int kSliceN = 32;                                        // output columns per W slice (UMMA N)
+constexpr int kStageLd = kSliceN + 4;                              // staged output tile row stride (floats)
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
+
 template <int K>
-__global__ void __launch_bounds__(kProjThreads, 1) proj_tf32x3_kernel(const ProjParams p) {
-  constexpr int CH = K / 4;                         // 16-byte k-chunks per row
-  constexpr int XV = kProjM * CH / kProjThreads;    // float4 of the X tile per thread
-  constexpr uint32_t A_LBO = kProjM * 16, B_LBO = kProjN * 16, SBO = 128;
-  constexpr uint32_t A_BYTES = kProjM * K * 4, B_BYTES = kProjN * K * 4;
-  static_assert(K % 8 == 0 && K <= kProjMaxK && (kProjM * CH) % kProjThreads == 0, "tile shape");
+__global__ void __launch_bounds__(kProjThreads2, 1) proj_tf32x3_kernel(const ProjParams p) {
+  constexpr int CH = K / 4;                                   // 16-byte k-chunks per row
+  constexpr int PT = kProdWarps * 32;                         // X producer threads
+  constexpr int XV = kProjM * CH / PT;                        // float4 of the X tile per producer thread
+  constexpr uint32_t A_LBO = kProjM * 16, B_LBO = kSliceN * 16, SBO = 128;
+  constexpr uint32_t A_BYTES = kProjM * K * 4, B_BYTES = kSliceN * K * 4;  // one image
+  static_assert(K % 8 == 0 && K <= kProjMaxK && (kProjM * CH) % PT == 0, "tile shape");
   extern __shared__ __align__(128) unsigned char smem[];
   float4* sA_hi = reinterpret_cast<float4*>(smem);
   float4* sA_lo = reinterpret_cast<float4*>(smem + A_BYTES);
-  unsigned char* sB_hi = smem + 2 * A_BYTES;
-  unsigned char* sB_lo = sB_hi + B_BYTES;
-  float* s_out = reinterpret_cast<float*>(sB_lo + B_BYTES);  // [128][kOutLd]: the output tile, for coalesced stores
-  __shared__ uint64_t s_bar_w, s_bar_mma;
+  unsigned char* sB = smem + 2 * A_BYTES;                     // [2 stages][hi | lo] images
+  float* s_out = reinterpret_cast<float*>(sB + 4 * B_BYTES);  // [128][kStageLd]
+  __shared__ uint64_t a_full, a_empty, b_full[2], b_empty[2], t_full[2], t_empty[2];
   __shared__ uint32_t s_tmem;
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int n_slices = p.n_out / kProjN;
-  const int slice = blockIdx.x % n_slices;
+  const int n_slices = p.n_out / kSliceN;
   const int tiles = (p.n + kProjM - 1) / kProjM;
-  const int t_step = gridDim.x / n_slices;
 
-  // ---- one-time setup: barriers, tensor memory, the W slice images --------------------------
   if (tid == 0) {
-    mbar_init(&s_bar_w, 1);
-    mbar_init(&s_bar_mma, 1);
+    mbar_init(&a_full, PT);
+    mbar_init(&a_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+      mbar_init(&t_full[i], 1);
+      mbar_init(&t_empty[i], kEpiWarps * 32);
+    }
     mbar_fence_init();
   }
-  if (w == 0) {  // 64 columns of tensor memory for the 128 x 64 fp32 accumulator
+  if (w == 0) {  // 64 columns of tensor memory: two 128 x 32 fp32 accumulator stages
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(&s_tmem)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -143,100 +165,33 @@ __global__ void __launch_bounds__(kProjThreads, 1) proj_tf32x3_kernel(const Proj
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = s_tmem;
-  if (tid == 0) {
-    const size_t img = (size_t)kProjN * K;  // floats of one slice image
-    mbar_expect_tx(&s_bar_w, 2 * B_BYTES);
-    bulk_g2s_range(sB_hi, p.w_img + (size_t)slice * img, B_BYTES, &s_bar_w);
-    bulk_g2s_range(sB_lo, p.w_img + ((size_t)n_slices + slice) * img, B_BYTES, &s_bar_w);
-  }
 
-  // this thread's pieces of an X tile: float4 i = tid + u * threads covers row (i % 8) + 8 * (i / (8 * CH))
-  // and chunk (i / 8) % CH: a warp reads 8 rows x 64 contiguous bytes and writes 512 contiguous bytes
-  auto piece = [&](int u, int& r, int& c) {
-    const int i = tid + u * kProjThreads;
-    r = (i & 7) + 8 * (i / (8 * CH));
-    c = (i >> 3) % CH;
-  };
-  float4 xv[XV];
-  auto load_tile = [&](int t) {
+  if (w < kEpiWarps) {
+    // ================================ epilogue ================================================
+    const int erow = w * 32 + lane;  // row of the tile = TMEM lane
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+      const int row = t * kProjM + erow;
+      for (int sl = 0; sl < n_slices; ++sl, ++it) {
+        const uint32_t st = it & 1u, ph = (it >> 1) & 1u;
+        mbar_wait(&t_full[st], ph);
+        tc_fence_after();
+        float y[32];
+        tmem_ld32(tmem_d + ((uint32_t)(w * 32) << 16) + st * kSliceN, y);
+        tc_fence_before();
+        mbar_arrive(&t_empty[st]);  // the accumulator stage may be overwritten
+        const int col0 = sl * kSliceN;
 #pragma unroll
-    for (int u = 0; u < XV; ++u) {
-      int r, c;
-      piece(u, r, c);
-      const int row = t * kProjM + r;
-      xv[u] = row < p.n ? __ldg(reinterpret_cast<const float4*>(p.x + (size_t)row * K) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  };
-  auto store_tile = [&]() {
+        for (int i = 0; i < 32; ++i) {
+          const float b = p.bias ? __ldg(p.bias + col0 + i) : 0.f;
+          const float sc = p.scale ? __ldg(p.scale + col0 + i) : 1.f;
+          y[i] = (y[i] + b) * sc;
+        }
+        float4* so = reinterpret_cast<float4*>(s_out + (size_t)erow * kStageLd);
 #pragma unroll
-    for (int u = 0; u < XV; ++u) {
-      int r, c;
-      piece(u, r, c);
-      float4 hi, lo;
-      split4(xv[u], hi, lo);
-      sA_hi[c * kProjM + r] = hi;
-      sA_lo[c * kProjM + r] = lo;
-    }
-    fence_proxy_async();
-  };
-
-  // epilogue role of this warp: rows of TMEM lane quarter (w % 4), column half (w / 4)
-  const int q4 = w & 3, ch = w >> 2;
-  const int col0 = slice * kProjN + ch * 32;               // first output column of this thread
-  float bia[32], scl[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    bia[i] = p.bias ? __ldg(p.bias + col0 + i) : 0.f;
-    scl[i] = p.scale ? __ldg(p.scale + col0 + i) : 1.f;
-  }
-
-  int t = blockIdx.x / n_slices;
-  if (t < tiles) load_tile(t);
-  mbar_wait(&s_bar_w, 0);
-  uint32_t phase = 0;
-  for (; t < tiles; t += t_step) {
-    store_tile();            // X(t): registers -> hi / lo images in shared memory
-    tc_fence_before();
-    __syncthreads();         // images complete; the previous tile's accumulator has been read by everyone
-    if (tid == 0) {
-      tc_fence_after();
-      constexpr uint32_t idesc = umma_idesc_tf32(kProjM, kProjN);
-      const uint32_t a_hi = smem_u32(sA_hi), a_lo = smem_u32(sA_lo), b_hi = smem_u32(sB_hi), b_lo = smem_u32(sB_lo);
-#pragma unroll
-      for (int ks = 0; ks < K / 8; ++ks) {
-        const uint64_t dah = umma_desc_kmajor(a_hi + ks * 2 * A_LBO, A_LBO, SBO);
-        const uint64_t dal = umma_desc_kmajor(a_lo + ks * 2 * A_LBO, A_LBO, SBO);
-        const uint64_t dbh = umma_desc_kmajor(b_hi + ks * 2 * B_LBO, B_LBO, SBO);
-        const uint64_t dbl = umma_desc_kmajor(b_lo + ks * 2 * B_LBO, B_LBO, SBO);
-        umma_tf32(tmem_d, dal, dbh, idesc, ks > 0 ? 1u : 0u);
-        umma_tf32(tmem_d, dah, dbl, idesc, 1u);
-        umma_tf32(tmem_d, dah, dbh, idesc, 1u);
-      }
-      umma_commit(&s_bar_mma);  // arrives when every MMA above has completed
-    }
-    const int t_next = t + t_step;
-    if (t_next < tiles) load_tile(t_next);  // global loads of the next tile fly during MMA + epilogue
-    mbar_wait(&s_bar_mma, phase);
-    phase ^= 1u;
-    tc_fence_after();
-    // ---- epilogue: accumulator row -> (y + bias) * scale -> out; GAT logits ---------------------
-    float y[32];
-    tmem_ld32(tmem_d + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(ch * 32), y);
-    const int row = t * kProjM + q4 * 32 + lane;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) y[i] = (y[i] + bia[i]) * scl[i];
-    {  // stage the row in shared memory: the tile is written out below in full 256-byte row segments
-      float4* so = reinterpret_cast<float4*>(s_out + (size_t)(q4 * 32 + lane) * kOutLd + ch * 32);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) so[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
-    }
-    if (row < p.n) {
-      if (p.head_dim > 0) {
-        // heads narrower than 32 columns lie inside this thread's 32 columns; wider heads are
-        // finished with one atomicAdd per thread (attn arrays zeroed by the launcher: at most
-        // head_dim / 32 addends per element, added in a fixed pairwise-commutative order for 2)
-        const int hd = p.head_dim, heads = p.n_out / hd;
-        if (hd <= 32) {  // hd in {8, 16, 32}: static reduction tree over the 32 columns
+        for (int i = 0; i < 8; ++i) so[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+        if (p.head_dim > 0 && row < p.n) {
+          const int hd = p.head_dim, heads = p.n_out / hd;
           float pl[32], pr[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -259,36 +214,113 @@ __global__ void __launch_bounds__(kProjThreads, 1) proj_tf32x3_kernel(const Proj
           } else if (hd == 16) {
             p.attn_row[at] = l8[0] + l8[1]; p.attn_row[at + 1] = l8[2] + l8[3];
             p.attn_col[at] = r8[0] + r8[1]; p.attn_col[at + 1] = r8[2] + r8[3];
-          } else {
+          } else if (hd == 32) {
             p.attn_row[at] = (l8[0] + l8[1]) + (l8[2] + l8[3]);
             p.attn_col[at] = (r8[0] + r8[1]) + (r8[2] + r8[3]);
+          } else {  // heads wider than a slice: one atomicAdd per 32-column piece (arrays zeroed by the launcher)
+            atomicAdd(p.attn_row + at, (l8[0] + l8[1]) + (l8[2] + l8[3]));
+            atomicAdd(p.attn_col + at, (r8[0] + r8[1]) + (r8[2] + r8[3]));
           }
-        } else {
-          float ar = 0.f, ac = 0.f;
+        }
+        epi_bar_sync();  // the 128 x 32 tile is staged
+        {
+          const int part = col0 / p.part_width;
+          float* obase = (part == 0 ? p.out0 : part == 1 ? p.out1 : part == 2 ? p.out2 : p.out3) + col0 % p.part_width;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            ar = fmaf(y[j], __ldg(p.a_l + col0 + j), ar);
-            ac = fmaf(y[j], __ldg(p.a_r + col0 + j), ac);
+          for (int u = 0; u < kProjM * (kSliceN / 4) / (kEpiWarps * 32); ++u) {
+            const int i = tid + u * kEpiWarps * 32, r = i / (kSliceN / 4), c4 = i % (kSliceN / 4);
+            const int grow = t * kProjM + r;
+            if (grow < p.n)
+              *reinterpret_cast<float4*>(obase + (size_t)grow * p.part_width + 4 * c4) =
+                  *reinterpret_cast<const float4*>(s_out + (size_t)r * kStageLd + 4 * c4);
           }
-          const int head = col0 / hd;
-          atomicAdd(p.attn_row + (size_t)row * heads + head, ar);
-          atomicAdd(p.attn_col + (size_t)row * heads + head, ac);
+        }
+        epi_bar_sync();  // staged tile consumed before the next slice overwrites it
+      }
+    }
+  } else if (w == kEpiWarps) {
+    // ================================ MMA issue ================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(kProjM, kSliceN);
+      const uint32_t a_hi = smem_u32(sA_hi), a_lo = smem_u32(sA_lo), b0 = smem_u32(sB);
+      uint32_t it = 0, tt = 0;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++tt) {
+        mbar_wait(&a_full, tt & 1u);
+        for (int sl = 0; sl < n_slices; ++sl, ++it) {
+          const uint32_t st = it & 1u, ph = (it >> 1) & 1u;
+          mbar_wait(&b_full[st], ph);
+          mbar_wait(&t_empty[st], ph ^ 1u);
+          tc_fence_after();
+          const uint32_t b_hi = b0 + st * 2 * B_BYTES, b_lo = b_hi + B_BYTES, d = tmem_d + st * kSliceN;
+#pragma unroll
+          for (int ks = 0; ks < K / 8; ++ks) {
+            const uint64_t dah = umma_desc_kmajor(a_hi + ks * 2 * A_LBO, A_LBO, SBO);
+            const uint64_t dal = umma_desc_kmajor(a_lo + ks * 2 * A_LBO, A_LBO, SBO);
+            const uint64_t dbh = umma_desc_kmajor(b_hi + ks * 2 * B_LBO, B_LBO, SBO);
+            const uint64_t dbl = umma_desc_kmajor(b_lo + ks * 2 * B_LBO, B_LBO, SBO);
+            umma_tf32(d, dal, dbh, idesc, ks > 0 ? 1u : 0u);
+            umma_tf32(d, dah, dbl, idesc, 1u);
+            umma_tf32(d, dah, dbh, idesc, 1u);
+          }
+          umma_commit(&b_empty[st]);              // the W stage may be refilled ...
+          umma_commit(&t_full[st]);               // ... and the accumulator stage is complete
+          if (sl == n_slices - 1) umma_commit(&a_empty);  // the X images may be replaced
         }
       }
     }
-    __syncthreads();  // the tile is staged (the loop-top barrier of the next tile protects its reuse)
-    {
-      const int scol = slice * kProjN;               // this slice inside its part
-      const int part = scol / p.part_width;
-      float* obase = (part == 0 ? p.out0 : part == 1 ? p.out1 : part == 2 ? p.out2 : p.out3) + scol % p.part_width;
-#pragma unroll
-      for (int u = 0; u < kProjM * (kProjN / 4) / kProjThreads; ++u) {
-        const int i = tid + u * kProjThreads, r = i / (kProjN / 4), c4 = i % (kProjN / 4);
-        const int grow = t * kProjM + r;
-        if (grow < p.n)
-          *reinterpret_cast<float4*>(obase + (size_t)grow * p.part_width + 4 * c4) =
-              *reinterpret_cast<const float4*>(s_out + (size_t)r * kOutLd + 4 * c4);
+  } else if (w == kEpiWarps + 1) {
+    // ================================ TMA producer =============================================
+    if (lane == 0) {
+      const size_t img = (size_t)kSliceN * K;  // floats of one slice image
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+        for (int sl = 0; sl < n_slices; ++sl, ++it) {
+          const uint32_t st = it & 1u, ph = (it >> 1) & 1u;
+          mbar_wait(&b_empty[st], ph ^ 1u);
+          mbar_expect_tx(&b_full[st], 2 * B_BYTES);
+          unsigned char* dst = sB + st * 2 * B_BYTES;
+          bulk_g2s_range(dst, p.w_img + (size_t)sl * img, B_BYTES, &b_full[st]);
+          bulk_g2s_range(dst + B_BYTES, p.w_img + ((size_t)n_slices + sl) * img, B_BYTES, &b_full[st]);
+        }
       }
+    }
+  } else {
+    // ================================ X producers ==============================================
+    const int ptid = tid - (kEpiWarps + 2) * 32;
+    // float4 i = ptid + u * PT covers row (i % 8) + 8 * (i / (8 * CH)), chunk (i / 8) % CH: a warp reads
+    // 8 rows x 64 contiguous bytes and writes 512 contiguous bytes of the chunk-major image
+    auto piece = [&](int u, int& r, int& c) {
+      const int i = ptid + u * PT;
+      r = (i & 7) + 8 * (i / (8 * CH));
+      c = (i >> 3) % CH;
+    };
+    float4 xv[XV];
+    auto load_tile = [&](int t) {
+#pragma unroll
+      for (int u = 0; u < XV; ++u) {
+        int r, c;
+        piece(u, r, c);
+        const int row = t * kProjM + r;
+        xv[u] = row < p.n ? __ldg(reinterpret_cast<const float4*>(p.x + (size_t)row * K) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    uint32_t tt = 0;
+    int t = blockIdx.x;
+    if (t < tiles) load_tile(t);
+    for (; t < tiles; t += gridDim.x, ++tt) {
+      mbar_wait(&a_empty, (tt & 1u) ^ 1u);  // the MMAs of the previous tile have read the images
+#pragma unroll
+      for (int u = 0; u < XV; ++u) {
+        int r, c;
+        piece(u, r, c);
+        float4 hi, lo;
+        split4(xv[u], hi, lo);
+        sA_hi[c * kProjM + r] = hi;
+        sA_lo[c * kProjM + r] = lo;
+      }
+      fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's operand reads
+      mbar_arrive(&a_full);
+      if (t + (int)gridDim.x < tiles) load_tile(t + gridDim.x);  // in flight during this tile's MMAs
     }
   }
   // ---- teardown ------------------------------------------------------------------------------------
@@ -306,8 +338,8 @@ static __global__ void proj_pack_kernel(int n_out, int k, const float* __restric
   const float4 x = __ldg(reinterpret_cast<const float4*>(W + (size_t)o * k) + c);
   float4 hi, lo;
   split4(x, hi, lo);
-  const int slice = o / kProjN, r = o % kProjN;
-  const size_t at = ((size_t)slice * ch + c) * kProjN + r;  // float4 index inside the hi images
+  const int slice = o / kSliceN, r = o % kSliceN;
+  const size_t at = ((size_t)slice * ch + c) * kSliceN + r;  // float4 index inside the hi images
   reinterpret_cast<float4*>(img)[at] = hi;
   reinterpret_cast<float4*>(img)[(size_t)n_out * ch + at] = lo;
 }
@@ -372,15 +404,12 @@ int dfgnn_proj_forward(int n, int k, int n_out, int part_width, const float* x, 
     cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
     return v > 0 ? v : 148;
   }();
-  const int n_slices = n_out / kProjN, tiles = (n + kProjM - 1) / kProjM;
-  int per_slice = sms / n_slices;               // CTAs working on the same slice
-  if (per_slice < 1) per_slice = 1;
-  if (per_slice > tiles) per_slice = tiles;
-  const int grid = per_slice * n_slices;
-  const size_t smem = (size_t)2 * kProjM * k * 4 + (size_t)2 * kProjN * k * 4 + (size_t)kProjM * kOutLd * 4;
+  const int tiles = (n + kProjM - 1) / kProjM;
+  const int grid = tiles < sms ? tiles : sms;
+  const size_t smem = (size_t)2 * kProjM * k * 4 + (size_t)4 * kSliceN * k * 4 + (size_t)kProjM * kStageLd * 4;
   auto launch = [&](auto kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kernel<<<grid, kProjThreads, smem, st>>>(p);
+    kernel<<<grid, kProjThreads2, smem, st>>>(p);
   };
   if (k == 128) launch(proj_tf32x3_kernel<128>);
   else if (k == 64) launch(proj_tf32x3_kernel<64>);
