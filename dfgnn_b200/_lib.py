@@ -45,11 +45,13 @@ _SIGNATURES = {
     "dfgnn_gt_hyper_forward": (c_int, [c_int] * 4 + [_P] * 7 + [c_int] + [_P] * 5 + [_P]),
     "dfgnn_gt_backward": (c_int, [c_int] * 5 + [_P] * 7 + [c_int] + [_P] * 9 + [_P]),
     "dfgnn_gt_backward_phase": (c_int, [c_int] * 6 + [_P] * 7 + [c_int] + [_P] * 9 + [_P]),
-    "dfgnn_block_plan_check": (c_int, [c_int] * 3 + [_P] * 5 + [_P]),
+    "dfgnn_block_plan_check": (c_int, [c_int] * 3 + [_P] * 6 + [_P]),
     "dfgnn_gt_block_supported": (c_int, [c_int] * 5),
     "dfgnn_set_block_mode": (c_int, [c_int]),
     "dfgnn_gt_dense_supported": (c_int, [c_int] * 3),
     "dfgnn_gt_dense_forward": (c_int, [c_int, _P] + [c_int] * 5 + [_P] * 7 + [_P]),
+    "dfgnn_gt_dense_tc_supported": (c_int, [c_int] * 3),
+    "dfgnn_gt_dense_tc_forward": (c_int, [c_int, _P] + [c_int] * 5 + [_P] * 7 + [_P]),
     "dfgnn_gt_block_forward": (c_int, [c_int, _P] + [c_int] * 5 + [_P] * 8 + [_P]),
     "dfgnn_gt_block_backward": (c_int, [c_int, c_int, _P] + [c_int] * 5 + [_P] * 15 + [_P]),
     "dfgnn_proj_weight_image_floats": (c_size_t, [c_int, c_int]),

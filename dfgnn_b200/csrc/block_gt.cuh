@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(NW * 32, 1) gt_block_bwd_col_kernel(const GtBl
 }
 
 // every column id of a block's rows lies inside the block; blk_ptr is increasing from 0 to m.
-// flag[0] != 0 on violation; flag[1] = largest block.
+// flag[0] != 0 on violation; flag[1] = largest block; flag[2]: see below.
 static __global__ void block_check_kernel(int n_blocks, int m, const int* __restrict__ blk_ptr,
                                           const int* __restrict__ row_ptr, const int* __restrict__ col_ind,
                                           int* __restrict__ flag) {
@@ -514,6 +514,17 @@ static __global__ void block_check_kernel(int n_blocks, int m, const int* __rest
   for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
     const int c = col_ind[e];
     if (c < lo || c >= hi) { atomicOr(flag, 1); break; }
+  }
+  // flag[2] != 0: some row's column ids are not strictly ascending (unsorted or duplicate edges);
+  // the dense kernels address attn_edge by the rank of a column inside its row and need that order
+  for (int r = lo + threadIdx.x; r < hi; r += blockDim.x) {
+    const int rs = row_ptr[r], re = row_ptr[r + 1];
+    int prev = -1;
+    for (int e = rs; e < re; ++e) {
+      const int c = col_ind[e];
+      if (c <= prev) { atomicOr(flag + 2, 1); break; }
+      prev = c;
+    }
   }
 }
 

@@ -6,15 +6,15 @@
 
 namespace dfgnn {
 
-// Mode (dfgnn_set_block_mode; initial value from DFGNN_B200_BLOCK=0|1|2): 0 auto, 1 off, 2 the
-// shared-memory-staged sparse kernels (block_gt.cuh) whenever they fit, 3 the dense tensor-core
-// kernels (dense_gt.cuh) whenever they fit.  Auto: dense kernels for dense batches (the caller
+// Mode (dfgnn_set_block_mode; initial value from DFGNN_B200_BLOCK=0|1|2|3): 0 auto, 1 off, 2 the
+// shared-memory-staged sparse kernels (block_gt.cuh) whenever they fit, 3 the dense mma.sync
+// kernels (dense_gt.cuh) whenever they fit, 4 the dense tcgen05 kernels (dense_tc.cu).  Auto: dense kernels for dense batches (the caller
 // checks the density), never the staged sparse ones (measured slower than the row-block kernels on
 // the PATTERN-shaped batch: both are instruction-issue bound).
 static std::atomic<int>& block_mode() {
   static std::atomic<int> v{[] {
     const char* e = getenv("DFGNN_B200_BLOCK");
-    return e ? (e[0] == '0' ? 1 : (e[0] == '2' ? 3 : 2)) : 0;
+    return e ? (e[0] == '0' ? 1 : (e[0] == '2' ? 3 : (e[0] == '3' ? 4 : 2))) : 0;
   }()};
   return v;
 }
@@ -79,17 +79,18 @@ using namespace dfgnn;
 extern "C" {
 
 int dfgnn_block_plan_check(int n_blocks, int m, int nnz, const int32_t* blk_ptr, const int32_t* row_ptr,
-                           const int32_t* col_ind, int32_t* flag_ws, int32_t* max_nodes_out, void* stream) {
+                           const int32_t* col_ind, int32_t* flag_ws, int32_t* max_nodes_out, int32_t* ascending_out,
+                           void* stream) {
   const char* fn = "dfgnn_block_plan_check";
   if (n_blocks < 1 || m < 0 || nnz < 0) { set_error("%s: invalid sizes", fn); return DFGNN_ERR_INVALID_ARGUMENT; }
   DFGNN_REQUIRE(blk_ptr, fn); DFGNN_REQUIRE(row_ptr, fn); DFGNN_REQUIRE(flag_ws, fn); DFGNN_REQUIRE(max_nodes_out, fn);
   if (nnz > 0) DFGNN_REQUIRE(col_ind, fn);
   cudaStream_t st = (cudaStream_t)stream;
-  cudaMemsetAsync(flag_ws, 0, 2 * sizeof(int32_t), st);
+  cudaMemsetAsync(flag_ws, 0, 3 * sizeof(int32_t), st);
   block_check_kernel<<<n_blocks, 256, 0, st>>>(n_blocks, m, blk_ptr, row_ptr, col_ind, flag_ws);
   if (int rc = check_launch(fn)) return rc;
-  int h_flag[2] = {0, 0};
-  cudaError_t err = cudaMemcpyAsync(h_flag, flag_ws, 2 * sizeof(int), cudaMemcpyDeviceToHost, st);
+  int h_flag[3] = {0, 0, 0};
+  cudaError_t err = cudaMemcpyAsync(h_flag, flag_ws, 3 * sizeof(int), cudaMemcpyDeviceToHost, st);
   if (err == cudaSuccess) err = cudaStreamSynchronize(st);
   if (err != cudaSuccess) { set_error("%s: %s", fn, cudaGetErrorString(err)); return (int)err; }
   if (h_flag[0]) {
@@ -97,11 +98,12 @@ int dfgnn_block_plan_check(int n_blocks, int m, int nnz, const int32_t* blk_ptr,
     return DFGNN_ERR_INVALID_ARGUMENT;
   }
   *max_nodes_out = h_flag[1];
+  if (ascending_out) *ascending_out = h_flag[2] ? 0 : 1;
   return DFGNN_OK;
 }
 
 int dfgnn_set_block_mode(int mode) {
-  if (mode < 0 || mode > 3) return block_override();
+  if (mode < 0 || mode > 4) return block_override();
   return block_mode().exchange(mode);
 }
 

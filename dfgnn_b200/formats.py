@@ -120,25 +120,32 @@ class BlockPlan:
     # dense tensor-core kernels from this fill ratio of the diagonal blocks on (automatic mode)
     DENSE_MIN_FILL = 0.15
 
-    def __init__(self, blk_ptr: torch.Tensor, n_blocks: int, max_nodes: int, sum_sq_nodes: int = 0):
+    def __init__(self, blk_ptr: torch.Tensor, n_blocks: int, max_nodes: int, sum_sq_nodes: int = 0,
+                 ascending: bool = True):
         self.blk_ptr = blk_ptr
         self.n_blocks = int(n_blocks)
         self.max_nodes = int(max_nodes)
         self.sum_sq_nodes = int(sum_sq_nodes)   # sum over graphs of nodes^2 = entries of the dense blocks
+        self.ascending = bool(ascending)        # column ids strictly ascending inside every row
         self._ok = {}
 
     def algorithm(self, m: int, nnz: int, h: int, f: int, unweighted: bool, training: bool = False) -> int:
-        """0 general kernels, 1 shared-memory-staged sparse kernels, 2 dense tensor-core kernels
-        (forward); see dfgnn_set_block_mode.  Automatic mode picks the dense kernels for INFERENCE on
-        dense batches (measured on the PATTERN-shaped batch: 0.35 ms vs 0.41 ms); the training forward
-        also scatters attn_edge, which costs the dense tiles more than it gains (0.47 vs 0.44 ms)."""
+        """0 general kernels, 1 shared-memory-staged sparse kernels, 2 dense mma.sync kernels
+        (forward), 3 dense tcgen05 kernels (csrc/dense_tc.cu); see dfgnn_set_block_mode.  The dense
+        kernels need unweighted scores and strictly ascending column ids per row (no duplicate
+        edges).  Automatic mode picks the tcgen05 kernels for dense batches wherever they apply
+        (f == 128, graphs of at most 256 nodes), else the mma.sync kernels for inference only."""
         L = _lib.lib()
         mode = L.dfgnn_set_block_mode(-1)
         key = ("algo", m, nnz, h, f, unweighted, training, mode)
         if key not in self._ok:
             algo = 0
-            if unweighted and L.dfgnn_gt_dense_supported(self.max_nodes, h, f):
-                fill = nnz / self.sum_sq_nodes if self.sum_sq_nodes > 0 else 0.0
+            fill = nnz / self.sum_sq_nodes if self.sum_sq_nodes > 0 else 0.0
+            dense_ok = unweighted and self.ascending and nnz > 0
+            if dense_ok and mode in (0, 4) and L.dfgnn_gt_dense_tc_supported(self.max_nodes, h, f):
+                if mode == 4 or fill >= self.DENSE_MIN_FILL:
+                    algo = 3
+            if algo == 0 and dense_ok and L.dfgnn_gt_dense_supported(self.max_nodes, h, f):
                 if mode == 3 or (fill >= self.DENSE_MIN_FILL and not training):
                     algo = 2
             if algo == 0 and L.dfgnn_gt_block_supported(self.max_nodes, m, nnz, h, f):
@@ -169,14 +176,14 @@ def block_plan(batch_num_nodes: torch.Tensor, row_ptr: torch.Tensor, col_ind: to
     blk[1:] = torch.cumsum(bnn, 0).to(torch.int32)
     blk = blk.to(dev)
     with torch.cuda.device(dev):
-        flag = torch.empty(2, dtype=torch.int32, device=dev)
-        mx = ctypes.c_int32(0)
+        flag = torch.empty(4, dtype=torch.int32, device=dev)
+        mx, asc = ctypes.c_int32(0), ctypes.c_int32(0)
         rc = _lib.lib().dfgnn_block_plan_check(
             bnn.numel(), m, col_ind.numel(), blk.data_ptr(), row_ptr.data_ptr(),
             col_ind.data_ptr() if col_ind.numel() else None, flag.data_ptr(), ctypes.addressof(mx),
-            torch.cuda.current_stream(dev).cuda_stream)
+            ctypes.addressof(asc), torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(rc, "block_plan")
-    return BlockPlan(blk, bnn.numel(), mx.value, int((bnn * bnn).sum()))
+    return BlockPlan(blk, bnn.numel(), mx.value, int((bnn * bnn).sum()), bool(asc.value))
 
 
 def attach_block_plan(g, row_ptr: torch.Tensor, col_ind: torch.Tensor):

@@ -46,14 +46,15 @@ def _val_ptr(val):
 def _blocks(row_ptr, m, nnz, h, f, val=None, backward=False, training=False):
     """-> (plan, algo): the block plan the preprocessing attached to row_ptr
     (formats.attach_block_plan) and the kernel family for this call -- 0 general, 1 shared-memory
-    staged (block_gt.cuh), 2 dense tensor-core (dense_gt.cuh, forward only)."""
+    staged (block_gt.cuh), 2 dense mma.sync (dense_gt.cuh, forward only), 3 dense tcgen05
+    (dense_tc.cu)."""
     from ..formats import find_block_plan
     plan = find_block_plan(row_ptr)
     if plan is None or plan.blk_ptr.device != row_ptr.device:
         return None, 0
     unweighted = val is None or getattr(val, "_dfgnn_ones", False)
     algo = plan.algorithm(m, nnz, h, f, unweighted, training or backward)
-    if backward and algo == 2:
+    if backward and algo >= 2:  # the dense kernels are forward kernels
         algo = 1 if plan.supported(m, nnz, h, f) else 0
     return (plan, algo) if algo else (None, 0)
 
@@ -92,6 +93,10 @@ def _check_gt(fn, indptr, indices, Q, K, V, rows=None, val=None):
 
 def _block_forward(plan, algo, m, nnz, h, f, row_ptr, col_ind, val, Q, K, V, out, attn):
     L = _lib.lib()
+    if algo == 3:
+        return L.dfgnn_gt_dense_tc_forward(plan.n_blocks, _ptr(plan.blk_ptr), plan.max_nodes, m, nnz, h, f,
+                                           _ptr(row_ptr), _ptr(col_ind), _ptr(Q), _ptr(K), _ptr(V), _ptr(out),
+                                           _ptr(attn), _stream(Q))
     if algo == 2:
         return L.dfgnn_gt_dense_forward(plan.n_blocks, _ptr(plan.blk_ptr), plan.max_nodes, m, nnz, h, f,
                                         _ptr(row_ptr), _ptr(col_ind), _ptr(Q), _ptr(K), _ptr(V), _ptr(out),

@@ -170,18 +170,20 @@ int dfgnn_gt_backward_cols(int col_begin, int n_sub, int nnz_sub, int m, int n, 
  * blocks in shared memory (csrc/block_gt.cuh).  Results are those of the entry points above.
  *
  * dfgnn_block_plan_check validates that every column id of a block's rows lies inside the block
- * (one small device -> host readback; flag_ws = 2 ints of device scratch) and returns the largest
- * block in *max_nodes_out (host).  dfgnn_gt_block_supported tells whether the block kernels would
+ * (one small device -> host readback; flag_ws = 3 ints of device scratch) and returns the largest
+ * block in *max_nodes_out (host) and, in *ascending_out (host, may be NULL), whether the column ids
+ * of every row are strictly ascending (sorted, no duplicate edges) -- the dense kernels need that.  dfgnn_gt_block_supported tells whether the block kernels would
  * be used for this size in the current mode (h == 1, f in {32, 64, 128}, both operand blocks of
  * the largest graph fit shared memory); callers fall back to the general entry points otherwise.
  */
 int dfgnn_block_plan_check(int n_blocks, int m, int nnz, const int32_t *blk_ptr,
                            const int32_t *row_ptr, const int32_t *col_ind, int32_t *flag_ws,
-                           int32_t *max_nodes_out, void *stream);
+                           int32_t *max_nodes_out, int32_t *ascending_out, void *stream);
 int dfgnn_gt_block_supported(int max_nodes, int m, int nnz, int h, int f);
 /* 0 = automatic choice (default: the dense kernels below for dense batches), 1 = general kernels
- * only, 2 = the shared-memory-staged sparse kernels whenever they fit, 3 = the dense kernels
- * whenever they fit; returns the previous mode (an out-of-range argument only queries). */
+ * only, 2 = the shared-memory-staged sparse kernels whenever they fit, 3 = the dense mma.sync
+ * kernels whenever they fit, 4 = the dense tcgen05 kernels whenever they fit; returns the previous
+ * mode (an out-of-range argument only queries). */
 int dfgnn_set_block_mode(int mode);
 /* = dfgnn_gt_hyper_forward (attn_edge may be NULL: inference). */
 int dfgnn_gt_block_forward(int n_blocks, const int32_t *blk_ptr, int max_nodes, int m, int nnz,
@@ -198,6 +200,18 @@ int dfgnn_gt_dense_forward(int n_blocks, const int32_t *blk_ptr, int max_nodes, 
                            int h, int f, const int32_t *row_ptr, const int32_t *col_ind,
                            const float *Q, const float *K, const float *V, float *out_feat,
                            float *attn_edge, void *stream);
+/*
+ * Dense tcgen05 variant (csrc/dense_tc.cu): per 128-row tile S = Q K^T and O = P V as tcgen05.mma
+ * kind::tf32 with the 3xTF32 split, accumulators in tensor memory, softmax by one thread per row
+ * straight from tensor memory.  h == 1, f == 128, graphs of at most 256 nodes, unweighted scores,
+ * strictly ascending column ids per row (dfgnn_block_plan_check).  Same outputs as
+ * dfgnn_gt_hyper_forward (attn_edge may be NULL: inference).
+ */
+int dfgnn_gt_dense_tc_supported(int max_nodes, int h, int f);
+int dfgnn_gt_dense_tc_forward(int n_blocks, const int32_t *blk_ptr, int max_nodes, int m, int nnz,
+                              int h, int f, const int32_t *row_ptr, const int32_t *col_ind,
+                              const float *Q, const float *K, const float *V, float *out_feat,
+                              float *attn_edge, void *stream);
 /* = dfgnn_gt_backward_phase on a square block-diagonal adjacency (n == m). */
 int dfgnn_gt_block_backward(int phases, int n_blocks, const int32_t *blk_ptr, int max_nodes, int m,
                             int nnz, int h, int f, const int32_t *row_ptr, const int32_t *col_ind,

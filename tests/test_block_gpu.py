@@ -182,3 +182,66 @@ def test_dense_tensor_core_forward(cuda, kind, dim):
     inf2 = N.gt_hyper_inference(row_ptr, col_ind, rows, val, smem, Q, K, V)[0]
     assert _lib.last_kernel(0) == ("gt_dense_fwd_kernel" if fill >= plan.DENSE_MIN_FILL else "dot_fwd_kernel")
     assert_close("automatic mode inference", inf2, o64)
+
+
+def _batch_tc(kind):
+    if kind == "wide":   # graphs of 130-256 nodes: two row tiles, two key halves, partial last slices
+        return graphs.batched_graph(5, 200.0, 40.0, 130, 256, 40.0, 15.0, 1, None, 6, "wide")
+    return _batch(kind)
+
+
+@pytest.mark.parametrize("kind", ["pattern", "pattern-max", "ragged", "wide"])
+def test_dense_tcgen05_forward(cuda, kind):
+    """dense_tc.cu: per 128-row tile S = Q K^T and O = P V on tcgen05 (3xTF32, accumulators in tensor
+    memory), softmax from tensor memory -- out and attn_edge against the fp64 oracle, training and
+    inference entry points, many more graphs than SMs would be needed to wrap the persistent loop, so
+    the batch is also run twice through a 2-CTA-sized plan below."""
+    _lib.lib().dfgnn_set_block_mode(4)
+    g = _batch_tc(kind)
+    n = g.num_nodes()
+    X = graphs.conv_inputs(n, 128, 29)
+    A, rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx, smem = preprocess_Hyper_fw_bw(g.to(cuda))
+    plan = row_ptr._dfgnn_blocks
+    assert plan.ascending and plan.algorithm(n, col_ind.numel(), 1, 128, True, training=True) == 3
+    Q, K, V, dO = (t.to(cuda) for t in (X.Q, X.K, X.V, X.dO))
+    out, attn = N.gt_hyper_forward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V)
+    assert _lib.last_kernel(0) == "gt_dense_tc_fwd_kernel"
+    o64, a64, dQ, dK, dV = _oracle(g, X)
+    assert_close("out", out, o64)
+    assert_close("attn_edge", attn, a64)
+    inf = N.gt_hyper_inference(row_ptr, col_ind, rows, val, smem, Q, K, V)[0]
+    assert _lib.last_kernel(0) == "gt_dense_tc_fwd_kernel"
+    assert torch.equal(inf, out)
+    # the backward consumes the dense forward's attn_edge
+    gq, gk, gv = N.gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V, attn, dO)
+    assert_close("grad_Q", gq, dQ)
+    assert_close("grad_K", gk, dK)
+    assert_close("grad_V", gv, dV)
+    # other widths and weighted scores stay on the other kernels
+    assert plan.algorithm(n, col_ind.numel(), 1, 64, True) != 3
+    assert plan.algorithm(n, col_ind.numel(), 1, 128, False) != 3
+
+
+def test_dense_tcgen05_persistent_loop_and_unsorted_fallback(cuda):
+    """600 graphs on 148 persistent CTAs (every CTA walks several graphs: ring slots, tensor memory
+    and barrier phases are reused across tiles); a CSR whose rows are not sorted by column falls
+    back to the general kernels."""
+    _lib.lib().dfgnn_set_block_mode(4)
+    g = graphs.batched_graph(600, 60.0, 50.0, 1, 200, 20.0, 15.0, 0, None, 8, "many")
+    n = g.num_nodes()
+    X = graphs.conv_inputs(n, 128, 31)
+    row_ptr, col_ind, rows, val, smem = preprocess_Hyper(g.to(cuda))
+    Q, K, V = (t.to(cuda) for t in (X.Q, X.K, X.V))
+    out = N.gt_hyper_inference(row_ptr, col_ind, rows, val, smem, Q, K, V)[0]
+    assert _lib.last_kernel(0) == "gt_dense_tc_fwd_kernel"
+    out2 = N.gt_hyper_inference(row_ptr.clone(), col_ind, rows, val, smem, Q, K, V)[0]
+    assert _lib.last_kernel(0) == "dot_fwd_kernel"
+    assert_close("dense tcgen05 vs general kernels", out, out2)
+    # reverse the column order inside every row: still a valid CSR, no longer ascending
+    rp = row_ptr.long()
+    pos = torch.arange(col_ind.numel(), device=cuda)
+    rowid = torch.repeat_interleave(torch.arange(n, device=cuda), rp[1:] - rp[:-1])
+    rev = (rp[rowid] + rp[rowid + 1] - 1 - pos)
+    ci_rev = col_ind[rev].contiguous()
+    plan = formats.block_plan(g.batch_num_nodes(), row_ptr, ci_rev)
+    assert not plan.ascending and plan.algorithm(n, ci_rev.numel(), 1, 128, True) != 3

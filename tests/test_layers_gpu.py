@@ -87,8 +87,10 @@ def test_fused_projection_in_the_gat_training_layer(cuda):
         (out * w).sum().backward()
         res.append((out.detach().clone(), [p.grad.clone() for p in layer.parameters()]))
     assert_close("gat layer out", res[1][0], res[0][0])
+    # parameter gradients are sums over all nodes with cancellation: an element that sums to ~0 keeps
+    # the rounding error of its largest terms, so the absolute allowance scales with the tensor
     for (name, _), a, b in zip(layer.named_parameters(), res[1][1], res[0][1]):
-        assert_close(name + ".grad", a, b, rtol=1e-3, atol=1e-4)
+        assert_close(name + ".grad", a, b, rtol=1e-3, atol=1e-4 * max(1.0, float(b.abs().max())))
 
 
 def test_agnn_literal_two_step_path(cuda):

@@ -30,7 +30,7 @@ def timeit(fn, it=10):
 
 
 print("lib", _lib.LIB_PATH)
-for mode, name in ((1, "general"), (2, "staged"), (3, "dense")):
+for mode, name in ((1, "general"), (2, "staged"), (3, "dense"), (4, "dense-tc")):
     _lib.lib().dfgnn_set_block_mode(mode)
     t_tr = timeit(lambda: N.gt_hyper_forward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V))
     k = _lib.last_kernel(0)
