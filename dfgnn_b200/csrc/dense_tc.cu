@@ -5,79 +5,156 @@
 // a small masked dense attention: S = Q K^T, P = softmax over the row's neighbours, O = P V.  The
 // per-edge kernels (fwd_kernels.cuh, block_gt.cuh) spend ~40 warp instructions and 1 KB of L1 /
 // shared-memory traffic per edge there and are load/store-unit bound at 0.45 ms per forward; as two
-// GEMMs per 128-row tile the same work is 96 tcgen05.mma instructions and the kernel is bound by
-// reading Q, K, V once and writing O and attn_edge once (0.3 GB per forward on that batch).
+// GEMMs per 128-row tile the kernel is bound by reading Q, K, V once and writing O and attn_edge once.
 //
 // fp32 parity (1e-4 relative) from TF32 tensor cores by the 3xTF32 split: x = hi + lo with hi = x
-// truncated to TF32, a b ~ a_lo b_hi + a_hi b_lo + a_hi b_hi, fp32 accumulation in tensor memory.
+// truncated to TF32, a b ~ a_hi b_hi + a_hi b_lo + a_lo b_hi, fp32 accumulation in tensor memory.
+// A tcgen05.mma kind::tf32 costs ~118 cycles for any N <= 128 and 128 cycles for N = 256 (measured,
+// tools/umma_bench.cu), so the hi and lo images of the B operand are STACKED along N: one N = 256 MMA
+// gives a_hi b_hi (columns 0-127) and a_hi b_lo (columns 128-255), one N = 128 MMA adds a_lo b_hi;
+// the two column halves are summed when the accumulator is read.
+//
+// The adjacency of the batch comes as a bitmap (dfgnn_block_adj_bits: 256 bits per row, bit j = key j
+// of the row's own graph), a format built once per batch like the CSC: the kernel never reads col_ind.
 //
 // One persistent CTA per SM walks graphs; a graph of n <= 256 nodes is one or two tiles of 128 query
 // rows.  Roles (warp specialised, mbarriers only):
-//   warps 0-3    softmax / epilogue: thread r owns tile row r = TMEM lane r.  Builds the row's adjacency
-//                bit mask from the CSR while the first product runs, then reads S from tensor memory in
-//                32-column pieces: pass 1 row max, pass 2 p = 2^(s - max) (unnormalised) split into the A
-//                images of the second product, pass 3 (training) normalised probabilities to attn_edge;
-//                finally O * (1 / row sum) -> out through a shared-memory staging buffer (coalesced).
-//   warp  4      MMA issue (one lane).  Product 1: S[128 x keys] += Q_slice K_slice^T over four 32-wide
-//                slices of the feature dimension (two key halves when n > 128).  Product 2:
-//                O[128 x 128] += P_slice V_slice over 32-key slices.  3 MMAs (lo*hi, hi*lo, hi*hi) per K = 8.
-//   warps 5-16   three loader groups of 4 warps, group g fills ring slot g: global -> registers (issued
-//                before the slot is free, so up to three stages of loads are in flight) -> hi / lo split ->
-//                canonical K-major images.  Product 1 stages carry Q (A) and K (B) slices; product 2
-//                stages carry V TRANSPOSED (B: rows = features, k = keys; read as coalesced scalars,
-//                stored as one float4 of four keys) while the softmax threads supply P (A).
-// Ring: 3 slots x {A_hi, A_lo, B_hi, B_lo} x (128 rows x 32 floats) = 192 KB.  Tensor memory: S in
-// columns [0, 256), O in [256, 384).
+//   warps 0-7    softmax / epilogue, two groups of 4 warps that share every tile: group g takes the
+//                32-column pieces cb with (cb & 1) == g; thread r of either group owns tile row r = TMEM
+//                lane r.  Pass 1 row max (combined through shared memory), pass 2 p = 2^(s - max)
+//                (unnormalised) split into the A images of the second product, pass 3 (training)
+//                normalised probabilities to attn_edge through a warp transposition (coalesced stores);
+//                finally O * (1 / row sum) -> out through a staging buffer (coalesced stores).
+//   warp  8      MMA issue (one lane).  Product 1: S[128 x keys] += Q_slice K_slice^T over slices of the
+//                feature dimension; product 2: O[128 x 128] += P_slice V_slice over 32-key slices.
+//   warps 9-16   two loader groups of 4 warps taking alternate ring stages: global -> registers (issued
+//                before the slot is free) -> hi / lo split -> canonical K-major images.  Product 1 stages
+//                carry Q (A) and K (B); product 2 stages carry V TRANSPOSED (B: rows = features, k = keys;
+//                read as coalesced scalars, stored as one float4 of four keys) while the softmax threads
+//                supply P (A).
+// Ring: 3 slots of 64 KB.  Stage formats (all images "chunk major": 16-byte k-chunk c of row r at
+// c * rows * 16 + r * 16):
+//   narrow product 1 (n <= 128), K = 32:  A_hi | A_lo (128 rows) | B = K_hi over K_lo (256 rows)
+//   wide product 1 (n > 128),   K = 16:  A_hi | A_lo (128 rows) | K_hi (256 rows) | K_lo (256 rows)
+//   product 2, K = 32 keys:              P_hi | P_lo (128 rows) | B = V^T_hi over V^T_lo (256 rows)
+// Tensor memory: S in columns [0, 256) (narrow tiles: two halves to be summed), O in [256, 512) (two
+// halves to be summed).
 //
 // Requirements (checked by the block plan, formats.py / dfgnn_block_plan_check): h == 1, f == 128,
 // unweighted scores, graphs of at most 256 nodes, column ids strictly ascending inside every row (no
-// duplicate edges: a dense mask cannot count an edge twice).  Reference counterpart:
+// duplicate edges: a bitmap cannot count an edge twice).  Reference counterpart:
 // fused_gtconv_hyper.cu:31-163 (forward) and, for the maths, DFGNN/layers/GT/gtconv_layer.py:28-45.
 #include "abi_common.h"
-#include "block_gt.cuh"
 #include "tc_common.cuh"
 
 namespace dfgnn {
 
-constexpr int kTcM = 128;                        // rows per tile (UMMA M) and rows of every image
+constexpr int kTcM = 128;                        // rows per tile (UMMA M)
 constexpr int kTcF = 128;                        // feature width
-constexpr int kTcKS = 32;                        // contraction slice of one ring stage
 constexpr int kTcSlots = 3;
-constexpr int kTcImg = kTcM * kTcKS * 4;         // one image: 128 rows x 32 floats = 16 KB
-constexpr int kTcSlotBytes = 4 * kTcImg;         // A_hi | A_lo | B_hi | B_lo
+constexpr int kTcSlotBytes = 64 * 1024;
 constexpr int kTcMaxNodes = 256;
-constexpr int kTcSoftWarps = 4, kTcLoadGroups = kTcSlots, kTcGroupWarps = 4;
+constexpr int kTcSoftWarps = 8, kTcLoadGroups = 2, kTcGroupWarps = 4;
 constexpr int kTcGroupThreads = kTcGroupWarps * 32;
+constexpr int kTcMmaWarp = kTcSoftWarps;
 constexpr int kTcThreads = (kTcSoftWarps + 1 + kTcLoadGroups * kTcGroupWarps) * 32;  // 544
-constexpr int kTcMaskW = kTcMaxNodes / 32;       // mask words per row
-constexpr int kTcStgLd = 36;                     // epilogue staging row stride (floats)
-constexpr uint32_t kTcLBO = kTcM * 16, kTcSBO = 128;
+constexpr int kTcMaskW = kTcMaxNodes / 32;       // bitmap words per row
+constexpr int kTcStgLd = 20;                     // epilogue staging: 16 columns per row + 4 floats of padding
+constexpr uint32_t kTcSBO = 128;
+constexpr uint32_t kTcLboA = 128 * 16;           // chunk stride of a 128-row image
+constexpr uint32_t kTcLboB = 256 * 16;           // chunk stride of a 256-row image
 constexpr int kTcColO = 256;                     // first tensor-memory column of O
 
-constexpr size_t kTcOffMask = (size_t)kTcSlots * kTcSlotBytes;
-constexpr size_t kTcOffStage = kTcOffMask + (size_t)kTcM * kTcMaskW * 4;
-constexpr size_t kTcOffRp = kTcOffStage + (size_t)kTcM * kTcStgLd * 4;
-constexpr size_t kTcSmemBytes = kTcOffRp + (size_t)(kTcM + 4) * 4;
+// slot carve (bytes)
+constexpr int kTcN1_Alo = 16 * 1024, kTcN1_B = 32 * 1024;                          // K = 32 stages
+constexpr int kTcW1_Alo = 8 * 1024, kTcW1_Bhi = 16 * 1024, kTcW1_Blo = 32 * 1024;  // K = 16 stages
 
-// barrier among the 128 threads of the softmax group
-__device__ __forceinline__ void soft_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+constexpr size_t kTcOffStage = (size_t)kTcSlots * kTcSlotBytes;
+constexpr size_t kTcOffPart = kTcOffStage + (size_t)2 * kTcM * kTcStgLd * 4;   // one staging buffer per softmax group
+constexpr size_t kTcSmemBytes = kTcOffPart + (size_t)4 * kTcM * 4;             // partial row max / sum of the two groups
 
-__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+// barrier among the 128 threads of one softmax group / among all 256 softmax threads
+__device__ __forceinline__ void soft_bar(int group) { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); }
+__device__ __forceinline__ void soft_bar_all() { asm volatile("bar.sync 3, 256;" ::: "memory"); }
 
-__global__ void __launch_bounds__(kTcThreads, 1) gt_dense_tc_fwd_kernel(const GtBlockFwdParams pp) {
-  const DotFwdParams& p = pp.c;
+__device__ __forceinline__ uint32_t sel8(const uint32_t (&a)[8], int i) {  // a[i] without local memory
+  uint32_t v = a[0];
+#pragma unroll
+  for (int k = 1; k < 8; ++k) v = (i == k) ? a[k] : v;
+  return v;
+}
+
+#ifdef DFGNN_TC_PROF
+// developer build: cycles block 0 spends in / waiting for each step (tools/time_tc.py prints them);
+// one thread per role: softmax tid 0, MMA tid 256, loader group 0 tid 288
+__device__ unsigned long long g_tc_prof[32];
+#define TC_ON() (blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 256 || threadIdx.x == 288))
+#define TC_TIMED(slot, stmt) do { const long long _t0 = clock64(); stmt; if (TC_ON()) g_tc_prof[slot] += (unsigned long long)(clock64() - _t0); } while (0)
+#define TC_MARK(var) const long long var = clock64()
+#define TC_SINCE(slot, var) do { if (TC_ON()) g_tc_prof[slot] += (unsigned long long)(clock64() - var); } while (0)
+#else
+#define TC_TIMED(slot, stmt) do { stmt; } while (0)
+#define TC_MARK(var)
+#define TC_SINCE(slot, var)
+#endif
+
+// the tiles of this CTA, in the order every role walks them.  With a schedule (sched_ptr / sched_idx:
+// the graphs of CTA c are sched_idx[sched_ptr[c] .. sched_ptr[c + 1]), balanced by the host from the
+// graph sizes) a CTA walks its own list; without one, graphs blockIdx.x, blockIdx.x + gridDim.x, ...
+struct TcTiles {
+  const int *blk, *sidx;
+  int i, i_end, step, mt, MT, lb, n;
+  __device__ TcTiles(const int* blk_, int nb, const int* sched_ptr, const int* sched_idx) : blk(blk_), sidx(sched_idx), mt(0), MT(0), lb(0), n(0) {
+    if (sched_ptr) {
+      i = __ldg(sched_ptr + blockIdx.x) - 1;
+      i_end = __ldg(sched_ptr + blockIdx.x + 1);
+      step = 1;
+    } else {
+      i = (int)blockIdx.x - (int)gridDim.x;
+      i_end = nb;
+      step = gridDim.x;
+    }
+  }
+  __device__ bool next() {
+    if (++mt < MT) return true;
+    for (i += step; i < i_end; i += step) {
+      const int b = sidx ? __ldg(sidx + i) : i;
+      lb = __ldg(blk + b);
+      n = __ldg(blk + b + 1) - lb;
+      if (n > 0) {
+        MT = (n + kTcM - 1) / kTcM;
+        mt = 0;
+        return true;
+      }
+    }
+    MT = 0;
+    return false;
+  }
+  __device__ int stages1() const { return MT == 1 ? 4 : 8; }   // product-1 stages of a tile
+  __device__ int stages2() const { return (n + 31) >> 5; }     // product-2 stages (32-key slices)
+};
+
+struct GtTcFwdParams {
+  int n_blocks;
+  const int* blk_ptr;
+  const int* row_ptr;
+  const int *sched_ptr, *sched_idx;  // optional balanced schedule (null: round robin)
+  const uint32_t* adj_bits;  // [m][8]
+  const float *Q, *K, *V;
+  float *out, *attn;         // attn may be null (inference)
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1) gt_dense_tc_fwd_kernel(const GtTcFwdParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t full_b[kTcSlots], full_a[kTcSlots], empty[kTcSlots], s_full, s_free, o_full, o_free;
   __shared__ uint32_t s_tmem;
-  uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem + kTcOffMask);
   float* s_stg = reinterpret_cast<float*>(smem + kTcOffStage);
-  int* s_rp = reinterpret_cast<int*>(smem + kTcOffRp);
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   if (tid == 0) {
     for (int i = 0; i < kTcSlots; ++i) {
       mbar_init(&full_b[i], kTcGroupThreads);
-      mbar_init(&full_a[i], kTcSoftWarps * 32);
+      mbar_init(&full_a[i], 128);  // one softmax group writes a whole P slice
       mbar_init(&empty[i], 1);
     }
     mbar_init(&s_full, 1);
@@ -86,7 +163,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gt_dense_tc_fwd_kernel(const Gt
     mbar_init(&o_free, kTcSoftWarps * 32);
     mbar_fence_init();
   }
-  if (w == 0) {  // all 512 columns: S (256) + O (128), one CTA per SM
+  if (w == 0) {  // all 512 columns, one CTA per SM
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -95,287 +172,407 @@ __global__ void __launch_bounds__(kTcThreads, 1) gt_dense_tc_fwd_kernel(const Gt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
-  const int nb = pp.b.n_blocks;
-
-  auto slot_img = [&](int slot, int which) -> float4* {  // which: 0 A_hi, 1 A_lo, 2 B_hi, 3 B_lo
-    return reinterpret_cast<float4*>(smem + (size_t)slot * kTcSlotBytes + (size_t)which * kTcImg);
-  };
+  TC_MARK(t_kernel);
 
   if (w < kTcSoftWarps) {
     // =============================== softmax / epilogue ===========================================
-    const int r = tid;  // tile row = TMEM lane
-    const uint32_t lane_base = tmem + ((uint32_t)(w * 32) << 16);
+    const int sg = w >> 2, r = tid & 127;  // group, tile row
+    const uint32_t lane_base = tmem + ((uint32_t)((w & 3) * 32) << 16);
     const bool train = p.attn != nullptr;
+    float* s_part = reinterpret_cast<float*>(smem + kTcOffPart);  // [max | sum][group][row]
+    float* stg = s_stg + (size_t)sg * kTcM * kTcStgLd;            // this group's staging buffer
+    float* tp = stg + (size_t)((w & 3) * 32) * kTcStgLd;          // this warp's 32 x 17 transposition tile
     uint32_t sc = 0, tc = 0;
-    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
-      const int lb = __ldg(pp.b.blk_ptr + b), n = __ldg(pp.b.blk_ptr + b + 1) - lb;
-      if (n <= 0) continue;
-      const int MT = (n + kTcM - 1) / kTcM, NS2 = (n + 31) >> 5;
-      for (int mt = 0; mt < MT; ++mt, ++tc) {
-        const int row = mt * kTcM + r;
-        // ---- segment pointers and adjacency bits of the tile's rows (while product 1 runs) ----
-        s_rp[r] = __ldg(p.row_ptr + lb + min(row, n));
-        if (r == 0) s_rp[kTcM] = __ldg(p.row_ptr + lb + min(mt * kTcM + kTcM, n));
-        {
-          uint4* mz = reinterpret_cast<uint4*>(s_mask + r * kTcMaskW);
-          mz[0] = make_uint4(0u, 0u, 0u, 0u);
-          mz[1] = make_uint4(0u, 0u, 0u, 0u);
-        }
-        soft_bar();
-        for (int rr0 = w * 32; rr0 < w * 32 + 32; rr0 += 4) {  // a warp per row, four rows in flight
-          int j[4][2];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int e0 = s_rp[rr0 + u], e1 = s_rp[rr0 + u + 1];
-            j[u][0] = e0 + lane < e1 ? __ldg(p.col_ind + e0 + lane) - lb : -1;
-            j[u][1] = e0 + lane + 32 < e1 ? __ldg(p.col_ind + e0 + lane + 32) - lb : -1;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            uint32_t* mrow = s_mask + (rr0 + u) * kTcMaskW;
-#pragma unroll
-            for (int v = 0; v < 2; ++v)
-              if (j[u][v] >= 0) atomicOr(mrow + (j[u][v] >> 5), 1u << (j[u][v] & 31));
-            for (int e = s_rp[rr0 + u] + 64 + lane; e < s_rp[rr0 + u + 1]; e += 32) {
-              const int jj = __ldg(p.col_ind + e) - lb;
-              atomicOr(mrow + (jj >> 5), 1u << (jj & 31));
-            }
-          }
-        }
-        soft_bar();
-        uint32_t mw[kTcMaskW];
-        {
-          const uint4 m0 = *reinterpret_cast<const uint4*>(s_mask + r * kTcMaskW);
-          const uint4 m1 = *reinterpret_cast<const uint4*>(s_mask + r * kTcMaskW + 4);
-          mw[0] = m0.x; mw[1] = m0.y; mw[2] = m0.z; mw[3] = m0.w;
-          mw[4] = m1.x; mw[5] = m1.y; mw[6] = m1.z; mw[7] = m1.w;
-        }
-        const uint32_t sc2 = sc + 4u * MT;  // stage index of the first product-2 stage of this tile
-        // ---- S is complete ----------------------------------------------------------------------
-        mbar_wait(&s_full, tc & 1u);
-        tc_fence_after();
-        float mx = kNeg;
-#pragma unroll
-        for (int cb = 0; cb < kTcMaskW; ++cb) {
-          if (cb < NS2) {
-            float s[32];
-            tmem_ld32(lane_base + cb * 32, s);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, ((mw[cb] >> i) & 1u) ? s[i] : kNeg);
-          }
-        }
-        float l = 0.f;
-#pragma unroll
-        for (int cb = 0; cb < kTcMaskW; ++cb) {
-          if (cb < NS2) {
-            float s[32];
-            tmem_ld32(lane_base + cb * 32, s);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              s[i] = ((mw[cb] >> i) & 1u) ? fast_exp2(s[i] - mx) : 0.f;
-              l += s[i];
-            }
-            const uint32_t st = sc2 + cb, slot = st % kTcSlots, k = st / kTcSlots;
-            mbar_wait(&empty[slot], (k & 1u) ^ 1u);
-            float4* a_hi = slot_img(slot, 0);
-            float4* a_lo = slot_img(slot, 1);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              float4 hi, lo;
-              split4(make_float4(s[4 * c], s[4 * c + 1], s[4 * c + 2], s[4 * c + 3]), hi, lo);
-              a_hi[c * kTcM + r] = hi;
-              a_lo[c * kTcM + r] = lo;
-            }
-            fence_proxy_async();
-            mbar_arrive(&full_a[slot]);
-          }
-        }
-        const float inv = l > 0.f ? 1.f / l : 0.f;
-        if (train) {  // attn_edge in CSR order: the row's neighbours are its set mask bits, ascending
-          float* ap = p.attn + s_rp[r];
-#pragma unroll
-          for (int cb = 0; cb < kTcMaskW; ++cb) {
-            if (cb < NS2) {  // warp-uniform: tcgen05.ld is a warp-collective
-              float s[32];
-              tmem_ld32(lane_base + cb * 32, s);
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if ((mw[cb] >> i) & 1u) *ap++ = fast_exp2(s[i] - mx) * inv;
-            }
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(&s_free);
-        // ---- O is complete ----------------------------------------------------------------------
-        mbar_wait(&o_full, tc & 1u);
-        tc_fence_after();
-        float* obase = p.out + (size_t)(lb + mt * kTcM) * kTcF;
-        const int rows_here = min(kTcM, n - mt * kTcM);
-#pragma unroll 1
-        for (int cq = 0; cq < kTcF / 32; ++cq) {
-          float y[32];
-          tmem_ld32(lane_base + kTcColO + cq * 32, y);
-          if (cq == kTcF / 32 - 1) {
-            tc_fence_before();
-            mbar_arrive(&o_free);
-          }
-          float4* so = reinterpret_cast<float4*>(s_stg + (size_t)r * kTcStgLd);
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            so[i] = make_float4(y[4 * i] * inv, y[4 * i + 1] * inv, y[4 * i + 2] * inv, y[4 * i + 3] * inv);
-          soft_bar();
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int i = tid + u * 128, rr = i >> 3, c4 = i & 7;
-            if (rr < rows_here)
-              *reinterpret_cast<float4*>(obase + (size_t)rr * kTcF + cq * 32 + 4 * c4) =
-                  *reinterpret_cast<const float4*>(s_stg + (size_t)rr * kTcStgLd + 4 * c4);
-          }
-          soft_bar();
-        }
-        sc = sc2 + NS2;
+
+    // bitmap words and first CSR position of this thread's row (and of the tile), loaded one tile ahead
+    uint4 pre0 = make_uint4(0u, 0u, 0u, 0u), pre1 = pre0;
+    int pre_e0 = 0, pre_t0 = 0;
+    auto prefetch_row = [&](const TcTiles& t) {
+      const int row = t.mt * kTcM + r;
+      pre0 = pre1 = make_uint4(0u, 0u, 0u, 0u);
+      pre_t0 = __ldg(p.row_ptr + t.lb + t.mt * kTcM);
+      pre_e0 = pre_t0;
+      if (row < t.n) {
+        const uint4* src = reinterpret_cast<const uint4*>(p.adj_bits + (size_t)(t.lb + row) * kTcMaskW);
+        pre0 = __ldg(src);
+        pre1 = __ldg(src + 1);
+        pre_e0 = __ldg(p.row_ptr + t.lb + row);
       }
+    };
+    TcTiles nxt(p.blk_ptr, p.n_blocks, p.sched_ptr, p.sched_idx);
+    bool have = nxt.next();
+    if (have) prefetch_row(nxt);
+    while (have) {
+      const TcTiles t = nxt;
+      uint32_t mw[kTcMaskW] = {pre0.x, pre0.y, pre0.z, pre0.w, pre1.x, pre1.y, pre1.z, pre1.w};
+      const int tile_e0 = pre_t0;
+      int e_rel = pre_e0 - pre_t0;  // CSR position of the row's next entry, relative to the tile's first (< 2^15)
+      have = nxt.next();
+      if (have) prefetch_row(nxt);
+
+      const bool narrow = t.MT == 1;
+      const int NS2 = t.stages2();
+      const uint32_t sc2 = sc + t.stages1();  // stage index of the first product-2 stage of this tile
+      auto load_s = [&](int cb, float (&s)[32]) {  // 32 columns of S (narrow tiles: the sum of the two halves)
+        tmem_ld32(lane_base + cb * 32, s);
+        if (narrow) {
+          float s2[32];
+          tmem_ld32(lane_base + 128 + cb * 32, s2);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s[i] += s2[i];
+        }
+      };
+      // ---- S is complete ----------------------------------------------------------------------
+      TC_TIMED(1, mbar_wait(&s_full, tc & 1u));
+      tc_fence_after();
+      TC_MARK(t_p1);
+      // pass 1: row max and row sum of 2^(s - max) over this group's pieces (online), then combined
+      float mx = kNeg, l = 0.f;
+#pragma unroll 1
+      for (int cb = sg; cb < NS2; cb += 2) {
+        float s[32];
+        load_s(cb, s);
+        const uint32_t m = sel8(mw, cb);
+        float cm = kNeg;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          s[i] = ((m >> i) & 1u) ? s[i] : kNeg;
+          cm = fmaxf(cm, s[i]);
+        }
+        if (cm > mx) {
+          l *= fast_exp2(mx - cm);
+          mx = cm;
+        }
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {  // masked entries: 2^(-1e30 - max) = 0 (a row without entries keeps l = 0:
+          a0 += ((m >> i) & 1u) ? fast_exp2(s[i] - mx) : 0.f;          // its mask words are 0)
+          a1 += ((m >> (i + 1)) & 1u) ? fast_exp2(s[i + 1] - mx) : 0.f;
+        }
+        l += a0 + a1;
+      }
+      s_part[sg * kTcM + r] = mx;
+      s_part[(2 + sg) * kTcM + r] = l;
+      soft_bar_all();
+      {
+        const float mo = s_part[(sg ^ 1) * kTcM + r], lo = s_part[(2 + (sg ^ 1)) * kTcM + r];
+        const float mn = fmaxf(mx, mo);
+        l = l * fast_exp2(mx - mn) + lo * fast_exp2(mo - mn);
+        mx = mn;
+      }
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      TC_SINCE(4, t_p1);
+      TC_MARK(t_p2);
+      // pass 2: normalised probabilities -> A images of product 2 and (training) attn_edge.
+      // attn_edge in CSR order: a row's neighbours are its set bitmap bits, ascending.  The 32-row x
+      // 16-column piece a warp holds (thread = row) is transposed through its slice of the staging buffer
+      // so that one store instruction writes the pieces of TWO rows (lanes 0-15 row rr, lanes 16-31 row
+      // rr + 16): contiguous floats instead of 32 different rows.
+      const int hl = lane & 15, hr = lane >> 4;
+      const uint32_t below = (1u << hl) - 1u;
+#pragma unroll 1
+      for (int cb = 0; cb < NS2; ++cb) {
+        const uint32_t m = sel8(mw, cb);
+        if ((cb & 1) != sg) {  // the other group's piece (warp-uniform branch)
+          e_rel += __popc(m);
+          continue;
+        }
+        float s[32];
+        load_s(cb, s);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s[i] = ((m >> i) & 1u) ? fast_exp2(s[i] - mx) * inv : 0.f;
+        const uint32_t st = sc2 + cb, slot = st % kTcSlots, k = st / kTcSlots;
+        TC_TIMED(2, mbar_wait(&empty[slot], (k & 1u) ^ 1u));
+        float4* a_hi = reinterpret_cast<float4*>(smem + (size_t)slot * kTcSlotBytes);
+        float4* a_lo = reinterpret_cast<float4*>(smem + (size_t)slot * kTcSlotBytes + kTcN1_Alo);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float4 hi, lo;
+          split4(make_float4(s[4 * c], s[4 * c + 1], s[4 * c + 2], s[4 * c + 3]), hi, lo);
+          a_hi[c * kTcM + r] = hi;
+          a_lo[c * kTcM + r] = lo;
+        }
+        fence_proxy_async();
+        mbar_arrive(&full_a[slot]);
+        if (train) {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) tp[lane * 17 + i] = s[16 * half + i];
+            __syncwarp();
+            const uint32_t mh = (m >> (16 * half)) & 0xffffu;
+            const uint32_t packed = ((uint32_t)e_rel << 16) | mh;
+#pragma unroll
+            for (int rr = 0; rr < 16; ++rr) {
+              const int src = rr + 16 * hr;
+              const uint32_t v = __shfl_sync(kFull, packed, src);
+              if ((v >> hl) & 1u) p.attn[tile_e0 + (int)(v >> 16) + __popc(v & below)] = tp[src * 17 + hl];
+            }
+            __syncwarp();
+            e_rel += __popc(mh);
+          }
+        }
+      }
+      TC_SINCE(5, t_p2);
+      tc_fence_before();
+      mbar_arrive(&s_free);
+      // ---- O is complete ----------------------------------------------------------------------
+      TC_TIMED(3, mbar_wait(&o_full, tc & 1u));
+      tc_fence_after();
+      TC_MARK(t_ep);
+      float* obase = p.out + (size_t)(t.lb + t.mt * kTcM) * kTcF;
+      const int rows_here = min(kTcM, t.n - t.mt * kTcM);
+#pragma unroll 1
+      for (int cq = sg; cq < kTcF / 32; cq += 2) {
+        float y[32];
+        {
+          float y2[32];
+          tmem_ld32(lane_base + kTcColO + cq * 32, y);
+          tmem_ld32(lane_base + kTcColO + 128 + cq * 32, y2);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) y[i] += y2[i];
+        }
+        if (cq + 2 >= kTcF / 32) {  // this thread's last read of O
+          tc_fence_before();
+          mbar_arrive(&o_free);
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float4* so = reinterpret_cast<float4*>(stg + (size_t)r * kTcStgLd);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            so[i] = make_float4(y[16 * half + 4 * i], y[16 * half + 4 * i + 1], y[16 * half + 4 * i + 2],
+                                y[16 * half + 4 * i + 3]);
+          soft_bar(sg);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {  // a warp stores 8 rows x 64 contiguous bytes
+            const int i = r + u * 128, rr = i >> 2, c4 = i & 3;
+            if (rr < rows_here)
+              *reinterpret_cast<float4*>(obase + (size_t)rr * kTcF + cq * 32 + 16 * half + 4 * c4) =
+                  *reinterpret_cast<const float4*>(stg + (size_t)rr * kTcStgLd + 4 * c4);
+          }
+          soft_bar(sg);
+        }
+      }
+      TC_SINCE(7, t_ep);
+      sc = sc2 + NS2;
+      ++tc;
     }
-  } else if (w == kTcSoftWarps) {
+  } else if (w == kTcMmaWarp) {
     // =============================== MMA issue ====================================================
     if (lane == 0) {
       uint32_t sc = 0, tc = 0, ka = 0;  // ka: bit s = parity of full_a[s]
-      constexpr uint32_t idesc2 = umma_idesc_tf32(kTcM, kTcF);
+      constexpr uint32_t id256 = umma_idesc_tf32(kTcM, 256), id128 = umma_idesc_tf32(kTcM, 128);
       const uint32_t ring = smem_u32(smem);
-      for (int b = blockIdx.x; b < nb; b += gridDim.x) {
-        const int lb = __ldg(pp.b.blk_ptr + b), n = __ldg(pp.b.blk_ptr + b + 1) - lb;
-        if (n <= 0) continue;
-        const int MT = (n + kTcM - 1) / kTcM, NS2 = (n + 31) >> 5;
-        for (int mt = 0; mt < MT; ++mt, ++tc) {
-          mbar_wait(&s_free, (tc & 1u) ^ 1u);  // the softmax threads have read S of the previous tile
-          tc_fence_after();
-          for (int kh = 0; kh < MT; ++kh) {
-            const int keys = min(kTcM, n - kh * kTcM);
-            const uint32_t idesc1 = umma_idesc_tf32(kTcM, (keys + 15) & ~15);
-            const uint32_t d = tmem + kh * kTcM;
-            for (int q = 0; q < kTcF / kTcKS; ++q, ++sc) {
-              const uint32_t slot = sc % kTcSlots, k = sc / kTcSlots;
-              mbar_wait(&full_b[slot], k & 1u);
-              tc_fence_after();
-              const uint32_t base = ring + slot * kTcSlotBytes;
-#pragma unroll
-              for (int ks = 0; ks < kTcKS / 8; ++ks) {
-                const uint32_t off = ks * 2 * kTcLBO;
-                const uint64_t dah = umma_desc_kmajor(base + off, kTcLBO, kTcSBO);
-                const uint64_t dal = umma_desc_kmajor(base + kTcImg + off, kTcLBO, kTcSBO);
-                const uint64_t dbh = umma_desc_kmajor(base + 2 * kTcImg + off, kTcLBO, kTcSBO);
-                const uint64_t dbl = umma_desc_kmajor(base + 3 * kTcImg + off, kTcLBO, kTcSBO);
-                umma_tf32(d, dal, dbh, idesc1, (q | ks) != 0 ? 1u : 0u);
-                umma_tf32(d, dah, dbl, idesc1, 1u);
-                umma_tf32(d, dah, dbh, idesc1, 1u);
-              }
-              umma_commit(&empty[slot]);
-            }
-          }
-          umma_commit(&s_full);
-          mbar_wait(&o_free, (tc & 1u) ^ 1u);  // O of the previous tile has been read
-          tc_fence_after();
-          for (int s = 0; s < NS2; ++s, ++sc) {
+      TcTiles t(p.blk_ptr, p.n_blocks, p.sched_ptr, p.sched_idx);
+      while (t.next()) {
+        TC_TIMED(8, mbar_wait(&s_free, (tc & 1u) ^ 1u));  // the softmax threads have read S of the previous tile
+        tc_fence_after();
+        if (t.MT == 1) {
+          // narrow tile: per K = 8, one N = 256 MMA (Q_hi x [K_hi over K_lo]) and one N = 128 MMA (Q_lo x K_hi)
+          for (int q = 0; q < 4; ++q, ++sc) {
             const uint32_t slot = sc % kTcSlots, k = sc / kTcSlots;
-            mbar_wait(&full_b[slot], k & 1u);
-            mbar_wait(&full_a[slot], (ka >> slot) & 1u);
-            ka ^= 1u << slot;
+            TC_TIMED(9, mbar_wait(&full_b[slot], k & 1u));
             tc_fence_after();
             const uint32_t base = ring + slot * kTcSlotBytes;
 #pragma unroll
-            for (int ks = 0; ks < kTcKS / 8; ++ks) {
-              const uint32_t off = ks * 2 * kTcLBO;
-              const uint64_t dah = umma_desc_kmajor(base + off, kTcLBO, kTcSBO);
-              const uint64_t dal = umma_desc_kmajor(base + kTcImg + off, kTcLBO, kTcSBO);
-              const uint64_t dbh = umma_desc_kmajor(base + 2 * kTcImg + off, kTcLBO, kTcSBO);
-              const uint64_t dbl = umma_desc_kmajor(base + 3 * kTcImg + off, kTcLBO, kTcSBO);
-              umma_tf32(tmem + kTcColO, dal, dbh, idesc2, (s | ks) != 0 ? 1u : 0u);
-              umma_tf32(tmem + kTcColO, dah, dbl, idesc2, 1u);
-              umma_tf32(tmem + kTcColO, dah, dbh, idesc2, 1u);
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t dah = umma_desc_kmajor(base + ks * 2 * kTcLboA, kTcLboA, kTcSBO);
+              const uint64_t dal = umma_desc_kmajor(base + kTcN1_Alo + ks * 2 * kTcLboA, kTcLboA, kTcSBO);
+              const uint64_t db = umma_desc_kmajor(base + kTcN1_B + ks * 2 * kTcLboB, kTcLboB, kTcSBO);
+              umma_tf32(tmem, dah, db, id256, (q | ks) != 0 ? 1u : 0u);
+              umma_tf32(tmem, dal, db, id128, 1u);
             }
             umma_commit(&empty[slot]);
           }
-          umma_commit(&o_full);
+        } else {
+          // wide tile: up to 256 keys in one MMA, 3 MMAs per K = 8, K = 16 per stage
+          const uint32_t idk = umma_idesc_tf32(kTcM, (t.n + 15) & ~15);
+          for (int q = 0; q < 8; ++q, ++sc) {
+            const uint32_t slot = sc % kTcSlots, k = sc / kTcSlots;
+            TC_TIMED(9, mbar_wait(&full_b[slot], k & 1u));
+            tc_fence_after();
+            const uint32_t base = ring + slot * kTcSlotBytes;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint64_t dah = umma_desc_kmajor(base + ks * 2 * kTcLboA, kTcLboA, kTcSBO);
+              const uint64_t dal = umma_desc_kmajor(base + kTcW1_Alo + ks * 2 * kTcLboA, kTcLboA, kTcSBO);
+              const uint64_t dbh = umma_desc_kmajor(base + kTcW1_Bhi + ks * 2 * kTcLboB, kTcLboB, kTcSBO);
+              const uint64_t dbl = umma_desc_kmajor(base + kTcW1_Blo + ks * 2 * kTcLboB, kTcLboB, kTcSBO);
+              umma_tf32(tmem, dal, dbh, idk, (q | ks) != 0 ? 1u : 0u);
+              umma_tf32(tmem, dah, dbl, idk, 1u);
+              umma_tf32(tmem, dah, dbh, idk, 1u);
+            }
+            umma_commit(&empty[slot]);
+          }
         }
+        umma_commit(&s_full);
+        TC_TIMED(10, mbar_wait(&o_free, (tc & 1u) ^ 1u));  // O of the previous tile has been read
+        tc_fence_after();
+        const int NS2 = t.stages2();
+        for (int s = 0; s < NS2; ++s, ++sc) {
+          const uint32_t slot = sc % kTcSlots, k = sc / kTcSlots;
+          TC_TIMED(11, mbar_wait(&full_b[slot], k & 1u));
+          TC_TIMED(12, mbar_wait(&full_a[slot], (ka >> slot) & 1u));
+          ka ^= 1u << slot;
+          tc_fence_after();
+          const uint32_t base = ring + slot * kTcSlotBytes;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t dah = umma_desc_kmajor(base + ks * 2 * kTcLboA, kTcLboA, kTcSBO);
+            const uint64_t dal = umma_desc_kmajor(base + kTcN1_Alo + ks * 2 * kTcLboA, kTcLboA, kTcSBO);
+            const uint64_t db = umma_desc_kmajor(base + kTcN1_B + ks * 2 * kTcLboB, kTcLboB, kTcSBO);
+            umma_tf32(tmem + kTcColO, dah, db, id256, (s | ks) != 0 ? 1u : 0u);
+            umma_tf32(tmem + kTcColO, dal, db, id128, 1u);
+          }
+          umma_commit(&empty[slot]);
+        }
+        umma_commit(&o_full);
+        ++tc;
       }
     }
   } else {
     // =============================== loaders ======================================================
-    const int g = (w - kTcSoftWarps - 1) / kTcGroupWarps;
-    const int lt = tid - (kTcSoftWarps + 1 + g * kTcGroupWarps) * 32;  // thread inside the group
-    float4* const a_hi = slot_img(g, 0);
-    float4* const a_lo = slot_img(g, 1);
-    float4* const b_hi = slot_img(g, 2);
-    float4* const b_lo = slot_img(g, 3);
+    const int g = (w - kTcMmaWarp - 1) / kTcGroupWarps;
+    const int lt = tid - (kTcMmaWarp + 1 + g * kTcGroupWarps) * 32;  // thread inside the group
     uint32_t sc = 0;
-    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
-      const int lb = __ldg(pp.b.blk_ptr + b), n = __ldg(pp.b.blk_ptr + b + 1) - lb;
-      if (n <= 0) continue;
-      const int MT = (n + kTcM - 1) / kTcM, NS2 = (n + 31) >> 5;
-      for (int mt = 0; mt < MT; ++mt) {
-        // ---- product 1: Q slice (A, scaled into the base-2 exponent domain) and K slice (B) ----
-        for (int kh = 0; kh < MT; ++kh) {
-          const int rows_a = min(kTcM, n - mt * kTcM), rows_b = min(kTcM, n - kh * kTcM);
-          for (int q = 0; q < kTcF / kTcKS; ++q, ++sc) {
-            if ((int)(sc % kTcSlots) != g) continue;
-            const float4* qsrc = reinterpret_cast<const float4*>(p.Q + (size_t)(lb + mt * kTcM) * kTcF + q * kTcKS);
-            const float4* ksrc = reinterpret_cast<const float4*>(p.K + (size_t)(lb + kh * kTcM) * kTcF + q * kTcKS);
-            float4 xa[8], xb[8];
-            // float4 i covers row (i & 7) + 8 * (i >> 6), chunk (i >> 3) & 7: a warp reads 8 rows x 64
-            // contiguous bytes and writes 4 x 128 contiguous bytes of the chunk-major images
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int i = lt + u * kTcGroupThreads, rr = (i & 7) + 8 * (i >> 6), c = (i >> 3) & 7;
-              xa[u] = rr < rows_a ? __ldg(qsrc + (size_t)rr * (kTcF / 4) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-              xb[u] = rr < rows_b ? __ldg(ksrc + (size_t)rr * (kTcF / 4) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            mbar_wait(&empty[g], ((sc / kTcSlots) & 1u) ^ 1u);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int i = lt + u * kTcGroupThreads, rr = (i & 7) + 8 * (i >> 6), c = (i >> 3) & 7;
-              float4 hi, lo;
-              split4(make_float4(xa[u].x * kLog2e, xa[u].y * kLog2e, xa[u].z * kLog2e, xa[u].w * kLog2e), hi, lo);
-              a_hi[c * kTcM + rr] = hi;
-              a_lo[c * kTcM + rr] = lo;
-              split4(xb[u], hi, lo);
-              b_hi[c * kTcM + rr] = hi;
-              b_lo[c * kTcM + rr] = lo;
-            }
-            fence_proxy_async();
-            mbar_arrive(&full_b[g]);
-          }
-        }
-        // ---- product 2: V transposed (B: row = feature lt, k = key) -------------------------------
-        for (int s = 0; s < NS2; ++s, ++sc) {
-          if ((int)(sc % kTcSlots) != g) continue;
-          const float* vsrc = p.V + (size_t)(lb + s * kTcKS) * kTcF + lt;
-          const int keys = n - s * kTcKS;  // valid keys of this slice (>= 1)
-          float4 xv[8];
+    TcTiles t(p.blk_ptr, p.n_blocks, p.sched_ptr, p.sched_idx);
+    while (t.next()) {
+      const int rows_a = min(kTcM, t.n - t.mt * kTcM);
+      const float* qrow = p.Q + (size_t)(t.lb + t.mt * kTcM) * kTcF;
+      const float* krow = p.K + (size_t)t.lb * kTcF;
+      if (t.MT == 1) {
+        // ---- narrow product 1, K = 32: Q slice (A, scaled into the base-2 exponent domain), K slice (B) ----
+        for (int q = 0; q < 4; ++q, ++sc) {
+          if ((int)(sc % kTcLoadGroups) != g) continue;
+          unsigned char* slot = smem + (size_t)(sc % kTcSlots) * kTcSlotBytes;
+          float4* const a_hi = reinterpret_cast<float4*>(slot);
+          float4* const a_lo = reinterpret_cast<float4*>(slot + kTcN1_Alo);
+          float4* const bst = reinterpret_cast<float4*>(slot + kTcN1_B);
+          const float4* qsrc = reinterpret_cast<const float4*>(qrow + q * 32);
+          const float4* ksrc = reinterpret_cast<const float4*>(krow + q * 32);
+          TC_MARK(t_ld1);
+          float4 xa[8], xb[8];
+          // float4 i covers row (i & 7) + 8 * (i >> 6), chunk (i >> 3) & 7: a warp reads 8 rows x 64
+          // contiguous bytes and writes 4 x 128 contiguous bytes of the chunk-major images
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            xv[u].x = 4 * u + 0 < keys ? __ldg(vsrc + (size_t)(4 * u + 0) * kTcF) : 0.f;
-            xv[u].y = 4 * u + 1 < keys ? __ldg(vsrc + (size_t)(4 * u + 1) * kTcF) : 0.f;
-            xv[u].z = 4 * u + 2 < keys ? __ldg(vsrc + (size_t)(4 * u + 2) * kTcF) : 0.f;
-            xv[u].w = 4 * u + 3 < keys ? __ldg(vsrc + (size_t)(4 * u + 3) * kTcF) : 0.f;
+            const int i = lt + u * kTcGroupThreads, rr = (i & 7) + 8 * (i >> 6), c = (i >> 3) & 7;
+            xa[u] = rr < rows_a ? __ldg(qsrc + (size_t)rr * (kTcF / 4) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            xb[u] = rr < t.n ? __ldg(ksrc + (size_t)rr * (kTcF / 4) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          mbar_wait(&empty[g], ((sc / kTcSlots) & 1u) ^ 1u);
+          TC_TIMED(16, mbar_wait(&empty[sc % kTcSlots], ((sc / kTcSlots) & 1u) ^ 1u));
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
+            const int i = lt + u * kTcGroupThreads, rr = (i & 7) + 8 * (i >> 6), c = (i >> 3) & 7;
             float4 hi, lo;
-            split4(xv[u], hi, lo);
-            b_hi[u * kTcM + lt] = hi;
-            b_lo[u * kTcM + lt] = lo;
+            split4(make_float4(xa[u].x * kLog2e, xa[u].y * kLog2e, xa[u].z * kLog2e, xa[u].w * kLog2e), hi, lo);
+            a_hi[c * 128 + rr] = hi;
+            a_lo[c * 128 + rr] = lo;
+            split4(xb[u], hi, lo);
+            bst[c * 256 + rr] = hi;
+            bst[c * 256 + 128 + rr] = lo;
           }
           fence_proxy_async();
-          mbar_arrive(&full_b[g]);
+          mbar_arrive(&full_b[sc % kTcSlots]);
+          TC_SINCE(18, t_ld1);
         }
+      } else {
+        // ---- wide product 1, K = 16: Q slice (128 rows), K slice (256 rows) ----------------------------
+        for (int q = 0; q < 8; ++q, ++sc) {
+          if ((int)(sc % kTcLoadGroups) != g) continue;
+          unsigned char* slot = smem + (size_t)(sc % kTcSlots) * kTcSlotBytes;
+          float4* const a_hi = reinterpret_cast<float4*>(slot);
+          float4* const a_lo = reinterpret_cast<float4*>(slot + kTcW1_Alo);
+          float4* const b_hi = reinterpret_cast<float4*>(slot + kTcW1_Bhi);
+          float4* const b_lo = reinterpret_cast<float4*>(slot + kTcW1_Blo);
+          const float4* qsrc = reinterpret_cast<const float4*>(qrow + q * 16);
+          const float4* ksrc = reinterpret_cast<const float4*>(krow + q * 16);
+          float4 xa[4], xb[8];
+          // float4 i covers row (i & 7) + 8 * (i >> 5), chunk (i >> 3) & 3
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int i = lt + u * kTcGroupThreads, rr = (i & 7) + 8 * (i >> 5), c = (i >> 3) & 3;
+            if (u < 4) xa[u] = rr < rows_a ? __ldg(qsrc + (size_t)rr * (kTcF / 4) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            xb[u] = rr < t.n ? __ldg(ksrc + (size_t)rr * (kTcF / 4) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          TC_TIMED(16, mbar_wait(&empty[sc % kTcSlots], ((sc / kTcSlots) & 1u) ^ 1u));
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int i = lt + u * kTcGroupThreads, rr = (i & 7) + 8 * (i >> 5), c = (i >> 3) & 3;
+            float4 hi, lo;
+            if (u < 4) {
+              split4(make_float4(xa[u].x * kLog2e, xa[u].y * kLog2e, xa[u].z * kLog2e, xa[u].w * kLog2e), hi, lo);
+              a_hi[c * 128 + rr] = hi;
+              a_lo[c * 128 + rr] = lo;
+            }
+            split4(xb[u], hi, lo);
+            b_hi[c * 256 + rr] = hi;
+            b_lo[c * 256 + rr] = lo;
+          }
+          fence_proxy_async();
+          mbar_arrive(&full_b[sc % kTcSlots]);
+        }
+      }
+      // ---- product 2: V transposed (B: row = feature lt, k = key), hi rows 0-127 over lo rows 128-255 ----
+      const int NS2 = t.stages2();
+      for (int s = 0; s < NS2; ++s, ++sc) {
+        if ((int)(sc % kTcLoadGroups) != g) continue;
+        unsigned char* slot = smem + (size_t)(sc % kTcSlots) * kTcSlotBytes;
+        float4* const bst = reinterpret_cast<float4*>(slot + kTcN1_B);
+        const float* vsrc = p.V + (size_t)(t.lb + s * 32) * kTcF + lt;
+        const int keys = t.n - s * 32;  // valid keys of this slice (>= 1)
+        TC_MARK(t_ld2);
+        float4 xv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          xv[u].x = 4 * u + 0 < keys ? __ldg(vsrc + (size_t)(4 * u + 0) * kTcF) : 0.f;
+          xv[u].y = 4 * u + 1 < keys ? __ldg(vsrc + (size_t)(4 * u + 1) * kTcF) : 0.f;
+          xv[u].z = 4 * u + 2 < keys ? __ldg(vsrc + (size_t)(4 * u + 2) * kTcF) : 0.f;
+          xv[u].w = 4 * u + 3 < keys ? __ldg(vsrc + (size_t)(4 * u + 3) * kTcF) : 0.f;
+        }
+        TC_TIMED(17, mbar_wait(&empty[sc % kTcSlots], ((sc / kTcSlots) & 1u) ^ 1u));
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          float4 hi, lo;
+          split4(xv[u], hi, lo);
+          bst[u * 256 + lt] = hi;
+          bst[u * 256 + 128 + lt] = lo;
+        }
+        fence_proxy_async();
+        mbar_arrive(&full_b[sc % kTcSlots]);
+        TC_SINCE(19, t_ld2);
       }
     }
   }
+#ifdef DFGNN_TC_PROF
+  if (TC_ON()) g_tc_prof[threadIdx.x == 288 ? 27 : 24 + (threadIdx.x >> 7)] += (unsigned long long)(clock64() - t_kernel);
+#endif
   // ---- teardown ------------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
   if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+}
+
+// adjacency bitmap of a block-diagonal batch: bit j of row r's 256 bits = (r, first node of r's graph + j)
+// is an edge.  One CTA per graph, a warp per row.
+static __global__ void block_adj_bits_kernel(int n_blocks, const int* __restrict__ blk_ptr, const int* __restrict__ row_ptr,
+                                             const int* __restrict__ col_ind, uint32_t* __restrict__ bits) {
+  const int b = blockIdx.x, lb = blk_ptr[b], n = blk_ptr[b + 1] - lb;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int r = w; r < n; r += nw) {
+    const int e0 = row_ptr[lb + r], e1 = row_ptr[lb + r + 1];
+    uint32_t mine = 0u;  // lane k < 8 ends up with word k
+    for (int e = e0 + lane; __any_sync(kFull, e < e1); e += 32) {
+      const int j = e < e1 ? col_ind[e] - lb : -1;
+#pragma unroll
+      for (int k = 0; k < kTcMaskW; ++k) {
+        const uint32_t word = __reduce_or_sync(kFull, (j >= 0 && (j >> 5) == k) ? (1u << (j & 31)) : 0u);
+        if (lane == k) mine |= word;
+      }
+    }
+    if (lane < kTcMaskW) bits[(size_t)(lb + r) * kTcMaskW + lane] = mine;
+  }
 }
 
 static bool dense_tc_supported(int max_nodes, int h, int f) {
@@ -400,14 +597,29 @@ extern "C" {
 
 int dfgnn_gt_dense_tc_supported(int max_nodes, int h, int f) { return dense_tc_supported(max_nodes, h, f) ? 1 : 0; }
 
+int dfgnn_block_adj_bits(int n_blocks, int max_nodes, int m, int nnz, const int32_t* blk_ptr, const int32_t* row_ptr,
+                         const int32_t* col_ind, uint32_t* adj_bits, void* stream) {
+  const char* fn = "dfgnn_block_adj_bits";
+  if (n_blocks < 1 || m < 0 || nnz < 0 || max_nodes < 1 || max_nodes > kTcMaxNodes) {
+    set_error("%s: needs a block plan with graphs of at most %d nodes (n_blocks=%d, max_nodes=%d)", fn, kTcMaxNodes,
+              n_blocks, max_nodes);
+    return DFGNN_ERR_INVALID_ARGUMENT;
+  }
+  if (m == 0) return DFGNN_OK;
+  DFGNN_REQUIRE(blk_ptr, fn); DFGNN_REQUIRE(row_ptr, fn); DFGNN_REQUIRE(adj_bits, fn);
+  if (nnz > 0) DFGNN_REQUIRE(col_ind, fn);
+  block_adj_bits_kernel<<<n_blocks, 256, 0, (cudaStream_t)stream>>>(n_blocks, blk_ptr, row_ptr, col_ind, adj_bits);
+  return check_launch(fn);
+}
+
 int dfgnn_gt_dense_tc_forward(int n_blocks, const int32_t* blk_ptr, int max_nodes, int m, int nnz, int h, int f,
-                              const int32_t* row_ptr, const int32_t* col_ind, const float* Q, const float* K,
-                              const float* V, float* out_feat, float* attn_edge, void* stream) {
+                              const int32_t* row_ptr, const uint32_t* adj_bits, int n_ctas, const int32_t* sched_ptr,
+                              const int32_t* sched_idx, const float* Q, const float* K, const float* V, float* out_feat,
+                              float* attn_edge, void* stream) {
   const char* fn = "dfgnn_gt_dense_tc_forward";
   if (int rc = check_common(fn, m, nnz, h, f)) return rc;
   if (m == 0) return DFGNN_OK;
-  DFGNN_REQUIRE(blk_ptr, fn); DFGNN_REQUIRE(row_ptr, fn);
-  if (nnz > 0) DFGNN_REQUIRE(col_ind, fn);
+  DFGNN_REQUIRE(blk_ptr, fn); DFGNN_REQUIRE(row_ptr, fn); DFGNN_REQUIRE(adj_bits, fn);
   DFGNN_REQUIRE(Q, fn); DFGNN_REQUIRE(K, fn); DFGNN_REQUIRE(V, fn); DFGNN_REQUIRE(out_feat, fn);
   if (n_blocks < 1 || !dense_tc_supported(max_nodes, h, f)) {
     set_error("%s: needs h == 1, f == %d and graphs of at most %d nodes (h=%d, f=%d, max_nodes=%d)", fn, kTcF,
@@ -415,14 +627,27 @@ int dfgnn_gt_dense_tc_forward(int n_blocks, const int32_t* blk_ptr, int max_node
     return DFGNN_ERR_UNSUPPORTED_DIM;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  GtBlockFwdParams p{{m, nnz, h, f, 0, row_ptr, col_ind, nullptr, Q, K, V, nullptr, out_feat, nnz > 0 ? attn_edge : nullptr},
-                     {blk_ptr, n_blocks, max_nodes}};
+  const bool sched = sched_ptr != nullptr && sched_idx != nullptr && n_ctas >= 1;
+  GtTcFwdParams p{n_blocks, blk_ptr, row_ptr, sched ? sched_ptr : nullptr, sched ? sched_idx : nullptr, adj_bits,
+                  Q, K, V, out_feat, nnz > 0 ? attn_edge : nullptr};
   auto kernel = gt_dense_tc_fwd_kernel;
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
-  const int grid = n_blocks < sm_count() ? n_blocks : sm_count();
+  const int grid = sched ? n_ctas : (n_blocks < sm_count() ? n_blocks : sm_count());
   kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(p);
   note_kernel(0, "gt_dense_tc_fwd_kernel");
   return check_launch(fn);
 }
+
+#ifdef DFGNN_TC_PROF
+__attribute__((visibility("default"))) int dfgnn_tc_prof_read(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_tc_prof, sizeof(g_tc_prof));
+  if (reset) {
+    unsigned long long z[32] = {0};
+    cudaMemcpyToSymbol(g_tc_prof, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 
 }  // extern "C"

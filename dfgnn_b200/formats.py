@@ -127,6 +127,8 @@ class BlockPlan:
         self.max_nodes = int(max_nodes)
         self.sum_sq_nodes = int(sum_sq_nodes)   # sum over graphs of nodes^2 = entries of the dense blocks
         self.ascending = bool(ascending)        # column ids strictly ascending inside every row
+        self.adj_bits = None                    # [m, 8] int32 adjacency bitmap (dense tcgen05 kernels)
+        self.n_ctas, self.sched_ptr, self.sched_idx = 0, None, None  # balanced graph lists of the persistent CTAs
         self._ok = {}
 
     def algorithm(self, m: int, nnz: int, h: int, f: int, unweighted: bool, training: bool = False) -> int:
@@ -142,7 +144,8 @@ class BlockPlan:
             algo = 0
             fill = nnz / self.sum_sq_nodes if self.sum_sq_nodes > 0 else 0.0
             dense_ok = unweighted and self.ascending and nnz > 0
-            if dense_ok and mode in (0, 4) and L.dfgnn_gt_dense_tc_supported(self.max_nodes, h, f):
+            if (dense_ok and self.adj_bits is not None and mode in (0, 4)
+                    and L.dfgnn_gt_dense_tc_supported(self.max_nodes, h, f)):
                 if mode == 4 or fill >= self.DENSE_MIN_FILL:
                     algo = 3
             if algo == 0 and dense_ok and L.dfgnn_gt_dense_supported(self.max_nodes, h, f):
@@ -183,7 +186,42 @@ def block_plan(batch_num_nodes: torch.Tensor, row_ptr: torch.Tensor, col_ind: to
             col_ind.data_ptr() if col_ind.numel() else None, flag.data_ptr(), ctypes.addressof(mx),
             ctypes.addressof(asc), torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(rc, "block_plan")
-    return BlockPlan(blk, bnn.numel(), mx.value, int((bnn * bnn).sum()), bool(asc.value))
+    plan = BlockPlan(blk, bnn.numel(), mx.value, int((bnn * bnn).sum()), bool(asc.value))
+    if plan.ascending and col_ind.numel() and mx.value <= 256:
+        # adjacency bitmap for the dense tcgen05 kernels (32 bytes per row), built once per batch
+        with torch.cuda.device(dev):
+            bits = torch.empty((m, 8), dtype=torch.int32, device=dev)
+            rc = _lib.lib().dfgnn_block_adj_bits(
+                plan.n_blocks, plan.max_nodes, m, col_ind.numel(), blk.data_ptr(), row_ptr.data_ptr(),
+                col_ind.data_ptr(), bits.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "block_adj_bits")
+        plan.adj_bits = bits
+        plan.n_ctas, plan.sched_ptr, plan.sched_idx = _balanced_schedule(bnn, dev)
+    return plan
+
+
+def _balanced_schedule(bnn: torch.Tensor, dev):
+    """Graph lists for the persistent CTAs of the dense tcgen05 kernels (one CTA per SM): longest
+    processing time first over a cost model of the MMA work (a graph of more than 128 nodes is two
+    row tiles over up to 256 keys).  Dealing 1024 PATTERN-shaped graphs round robin leaves the busiest
+    SM with 1.65x the mean work; this schedule 1.05x."""
+    import heapq
+    import numpy as np
+    n = bnn.numpy().astype(np.int64)
+    slices = (n + 31) // 32
+    cost = np.where(n <= 128, 16 * 246 + slices * 4 * 246, 2 * (16 * 384 + slices * 4 * 246)).astype(np.int64)
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    g = int(min(len(n), sms))
+    heap = [(0, c) for c in range(g)]
+    lists = [[] for _ in range(g)]
+    for b in np.argsort(-cost, kind="stable"):
+        load, c = heapq.heappop(heap)
+        lists[c].append(int(b))
+        heapq.heappush(heap, (load + int(cost[b]), c))
+    ptr = np.zeros(g + 1, dtype=np.int32)
+    ptr[1:] = np.cumsum([len(x) for x in lists])
+    idx = np.fromiter((b for x in lists for b in x), dtype=np.int32, count=len(n))
+    return g, torch.from_numpy(ptr).to(dev), torch.from_numpy(idx).to(dev)
 
 
 def attach_block_plan(g, row_ptr: torch.Tensor, col_ind: torch.Tensor):

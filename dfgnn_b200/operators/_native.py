@@ -95,7 +95,8 @@ def _block_forward(plan, algo, m, nnz, h, f, row_ptr, col_ind, val, Q, K, V, out
     L = _lib.lib()
     if algo == 3:
         return L.dfgnn_gt_dense_tc_forward(plan.n_blocks, _ptr(plan.blk_ptr), plan.max_nodes, m, nnz, h, f,
-                                           _ptr(row_ptr), _ptr(col_ind), _ptr(Q), _ptr(K), _ptr(V), _ptr(out),
+                                           _ptr(row_ptr), _ptr(plan.adj_bits), plan.n_ctas, _ptr(plan.sched_ptr),
+                                           _ptr(plan.sched_idx), _ptr(Q), _ptr(K), _ptr(V), _ptr(out),
                                            _ptr(attn), _stream(Q))
     if algo == 2:
         return L.dfgnn_gt_dense_forward(plan.n_blocks, _ptr(plan.blk_ptr), plan.max_nodes, m, nnz, h, f,

@@ -206,10 +206,21 @@ int dfgnn_gt_dense_forward(int n_blocks, const int32_t *blk_ptr, int max_nodes, 
  * straight from tensor memory.  h == 1, f == 128, graphs of at most 256 nodes, unweighted scores,
  * strictly ascending column ids per row (dfgnn_block_plan_check).  Same outputs as
  * dfgnn_gt_hyper_forward (attn_edge may be NULL: inference).
+ *
+ * The adjacency is passed as a bitmap, a format built once per batch (like the CSC of
+ * preprocess_Hyper_fw_bw, DFGNN/layers/util.py:116-142): adj_bits [m][8] uint32, bit j of row r =
+ * (r, first node of r's graph + j) is an edge.  dfgnn_block_adj_bits builds it from the CSR.
+ * The kernel is persistent (one CTA per SM walks several graphs); sched_ptr [n_ctas + 1] / sched_idx
+ * [n_blocks] optionally give every CTA its own list of graphs (balanced by the caller from the graph
+ * sizes, which it knows from batch_num_nodes); NULL = graphs dealt round robin over the SMs.
  */
 int dfgnn_gt_dense_tc_supported(int max_nodes, int h, int f);
+int dfgnn_block_adj_bits(int n_blocks, int max_nodes, int m, int nnz, const int32_t *blk_ptr,
+                         const int32_t *row_ptr, const int32_t *col_ind, uint32_t *adj_bits,
+                         void *stream);
 int dfgnn_gt_dense_tc_forward(int n_blocks, const int32_t *blk_ptr, int max_nodes, int m, int nnz,
-                              int h, int f, const int32_t *row_ptr, const int32_t *col_ind,
+                              int h, int f, const int32_t *row_ptr, const uint32_t *adj_bits,
+                              int n_ctas, const int32_t *sched_ptr, const int32_t *sched_idx,
                               const float *Q, const float *K, const float *V, float *out_feat,
                               float *attn_edge, void *stream);
 /* = dfgnn_gt_backward_phase on a square block-diagonal adjacency (n == m). */
