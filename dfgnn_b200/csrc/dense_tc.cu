@@ -77,6 +77,8 @@ constexpr size_t kTcSmemBytes = kTcOffPart + (size_t)4 * kTcM * 4;             /
 __device__ __forceinline__ void soft_bar(int group) { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); }
 __device__ __forceinline__ void soft_bar_all() { asm volatile("bar.sync 3, 256;" ::: "memory"); }
 
+__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
 __device__ __forceinline__ uint32_t sel8(const uint32_t (&a)[8], int i) {  // a[i] without local memory
   uint32_t v = a[0];
 #pragma unroll
@@ -575,6 +577,280 @@ static __global__ void block_adj_bits_kernel(int n_blocks, const int* __restrict
   }
 }
 
+// ======================================================================================================
+// Backward, column side: dV_j = sum_i p_ij dO_i, dK_j = sum_i dS_ij Q_i from the row side's packed scratch
+// {dS_e, p_e} (CSR order; gt_bwd_row_kernel or the dense row-side kernel writes it).  Reference counterpart:
+// the SpMM-over-CSC half of fused_gtconv_backward (DFGNN/src/fused_gtconv/fused_gtconv.cu, gt_backward).
+//
+// Work item = (graph, 128-key tile kt): dV[keys x 128] = P^T dO and dK = dS^T Q, contraction over the rows of
+// the graph in 16-row slices (one ring stage each).  M = keys, so the A operands are the TRANSPOSED tiles
+// P^T / dS^T: element (key j, row i) at chunk i / 4, image row j, word i % 4 -- written straight from the
+// CSR scratch through the adjacency bitmap (a warp covers 8 keys x 4 rows = 128 contiguous bytes of an image,
+// every element of the image is written, zeros where there is no edge).  B operands: dO^T / Q^T slices
+// (rows = features), hi over lo stacked along N like in the forward.
+//   warps 0-7   workers: per item a table of the tile's bitmap words and CSR positions per row, then per
+//               stage 8 scratch loads per thread -> hi / lo -> the four A images; after the item's last stage
+//               the epilogue (group 0: dV, group 1: dK; two column halves summed, staged, coalesced stores)
+//   warp  8     MMA issue: per K = 8 and product one N = 256 MMA (A_hi x [B_hi over B_lo]) + one N = 128 MMA
+//               (A_lo x B_hi); dV in tensor-memory columns [0, 256), dK in [256, 512)
+//   warps 9-12  loaders of the B images (thread = feature, coalesced scalar loads of 16 rows)
+constexpr int kBcWorkWarps = 8, kBcLoadWarps = 4;
+constexpr int kBcThreads = (kBcWorkWarps + 1 + kBcLoadWarps) * 32;  // 416
+constexpr int kBcA = 8 * 1024;                       // one A image: 4 chunks x 128 rows x 16 B
+constexpr int kBcOffB0 = 4 * kBcA, kBcOffB1 = 4 * kBcA + 16 * 1024;  // dO^T / Q^T images (256 rows, hi over lo)
+constexpr size_t kBcOffTab = (size_t)kTcSlots * kTcSlotBytes;          // [256 rows][uint4 words | int4 positions]
+constexpr size_t kBcOffStage = kBcOffTab + (size_t)kTcMaxNodes * 32;
+constexpr size_t kBcSmemBytes = kBcOffStage + (size_t)2 * kTcM * kTcStgLd * 4;
+
+struct TcItems {  // (graph, key tile) items of this CTA; item id = 2 * graph + kt
+  const int *blk, *sidx;
+  int i, i_end, step, lb, n, kt;
+  __device__ TcItems(const int* blk_, int nb, const int* sched_ptr, const int* sched_idx) : blk(blk_), sidx(sched_idx), lb(0), n(0), kt(0) {
+    if (sched_ptr) {
+      i = __ldg(sched_ptr + blockIdx.x) - 1;
+      i_end = __ldg(sched_ptr + blockIdx.x + 1);
+      step = 1;
+    } else {
+      i = (int)blockIdx.x - (int)gridDim.x;
+      i_end = 2 * nb;
+      step = gridDim.x;
+    }
+  }
+  __device__ bool next() {
+    for (i += step; i < i_end; i += step) {
+      const int item = sidx ? __ldg(sidx + i) : i;
+      const int b = item >> 1;
+      kt = item & 1;
+      lb = __ldg(blk + b);
+      n = __ldg(blk + b + 1) - lb;
+      if (n > kt * kTcM) return true;
+    }
+    return false;
+  }
+  __device__ int stages() const { return (n + 15) >> 4; }
+};
+
+struct GtTcBwdColParams {
+  int n_blocks;
+  const int *blk_ptr, *row_ptr, *sched_ptr, *sched_idx;
+  const uint32_t* adj_bits;
+  const float2* scratch;  // [nnz] {dS_e, p_e}
+  const float *dO, *Q;
+  float *dK, *dV;
+};
+
+__global__ void __launch_bounds__(kBcThreads, 1) gt_dense_tc_bwd_col_kernel(const GtTcBwdColParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t full_a[kTcSlots], full_b[kTcSlots], empty[kTcSlots], acc_full, acc_free;
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) {
+    for (int i = 0; i < kTcSlots; ++i) {
+      mbar_init(&full_a[i], kBcWorkWarps * 32);
+      mbar_init(&full_b[i], kBcLoadWarps * 32);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(&acc_full, 1);
+    mbar_init(&acc_free, kBcWorkWarps * 32);
+    mbar_fence_init();
+  }
+  if (w == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+
+  if (w < kBcWorkWarps) {
+    // =============================== workers: A images, then the epilogue =========================
+    uint4* s_tabw = reinterpret_cast<uint4*>(smem + kBcOffTab);           // bitmap words of the key tile, per row
+    int4* s_tabc = reinterpret_cast<int4*>(smem + kBcOffTab) + kTcMaxNodes;  // CSR position of the first edge of each word
+    const int eg = w >> 2;                                                 // epilogue group: 0 dV, 1 dK
+    float* stg = reinterpret_cast<float*>(smem + kBcOffStage) + (size_t)eg * kTcM * kTcStgLd;
+    const uint32_t lane_base = tmem + ((uint32_t)((w & 3) * 32) << 16) + eg * 256;
+    const int i_loc = 4 * (w & 3) + (lane & 3);  // this thread's row inside a 16-row slice
+    const int j0 = 8 * (w >> 2) + (lane >> 2);   // its key in iteration u: j0 + 16 u
+    uint32_t sc = 0, tc = 0;
+    TcItems t(p.blk_ptr, p.n_blocks, p.sched_ptr, p.sched_idx);
+    while (t.next()) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // the previous item's stages have read the tables
+      {
+        const int row = tid;  // one table row per thread
+        uint4 ww = make_uint4(0u, 0u, 0u, 0u);
+        int4 cc = make_int4(0, 0, 0, 0);
+        if (row < t.n) {
+          const uint4* src = reinterpret_cast<const uint4*>(p.adj_bits + (size_t)(t.lb + row) * kTcMaskW);
+          int e = __ldg(p.row_ptr + t.lb + row);
+          if (t.kt) {
+            const uint4 lo = __ldg(src);
+            e += __popc(lo.x) + __popc(lo.y) + __popc(lo.z) + __popc(lo.w);
+          }
+          ww = __ldg(src + t.kt);
+          cc.x = e;
+          cc.y = cc.x + __popc(ww.x);
+          cc.z = cc.y + __popc(ww.y);
+          cc.w = cc.z + __popc(ww.z);
+        }
+        s_tabw[row] = ww;
+        s_tabc[row] = cc;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int NS = t.stages();
+      for (int s = 0; s < NS; ++s, ++sc) {
+        const uint32_t slot = sc % kTcSlots;
+        const uint4 ww = s_tabw[16 * s + i_loc];
+        const int4 cc = s_tabc[16 * s + i_loc];
+        float2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = j0 + 16 * u, bit = j & 31;
+          const uint32_t word = (u >> 1) == 0 ? ww.x : (u >> 1) == 1 ? ww.y : (u >> 1) == 2 ? ww.z : ww.w;
+          const int cbase = (u >> 1) == 0 ? cc.x : (u >> 1) == 1 ? cc.y : (u >> 1) == 2 ? cc.z : cc.w;
+          v[u] = make_float2(0.f, 0.f);
+          if ((word >> bit) & 1u) v[u] = __ldg(p.scratch + cbase + __popc(word & ((1u << bit) - 1u)));
+        }
+        mbar_wait(&empty[slot], ((sc / kTcSlots) & 1u) ^ 1u);
+        float* img = reinterpret_cast<float*>(smem + (size_t)slot * kTcSlotBytes);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = j0 + 16 * u;
+          const int at = ((w & 3) * kTcM + j) * 4 + (lane & 3);  // chunk (w & 3), image row j, word i % 4
+          const float ph = trunc_tf32(v[u].y), dh = trunc_tf32(v[u].x);
+          img[at] = ph;
+          img[kBcA / 4 + at] = v[u].y - ph;
+          img[2 * kBcA / 4 + at] = dh;
+          img[3 * kBcA / 4 + at] = v[u].x - dh;
+        }
+        fence_proxy_async();
+        mbar_arrive(&full_a[slot]);
+      }
+      // ---- epilogue: the accumulators of this item ----------------------------------------------
+      mbar_wait(&acc_full, tc & 1u);
+      tc_fence_after();
+      float* obase = (eg == 0 ? p.dV : p.dK) + (size_t)(t.lb + t.kt * kTcM) * kTcF;
+      const int rows_here = min(kTcM, t.n - t.kt * kTcM), r = tid & 127;
+#pragma unroll 1
+      for (int cq = 0; cq < kTcF / 32; ++cq) {
+        float y[32];
+        {
+          float y2[32];
+          tmem_ld32(lane_base + cq * 32, y);
+          tmem_ld32(lane_base + 128 + cq * 32, y2);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) y[i] += y2[i];
+        }
+        if (cq == kTcF / 32 - 1) {
+          tc_fence_before();
+          mbar_arrive(&acc_free);
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float4* so = reinterpret_cast<float4*>(stg + (size_t)r * kTcStgLd);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            so[i] = make_float4(y[16 * half + 4 * i], y[16 * half + 4 * i + 1], y[16 * half + 4 * i + 2],
+                                y[16 * half + 4 * i + 3]);
+          soft_bar(eg + 3);  // barrier ids 4 and 5: the 128 threads of this epilogue group
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = r + u * 128, rr = i >> 2, c4 = i & 3;
+            if (rr < rows_here)
+              *reinterpret_cast<float4*>(obase + (size_t)rr * kTcF + cq * 32 + 16 * half + 4 * c4) =
+                  *reinterpret_cast<const float4*>(stg + (size_t)rr * kTcStgLd + 4 * c4);
+          }
+          soft_bar(eg + 3);
+        }
+      }
+      ++tc;
+    }
+  } else if (w == kBcWorkWarps) {
+    // =============================== MMA issue ====================================================
+    if (lane == 0) {
+      uint32_t sc = 0, tc = 0;
+      constexpr uint32_t id256 = umma_idesc_tf32(kTcM, 256), id128 = umma_idesc_tf32(kTcM, 128);
+      const uint32_t ring = smem_u32(smem);
+      TcItems t(p.blk_ptr, p.n_blocks, p.sched_ptr, p.sched_idx);
+      while (t.next()) {
+        mbar_wait(&acc_free, (tc & 1u) ^ 1u);
+        tc_fence_after();
+        const int NS = t.stages();
+        for (int s = 0; s < NS; ++s, ++sc) {
+          const uint32_t slot = sc % kTcSlots, k = sc / kTcSlots;
+          mbar_wait(&full_b[slot], k & 1u);
+          mbar_wait(&full_a[slot], k & 1u);
+          tc_fence_after();
+          const uint32_t base = ring + slot * kTcSlotBytes;
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint32_t ao = ks * 2 * kTcLboA, bo = ks * 2 * kTcLboB;
+            const uint64_t dph = umma_desc_kmajor(base + ao, kTcLboA, kTcSBO);
+            const uint64_t dpl = umma_desc_kmajor(base + kBcA + ao, kTcLboA, kTcSBO);
+            const uint64_t dsh = umma_desc_kmajor(base + 2 * kBcA + ao, kTcLboA, kTcSBO);
+            const uint64_t dsl = umma_desc_kmajor(base + 3 * kBcA + ao, kTcLboA, kTcSBO);
+            const uint64_t db0 = umma_desc_kmajor(base + kBcOffB0 + bo, kTcLboB, kTcSBO);
+            const uint64_t db1 = umma_desc_kmajor(base + kBcOffB1 + bo, kTcLboB, kTcSBO);
+            const uint32_t acc = (s | ks) != 0 ? 1u : 0u;
+            umma_tf32(tmem, dph, db0, id256, acc);        // dV += P^T_hi [dO_hi | dO_lo]
+            umma_tf32(tmem, dpl, db0, id128, 1u);         // dV += P^T_lo dO_hi
+            umma_tf32(tmem + 256, dsh, db1, id256, acc);  // dK += dS^T_hi [Q_hi | Q_lo]
+            umma_tf32(tmem + 256, dsl, db1, id128, 1u);   // dK += dS^T_lo Q_hi
+          }
+          umma_commit(&empty[slot]);
+        }
+        umma_commit(&acc_full);
+        ++tc;
+      }
+    }
+  } else {
+    // =============================== loaders: dO^T and Q^T slices ==================================
+    const int lf = tid - (kBcWorkWarps + 1) * 32;  // feature
+    uint32_t sc = 0;
+    TcItems t(p.blk_ptr, p.n_blocks, p.sched_ptr, p.sched_idx);
+    while (t.next()) {
+      const int NS = t.stages();
+      for (int s = 0; s < NS; ++s, ++sc) {
+        const uint32_t slot = sc % kTcSlots;
+        const float* gsrc = p.dO + (size_t)(t.lb + 16 * s) * kTcF + lf;
+        const float* qsrc = p.Q + (size_t)(t.lb + 16 * s) * kTcF + lf;
+        const int rows = t.n - 16 * s;  // valid rows of this slice (>= 1)
+        float4 xg[4], xq[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          xg[c].x = 4 * c + 0 < rows ? __ldg(gsrc + (size_t)(4 * c + 0) * kTcF) : 0.f;
+          xg[c].y = 4 * c + 1 < rows ? __ldg(gsrc + (size_t)(4 * c + 1) * kTcF) : 0.f;
+          xg[c].z = 4 * c + 2 < rows ? __ldg(gsrc + (size_t)(4 * c + 2) * kTcF) : 0.f;
+          xg[c].w = 4 * c + 3 < rows ? __ldg(gsrc + (size_t)(4 * c + 3) * kTcF) : 0.f;
+          xq[c].x = 4 * c + 0 < rows ? __ldg(qsrc + (size_t)(4 * c + 0) * kTcF) : 0.f;
+          xq[c].y = 4 * c + 1 < rows ? __ldg(qsrc + (size_t)(4 * c + 1) * kTcF) : 0.f;
+          xq[c].z = 4 * c + 2 < rows ? __ldg(qsrc + (size_t)(4 * c + 2) * kTcF) : 0.f;
+          xq[c].w = 4 * c + 3 < rows ? __ldg(qsrc + (size_t)(4 * c + 3) * kTcF) : 0.f;
+        }
+        mbar_wait(&empty[slot], ((sc / kTcSlots) & 1u) ^ 1u);
+        float4* b0 = reinterpret_cast<float4*>(smem + (size_t)slot * kTcSlotBytes + kBcOffB0);
+        float4* b1 = reinterpret_cast<float4*>(smem + (size_t)slot * kTcSlotBytes + kBcOffB1);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float4 hi, lo;
+          split4(xg[c], hi, lo);
+          b0[c * 256 + lf] = hi;
+          b0[c * 256 + 128 + lf] = lo;
+          split4(xq[c], hi, lo);
+          b1[c * 256 + lf] = hi;
+          b1[c * 256 + 128 + lf] = lo;
+        }
+        fence_proxy_async();
+        mbar_arrive(&full_b[slot]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+}
+
 static bool dense_tc_supported(int max_nodes, int h, int f) {
   return h == 1 && f == kTcF && max_nodes >= 1 && max_nodes <= kTcMaxNodes;
 }
@@ -635,6 +911,33 @@ int dfgnn_gt_dense_tc_forward(int n_blocks, const int32_t* blk_ptr, int max_node
   const int grid = sched ? n_ctas : (n_blocks < sm_count() ? n_blocks : sm_count());
   kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(p);
   note_kernel(0, "gt_dense_tc_fwd_kernel");
+  return check_launch(fn);
+}
+
+int dfgnn_gt_dense_tc_backward_col(int n_blocks, const int32_t* blk_ptr, int max_nodes, int m, int nnz, int h, int f,
+                                   const int32_t* row_ptr, const uint32_t* adj_bits, int n_ctas, const int32_t* sched_ptr,
+                                   const int32_t* sched_idx, const float* Q, const float* grad_out, const float* grad_edge,
+                                   float* grad_K, float* grad_V, void* stream) {
+  const char* fn = "dfgnn_gt_dense_tc_backward_col";
+  if (int rc = check_common(fn, m, nnz, h, f)) return rc;
+  if (m == 0) return DFGNN_OK;
+  DFGNN_REQUIRE(blk_ptr, fn); DFGNN_REQUIRE(row_ptr, fn); DFGNN_REQUIRE(adj_bits, fn);
+  DFGNN_REQUIRE(Q, fn); DFGNN_REQUIRE(grad_out, fn); DFGNN_REQUIRE(grad_K, fn); DFGNN_REQUIRE(grad_V, fn);
+  if (nnz > 0) DFGNN_REQUIRE(grad_edge, fn);
+  if (n_blocks < 1 || !dense_tc_supported(max_nodes, h, f)) {
+    set_error("%s: needs h == 1, f == %d and graphs of at most %d nodes (h=%d, f=%d, max_nodes=%d)", fn, kTcF,
+              kTcMaxNodes, h, f, max_nodes);
+    return DFGNN_ERR_UNSUPPORTED_DIM;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool sched = sched_ptr != nullptr && sched_idx != nullptr && n_ctas >= 1;
+  GtTcBwdColParams p{n_blocks, blk_ptr, row_ptr, sched ? sched_ptr : nullptr, sched ? sched_idx : nullptr, adj_bits,
+                     reinterpret_cast<const float2*>(grad_edge), grad_out, Q, grad_K, grad_V};
+  auto kernel = gt_dense_tc_bwd_col_kernel;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBcSmemBytes);
+  const int grid = sched ? n_ctas : (2 * n_blocks < sm_count() ? 2 * n_blocks : sm_count());
+  kernel<<<grid, kBcThreads, kBcSmemBytes, st>>>(p);
+  note_kernel(2, "gt_dense_tc_bwd_col_kernel");
   return check_launch(fn);
 }
 

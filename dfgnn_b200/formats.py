@@ -129,6 +129,7 @@ class BlockPlan:
         self.ascending = bool(ascending)        # column ids strictly ascending inside every row
         self.adj_bits = None                    # [m, 8] int32 adjacency bitmap (dense tcgen05 kernels)
         self.n_ctas, self.sched_ptr, self.sched_idx = 0, None, None  # balanced graph lists of the persistent CTAs
+        self.col_sched = (0, None, None)        # the same for the (graph, key tile) items of the column-side backward
         self._ok = {}
 
     def algorithm(self, m: int, nnz: int, h: int, f: int, unweighted: bool, training: bool = False) -> int:
@@ -197,30 +198,40 @@ def block_plan(batch_num_nodes: torch.Tensor, row_ptr: torch.Tensor, col_ind: to
         _lib.check(rc, "block_adj_bits")
         plan.adj_bits = bits
         plan.n_ctas, plan.sched_ptr, plan.sched_idx = _balanced_schedule(bnn, dev)
+        plan.col_sched = _balanced_schedule(bnn, dev, column_items=True)
     return plan
 
 
-def _balanced_schedule(bnn: torch.Tensor, dev):
-    """Graph lists for the persistent CTAs of the dense tcgen05 kernels (one CTA per SM): longest
-    processing time first over a cost model of the MMA work (a graph of more than 128 nodes is two
-    row tiles over up to 256 keys).  Dealing 1024 PATTERN-shaped graphs round robin leaves the busiest
-    SM with 1.65x the mean work; this schedule 1.05x."""
+def _balanced_schedule(bnn: torch.Tensor, dev, column_items: bool = False):
+    """Work lists for the persistent CTAs of the dense tcgen05 kernels (one CTA per SM): longest
+    processing time first over a cost model of the MMA work.  Forward / row side: one entry per
+    graph (a graph of more than 128 nodes is two row tiles over up to 256 keys).  Column side
+    (``column_items``): one entry per (graph, 128-key tile), id = 2 * graph + tile, cost = the 16-row
+    slices of the graph.  Dealing 1024 PATTERN-shaped graphs round robin leaves the busiest SM with
+    1.65x the mean work; this schedule 1.05x.  -> (number of CTAs, ptr [ctas + 1], ids)."""
     import heapq
     import numpy as np
     n = bnn.numpy().astype(np.int64)
-    slices = (n + 31) // 32
-    cost = np.where(n <= 128, 16 * 246 + slices * 4 * 246, 2 * (16 * 384 + slices * 4 * 246)).astype(np.int64)
+    if column_items:
+        slices = (n + 15) // 16
+        ids = np.concatenate([2 * np.arange(len(n)), 2 * np.nonzero(n > 128)[0] + 1])
+        cost = np.concatenate([slices, slices[n > 128]]) * 1000 + 4000   # + epilogue
+    else:
+        slices = (n + 31) // 32
+        ids = np.arange(len(n))
+        cost = np.where(n <= 128, 16 * 246 + slices * 4 * 246, 2 * (16 * 384 + slices * 4 * 246))
+    cost = cost.astype(np.int64)
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    g = int(min(len(n), sms))
+    g = int(min(len(ids), sms))
     heap = [(0, c) for c in range(g)]
     lists = [[] for _ in range(g)]
-    for b in np.argsort(-cost, kind="stable"):
+    for k in np.argsort(-cost, kind="stable"):
         load, c = heapq.heappop(heap)
-        lists[c].append(int(b))
-        heapq.heappush(heap, (load + int(cost[b]), c))
+        lists[c].append(int(ids[k]))
+        heapq.heappush(heap, (load + int(cost[k]), c))
     ptr = np.zeros(g + 1, dtype=np.int32)
     ptr[1:] = np.cumsum([len(x) for x in lists])
-    idx = np.fromiter((b for x in lists for b in x), dtype=np.int32, count=len(n))
+    idx = np.fromiter((b for x in lists for b in x), dtype=np.int32, count=len(ids))
     return g, torch.from_numpy(ptr).to(dev), torch.from_numpy(idx).to(dev)
 
 

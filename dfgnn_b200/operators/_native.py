@@ -54,7 +54,7 @@ def _blocks(row_ptr, m, nnz, h, f, val=None, backward=False, training=False):
         return None, 0
     unweighted = val is None or getattr(val, "_dfgnn_ones", False)
     algo = plan.algorithm(m, nnz, h, f, unweighted, training or backward)
-    if backward and algo >= 2:  # the dense kernels are forward kernels
+    if backward and algo == 2:  # the mma.sync dense kernels are forward kernels
         algo = 1 if plan.supported(m, nnz, h, f) else 0
     return (plan, algo) if algo else (None, 0)
 
@@ -161,7 +161,18 @@ def gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem_con
                 _ptr(row_ind), _ptr(val_idx), int(smem_consume), _ptr(Q), _ptr(K), _ptr(V),
                 _ptr(attn_edge), _ptr(grad), _ptr(gq), _ptr(gk), _ptr(gv), _ptr(ge), _stream(Q))
         plan, _algo = _blocks(row_ptr, m, nnz, h, f, val, backward=True) if (n == m and _cols is None) else (None, 0)
-        if plan is not None:
+        if plan is not None and _algo == 3:
+            # dense batch: general row-side kernel (dQ + the packed scratch), tcgen05 column side
+            rc = 0
+            if _phases & 1:
+                rc = _lib.lib().dfgnn_gt_backward_phase(1, *tail)
+            if rc == 0 and (_phases & 2):
+                nc, sp, si = plan.col_sched
+                rc = _lib.lib().dfgnn_gt_dense_tc_backward_col(
+                    plan.n_blocks, _ptr(plan.blk_ptr), plan.max_nodes, m, nnz, h, f, _ptr(row_ptr),
+                    _ptr(plan.adj_bits), nc, _ptr(sp), _ptr(si), _ptr(Q), _ptr(grad), _ptr(ge), _ptr(gk), _ptr(gv),
+                    _stream(Q))
+        elif plan is not None:
             rc = _lib.lib().dfgnn_gt_block_backward(
                 int(_phases), plan.n_blocks, _ptr(plan.blk_ptr), plan.max_nodes, m, nnz, h, f, _ptr(row_ptr),
                 _ptr(col_ind), _val_ptr(val), _ptr(col_ptr), _ptr(row_ind), _ptr(val_idx), _ptr(Q), _ptr(K),

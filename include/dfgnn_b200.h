@@ -223,6 +223,20 @@ int dfgnn_gt_dense_tc_forward(int n_blocks, const int32_t *blk_ptr, int max_node
                               int n_ctas, const int32_t *sched_ptr, const int32_t *sched_idx,
                               const float *Q, const float *K, const float *V, float *out_feat,
                               float *attn_edge, void *stream);
+/*
+ * Column side of the GT backward on tcgen05 (csrc/dense_tc.cu): grad_V = P^T grad_out and
+ * grad_K = dS^T Q per (graph, 128-key tile) from the row side's packed scratch grad_edge [nnz][2] =
+ * {dS_e, p_e} in CSR order (what dfgnn_gt_backward_phase(1, ...) leaves there).  Same requirements and
+ * bitmap / schedule arguments as dfgnn_gt_dense_tc_forward; the schedule lists (graph, key tile) items,
+ * item id = 2 * graph + key tile.  Replaces the column-side half of gt_backward
+ * (DFGNN/src/fused_gtconv/fused_gtconv.cpp:125-172) for such batches.
+ */
+int dfgnn_gt_dense_tc_backward_col(int n_blocks, const int32_t *blk_ptr, int max_nodes, int m,
+                                   int nnz, int h, int f, const int32_t *row_ptr,
+                                   const uint32_t *adj_bits, int n_ctas, const int32_t *sched_ptr,
+                                   const int32_t *sched_idx, const float *Q, const float *grad_out,
+                                   const float *grad_edge, float *grad_K, float *grad_V,
+                                   void *stream);
 /* = dfgnn_gt_backward_phase on a square block-diagonal adjacency (n == m). */
 int dfgnn_gt_block_backward(int phases, int n_blocks, const int32_t *blk_ptr, int max_nodes, int m,
                             int nnz, int h, int f, const int32_t *row_ptr, const int32_t *col_ind,

@@ -173,14 +173,16 @@ def test_dense_tensor_core_forward(cuda, kind, dim):
     assert_close("grad_Q", gq, dQ)
     assert_close("grad_K", gk, dK)
     assert_close("grad_V", gv, dV)
-    # automatic mode picks the dense kernels from the fill ratio of the blocks
+    # automatic mode picks the dense kernels from the fill ratio of the blocks: tcgen05 (dense_tc.cu) at
+    # f = 128 for training and inference, mma.sync at f = 64 for inference only
     _lib.lib().dfgnn_set_block_mode(0)
     plan = row_ptr._dfgnn_blocks
-    fill = col_ind.numel() / plan.sum_sq_nodes
-    assert plan.algorithm(n, col_ind.numel(), 1, dim, True) == (2 if fill >= plan.DENSE_MIN_FILL else 0)
-    assert plan.algorithm(n, col_ind.numel(), 1, dim, True, training=True) == 0
+    dense = col_ind.numel() / plan.sum_sq_nodes >= plan.DENSE_MIN_FILL
+    tc = dense and dim == 128
+    assert plan.algorithm(n, col_ind.numel(), 1, dim, True) == (3 if tc else 2 if dense else 0)
+    assert plan.algorithm(n, col_ind.numel(), 1, dim, True, training=True) == (3 if tc else 0)
     inf2 = N.gt_hyper_inference(row_ptr, col_ind, rows, val, smem, Q, K, V)[0]
-    assert _lib.last_kernel(0) == ("gt_dense_fwd_kernel" if fill >= plan.DENSE_MIN_FILL else "dot_fwd_kernel")
+    assert _lib.last_kernel(0) == ("gt_dense_tc_fwd_kernel" if tc else "gt_dense_fwd_kernel" if dense else "dot_fwd_kernel")
     assert_close("automatic mode inference", inf2, o64)
 
 
@@ -212,8 +214,9 @@ def test_dense_tcgen05_forward(cuda, kind):
     inf = N.gt_hyper_inference(row_ptr, col_ind, rows, val, smem, Q, K, V)[0]
     assert _lib.last_kernel(0) == "gt_dense_tc_fwd_kernel"
     assert torch.equal(inf, out)
-    # the backward consumes the dense forward's attn_edge
+    # backward: row side on the general kernel (writes the packed scratch), column side on tcgen05
     gq, gk, gv = N.gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V, attn, dO)
+    assert _lib.last_kernel(2) == "gt_dense_tc_bwd_col_kernel"
     assert_close("grad_Q", gq, dQ)
     assert_close("grad_K", gk, dK)
     assert_close("grad_V", gv, dV)
