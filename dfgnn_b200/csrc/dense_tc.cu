@@ -77,8 +77,6 @@ constexpr size_t kTcSmemBytes = kTcOffPart + (size_t)4 * kTcM * 4;             /
 __device__ __forceinline__ void soft_bar(int group) { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); }
 __device__ __forceinline__ void soft_bar_all() { asm volatile("bar.sync 3, 256;" ::: "memory"); }
 
-__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
-
 __device__ __forceinline__ uint32_t sel8(const uint32_t (&a)[8], int i) {  // a[i] without local memory
   uint32_t v = a[0];
 #pragma unroll
@@ -718,7 +716,7 @@ __global__ void __launch_bounds__(kBcThreads, 1) gt_dense_tc_bwd_col_kernel(cons
         for (int u = 0; u < 8; ++u) {
           const int j = j0 + 16 * u;
           const int at = ((w & 3) * kTcM + j) * 4 + (lane & 3);  // chunk (w & 3), image row j, word i % 4
-          const float ph = trunc_tf32(v[u].y), dh = trunc_tf32(v[u].x);
+          const float ph = round_tf32(v[u].y), dh = round_tf32(v[u].x);
           img[at] = ph;
           img[kBcA / 4 + at] = v[u].y - ph;
           img[2 * kBcA / 4 + at] = dh;

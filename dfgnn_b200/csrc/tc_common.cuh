@@ -55,13 +55,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// x = hi + lo, hi = x truncated to TF32 (the tensor core ignores the 13 low mantissa bits anyway;
-// the mask makes hi exact whatever it does with them), lo exact in fp32
+// x = hi + lo with hi = x rounded to TF32 (10 mantissa bits; round half away from zero by an integer add
+// on the bit pattern -- cvt.rna.tf32.f32 is a seven-instruction sequence on sm_100a) and lo = x - hi exact
+// in fp32.  Rounding instead of truncating halves |lo| (<= 2^-11 |x|) and makes the error the tensor core
+// adds by truncating lo to TF32 (<= 2^-21 |x|) sign-symmetric: truncated hi gave every product a one-sided
+// error of up to 2^-20, which a sum over 128 same-sign terms does not average away.
+__device__ __forceinline__ float round_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 __device__ __forceinline__ void split4(const float4 x, float4& hi, float4& lo) {
-  hi.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
-  hi.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
-  hi.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
-  hi.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+  hi.x = round_tf32(x.x);
+  hi.y = round_tf32(x.y);
+  hi.z = round_tf32(x.z);
+  hi.w = round_tf32(x.w);
   lo = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
 }
 

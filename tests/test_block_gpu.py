@@ -12,7 +12,7 @@ from dfgnn_b200.operators import GTConvFuse_hyper
 from dfgnn_b200.operators import _native as N
 from oracle import cpu_oracle as O
 
-from .helpers import assert_close
+from .helpers import assert_close, assert_close_bulk
 
 pytestmark = pytest.mark.gpu
 
@@ -233,13 +233,28 @@ def test_dense_tcgen05_persistent_loop_and_unsorted_fallback(cuda):
     g = graphs.batched_graph(600, 60.0, 50.0, 1, 200, 20.0, 15.0, 0, None, 8, "many")
     n = g.num_nodes()
     X = graphs.conv_inputs(n, 128, 31)
-    row_ptr, col_ind, rows, val, smem = preprocess_Hyper(g.to(cuda))
-    Q, K, V = (t.to(cuda) for t in (X.Q, X.K, X.V))
+    A, rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx, smem = preprocess_Hyper_fw_bw(g.to(cuda))
+    Q, K, V, dO = (t.to(cuda) for t in (X.Q, X.K, X.V, X.dO))
     out = N.gt_hyper_inference(row_ptr, col_ind, rows, val, smem, Q, K, V)[0]
     assert _lib.last_kernel(0) == "gt_dense_tc_fwd_kernel"
-    out2 = N.gt_hyper_inference(row_ptr.clone(), col_ind, rows, val, smem, Q, K, V)[0]
+    rp2 = row_ptr.clone()  # no plan attached: general kernels
+    out2 = N.gt_hyper_inference(rp2, col_ind, rows, val, smem, Q, K, V)[0]
     assert _lib.last_kernel(0) == "dot_fwd_kernel"
     assert_close("dense tcgen05 vs general kernels", out, out2)
+    # training forward + backward through the persistent loops (several tiles / items per CTA)
+    o_t, attn = N.gt_hyper_forward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V)
+    assert _lib.last_kernel(0) == "gt_dense_tc_fwd_kernel"
+    gq, gk, gv = N.gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V, attn, dO)
+    assert _lib.last_kernel(2) == "gt_dense_tc_bwd_col_kernel"
+    o_g, attn_g = N.gt_hyper_forward(rp2, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V)
+    gq2, gk2, gv2 = N.gt_backward(rp2, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V, attn_g, dO)
+    assert _lib.last_kernel(2) == "gt_bwd_col_kernel"
+    assert_close("persistent loop out", o_t, o_g)
+    assert_close("persistent loop attn_edge", attn, attn_g)
+    # gradients are sums of ~20 cancelling terms computed from two slightly different attn_edge (fp32 dot
+    # products vs 3xTF32): the full-size allowance (a 1e-6 fraction of the elements up to 2x the tolerance)
+    for name, a, b in (("grad_Q", gq, gq2), ("grad_K", gk, gk2), ("grad_V", gv, gv2)):
+        assert_close_bulk("persistent loop " + name, a, b)
     # reverse the column order inside every row: still a valid CSR, no longer ascending
     rp = row_ptr.long()
     pos = torch.arange(col_ind.numel(), device=cuda)
