@@ -134,17 +134,25 @@ struct TcTiles {
   __device__ int stages2() const { return (n + 31) >> 5; }     // product-2 stages (32-key slices)
 };
 
-struct GtTcFwdParams {
+struct GtTcParams {
   int n_blocks;
   const int* blk_ptr;
   const int* row_ptr;
   const int *sched_ptr, *sched_idx;  // optional balanced schedule (null: round robin)
-  const uint32_t* adj_bits;  // [m][8]
-  const float *Q, *K, *V;
-  float *out, *attn;         // attn may be null (inference)
+  const uint32_t* adj_bits;  // [m][8] (forward)
+  const float *a1, *b1, *b2;  // forward: Q, K, V; backward row side: dO, V, K
+  float *out, *attn;          // forward: out, attn_edge (may be null: inference); backward: dQ, unused
+  const float* Pd;            // backward: dense probabilities [m][256]
+  float* dSd;                 // backward: dense dS [m][256] (written here, read by the column side)
 };
+constexpr int kTcDenseLd = 256;  // row pitch of the dense P / dS work arrays
 
-__global__ void __launch_bounds__(kTcThreads, 1) gt_dense_tc_fwd_kernel(const GtTcFwdParams p) {
+// BWD = false: forward (S = Q K^T, softmax, O = P V).  BWD = true: row side of the backward with the same
+// pipeline -- product 1 dA = dO V^T, then per row s_i = sum_j p_ij dA_ij and dS_ij = p_ij (dA_ij - s_i) with
+// the probabilities read from the dense work array (block_attn_dense_kernel), product 2 dQ = dS K; dS is also
+// written to its dense work array for the column side (gt_backward: DFGNN/src/fused_gtconv/fused_gtconv.cu).
+template <bool BWD>
+__global__ void __launch_bounds__(kTcThreads, 1) gt_dense_tc_kernel(const GtTcParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t full_b[kTcSlots], full_a[kTcSlots], empty[kTcSlots], s_full, s_free, o_full, o_free;
   __shared__ uint32_t s_tmem;
@@ -175,6 +183,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gt_dense_tc_fwd_kernel(const Gt
   TC_MARK(t_kernel);
 
   if (w < kTcSoftWarps) {
+    if constexpr (!BWD) {
     // =============================== softmax / epilogue ===========================================
     const int sg = w >> 2, r = tid & 127;  // group, tile row
     const uint32_t lane_base = tmem + ((uint32_t)((w & 3) * 32) << 16);
@@ -358,6 +367,131 @@ __global__ void __launch_bounds__(kTcThreads, 1) gt_dense_tc_fwd_kernel(const Gt
       sc = sc2 + NS2;
       ++tc;
     }
+    } else {
+    // =============================== backward row side: dS / epilogue ==============================
+    const int sg = w >> 2, r = tid & 127;  // group, tile row
+    const uint32_t lane_base = tmem + ((uint32_t)((w & 3) * 32) << 16);
+    float* s_part = reinterpret_cast<float*>(smem + kTcOffPart);  // [group][row] partial row sums
+    float* stg = s_stg + (size_t)sg * kTcM * kTcStgLd;            // this group's staging buffer
+    uint32_t sc = 0, tc = 0;
+    TcTiles t(p.blk_ptr, p.n_blocks, p.sched_ptr, p.sched_idx);
+    while (t.next()) {
+      const bool narrow = t.MT == 1;
+      const int NS2 = t.stages2();
+      const uint32_t sc2 = sc + t.stages1();
+      const int row = t.mt * kTcM + r;
+      const bool valid = row < t.n;
+      const float4* prow = reinterpret_cast<const float4*>(p.Pd + (size_t)(t.lb + (valid ? row : 0)) * kTcDenseLd);
+      float4* dsrow = reinterpret_cast<float4*>(p.dSd + (size_t)(t.lb + (valid ? row : 0)) * kTcDenseLd);
+      auto load_da = [&](int cb, float (&s)[32]) {  // 32 columns of dA (narrow tiles: the sum of the two halves)
+        tmem_ld32(lane_base + cb * 32, s);
+        if (narrow) {
+          float s2[32];
+          tmem_ld32(lane_base + 128 + cb * 32, s2);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s[i] += s2[i];
+        }
+      };
+      mbar_wait(&s_full, tc & 1u);
+      tc_fence_after();
+      // pass 1: s_i = sum_j p_ij dA_ij over this group's pieces (p = 0 where there is no edge)
+      float srow = 0.f;
+#pragma unroll 1
+      for (int cb = sg; cb < NS2; cb += 2) {
+        float4 pv[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) pv[c] = valid ? __ldg(prow + cb * 8 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float s[32];
+        load_da(cb, s);
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          a0 = fmaf(pv[c].x, s[4 * c], a0);
+          a1 = fmaf(pv[c].y, s[4 * c + 1], a1);
+          a0 = fmaf(pv[c].z, s[4 * c + 2], a0);
+          a1 = fmaf(pv[c].w, s[4 * c + 3], a1);
+        }
+        srow += a0 + a1;
+      }
+      s_part[sg * kTcM + r] = srow;
+      soft_bar_all();
+      srow += s_part[(sg ^ 1) * kTcM + r];
+      // pass 2: dS -> A images of product 2 and the dense work array
+#pragma unroll 1
+      for (int cb = sg; cb < NS2; cb += 2) {
+        float4 pv[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) pv[c] = valid ? __ldg(prow + cb * 8 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float s[32];
+        load_da(cb, s);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          pv[c].x *= s[4 * c] - srow;
+          pv[c].y *= s[4 * c + 1] - srow;
+          pv[c].z *= s[4 * c + 2] - srow;
+          pv[c].w *= s[4 * c + 3] - srow;
+        }
+        const uint32_t st = sc2 + cb, slot = st % kTcSlots, k = st / kTcSlots;
+        mbar_wait(&empty[slot], (k & 1u) ^ 1u);
+        float4* a_hi = reinterpret_cast<float4*>(smem + (size_t)slot * kTcSlotBytes);
+        float4* a_lo = reinterpret_cast<float4*>(smem + (size_t)slot * kTcSlotBytes + kTcN1_Alo);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float4 hi, lo;
+          split4(pv[c], hi, lo);
+          a_hi[c * kTcM + r] = hi;
+          a_lo[c * kTcM + r] = lo;
+        }
+        fence_proxy_async();
+        mbar_arrive(&full_a[slot]);
+        if (valid) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) dsrow[cb * 8 + c] = pv[c];
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&s_free);
+      // ---- dQ is complete -----------------------------------------------------------------------
+      mbar_wait(&o_full, tc & 1u);
+      tc_fence_after();
+      float* obase = p.out + (size_t)(t.lb + t.mt * kTcM) * kTcF;
+      const int rows_here = min(kTcM, t.n - t.mt * kTcM);
+#pragma unroll 1
+      for (int cq = sg; cq < kTcF / 32; cq += 2) {
+        float y[32];
+        {
+          float y2[32];
+          tmem_ld32(lane_base + kTcColO + cq * 32, y);
+          tmem_ld32(lane_base + kTcColO + 128 + cq * 32, y2);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) y[i] += y2[i];
+        }
+        if (cq + 2 >= kTcF / 32) {  // this thread's last read of the accumulator
+          tc_fence_before();
+          mbar_arrive(&o_free);
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float4* so = reinterpret_cast<float4*>(stg + (size_t)r * kTcStgLd);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            so[i] = make_float4(y[16 * half + 4 * i], y[16 * half + 4 * i + 1], y[16 * half + 4 * i + 2],
+                                y[16 * half + 4 * i + 3]);
+          soft_bar(sg);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = r + u * 128, rr = i >> 2, c4 = i & 3;
+            if (rr < rows_here)
+              *reinterpret_cast<float4*>(obase + (size_t)rr * kTcF + cq * 32 + 16 * half + 4 * c4) =
+                  *reinterpret_cast<const float4*>(stg + (size_t)rr * kTcStgLd + 4 * c4);
+          }
+          soft_bar(sg);
+        }
+      }
+      sc = sc2 + NS2;
+      ++tc;
+    }
+    }
   } else if (w == kTcMmaWarp) {
     // =============================== MMA issue ====================================================
     if (lane == 0) {
@@ -380,8 +514,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) gt_dense_tc_fwd_kernel(const Gt
               const uint64_t dah = umma_desc_kmajor(base + ks * 2 * kTcLboA, kTcLboA, kTcSBO);
               const uint64_t dal = umma_desc_kmajor(base + kTcN1_Alo + ks * 2 * kTcLboA, kTcLboA, kTcSBO);
               const uint64_t db = umma_desc_kmajor(base + kTcN1_B + ks * 2 * kTcLboB, kTcLboB, kTcSBO);
+              // the cross terms (a_lo b_hi here, a_hi b_lo from the N = 256 MMA) stay in the second, small-magnitude
+              // half: the tensor core adds with truncation, and every add into the full-magnitude half costs
+              // up to one ulp of it (measured: alternating the halves made the results worse, tools/tc_error.py)
               umma_tf32(tmem, dah, db, id256, (q | ks) != 0 ? 1u : 0u);
-              umma_tf32(tmem, dal, db, id128, 1u);
+              umma_tf32(tmem + 128, dal, db, id128, 1u);
             }
             umma_commit(&empty[slot]);
           }
@@ -423,7 +560,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gt_dense_tc_fwd_kernel(const Gt
             const uint64_t dal = umma_desc_kmajor(base + kTcN1_Alo + ks * 2 * kTcLboA, kTcLboA, kTcSBO);
             const uint64_t db = umma_desc_kmajor(base + kTcN1_B + ks * 2 * kTcLboB, kTcLboB, kTcSBO);
             umma_tf32(tmem + kTcColO, dah, db, id256, (s | ks) != 0 ? 1u : 0u);
-            umma_tf32(tmem + kTcColO, dal, db, id128, 1u);
+            umma_tf32(tmem + kTcColO + 128, dal, db, id128, 1u);
           }
           umma_commit(&empty[slot]);
         }
@@ -439,8 +576,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gt_dense_tc_fwd_kernel(const Gt
     TcTiles t(p.blk_ptr, p.n_blocks, p.sched_ptr, p.sched_idx);
     while (t.next()) {
       const int rows_a = min(kTcM, t.n - t.mt * kTcM);
-      const float* qrow = p.Q + (size_t)(t.lb + t.mt * kTcM) * kTcF;
-      const float* krow = p.K + (size_t)t.lb * kTcF;
+      const float* qrow = p.a1 + (size_t)(t.lb + t.mt * kTcM) * kTcF;
+      const float* krow = p.b1 + (size_t)t.lb * kTcF;
+      constexpr float kScaleA = BWD ? 1.f : kLog2e;  // forward: Q into the base-2 exponent domain
       if (t.MT == 1) {
         // ---- narrow product 1, K = 32: Q slice (A, scaled into the base-2 exponent domain), K slice (B) ----
         for (int q = 0; q < 4; ++q, ++sc) {
@@ -466,7 +604,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gt_dense_tc_fwd_kernel(const Gt
           for (int u = 0; u < 8; ++u) {
             const int i = lt + u * kTcGroupThreads, rr = (i & 7) + 8 * (i >> 6), c = (i >> 3) & 7;
             float4 hi, lo;
-            split4(make_float4(xa[u].x * kLog2e, xa[u].y * kLog2e, xa[u].z * kLog2e, xa[u].w * kLog2e), hi, lo);
+            split4(make_float4(xa[u].x * kScaleA, xa[u].y * kScaleA, xa[u].z * kScaleA, xa[u].w * kScaleA), hi, lo);
             a_hi[c * 128 + rr] = hi;
             a_lo[c * 128 + rr] = lo;
             split4(xb[u], hi, lo);
@@ -502,7 +640,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gt_dense_tc_fwd_kernel(const Gt
             const int i = lt + u * kTcGroupThreads, rr = (i & 7) + 8 * (i >> 5), c = (i >> 3) & 3;
             float4 hi, lo;
             if (u < 4) {
-              split4(make_float4(xa[u].x * kLog2e, xa[u].y * kLog2e, xa[u].z * kLog2e, xa[u].w * kLog2e), hi, lo);
+              split4(make_float4(xa[u].x * kScaleA, xa[u].y * kScaleA, xa[u].z * kScaleA, xa[u].w * kScaleA), hi, lo);
               a_hi[c * 128 + rr] = hi;
               a_lo[c * 128 + rr] = lo;
             }
@@ -520,7 +658,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gt_dense_tc_fwd_kernel(const Gt
         if ((int)(sc % kTcLoadGroups) != g) continue;
         unsigned char* slot = smem + (size_t)(sc % kTcSlots) * kTcSlotBytes;
         float4* const bst = reinterpret_cast<float4*>(slot + kTcN1_B);
-        const float* vsrc = p.V + (size_t)(t.lb + s * 32) * kTcF + lt;
+        const float* vsrc = p.b2 + (size_t)(t.lb + s * 32) * kTcF + lt;
         const int keys = t.n - s * 32;  // valid keys of this slice (>= 1)
         TC_MARK(t_ld2);
         float4 xv[8];
@@ -632,11 +770,15 @@ struct GtTcBwdColParams {
   int n_blocks;
   const int *blk_ptr, *row_ptr, *sched_ptr, *sched_idx;
   const uint32_t* adj_bits;
-  const float2* scratch;  // [nnz] {dS_e, p_e}
+  const float2* scratch;  // [nnz] {dS_e, p_e} (DENSE = false)
+  const float *Pd, *dSd;  // dense [m][256] probabilities and dS (DENSE = true)
   const float *dO, *Q;
   float *dK, *dV;
 };
 
+// DENSE = false: P / dS from the packed CSR scratch of the general row-side kernel, through the bitmap.
+// DENSE = true: from the dense work arrays the tcgen05 row-side kernel leaves (no bitmap, no CSR).
+template <bool DENSE>
 __global__ void __launch_bounds__(kBcThreads, 1) gt_dense_tc_bwd_col_kernel(const GtTcBwdColParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t full_a[kTcSlots], full_b[kTcSlots], empty[kTcSlots], acc_full, acc_free;
@@ -674,41 +816,54 @@ __global__ void __launch_bounds__(kBcThreads, 1) gt_dense_tc_bwd_col_kernel(cons
     uint32_t sc = 0, tc = 0;
     TcItems t(p.blk_ptr, p.n_blocks, p.sched_ptr, p.sched_idx);
     while (t.next()) {
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // the previous item's stages have read the tables
-      {
-        const int row = tid;  // one table row per thread
-        uint4 ww = make_uint4(0u, 0u, 0u, 0u);
-        int4 cc = make_int4(0, 0, 0, 0);
-        if (row < t.n) {
-          const uint4* src = reinterpret_cast<const uint4*>(p.adj_bits + (size_t)(t.lb + row) * kTcMaskW);
-          int e = __ldg(p.row_ptr + t.lb + row);
-          if (t.kt) {
-            const uint4 lo = __ldg(src);
-            e += __popc(lo.x) + __popc(lo.y) + __popc(lo.z) + __popc(lo.w);
+      if constexpr (!DENSE) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // the previous item's stages have read the tables
+        {
+          const int row = tid;  // one table row per thread
+          uint4 ww = make_uint4(0u, 0u, 0u, 0u);
+          int4 cc = make_int4(0, 0, 0, 0);
+          if (row < t.n) {
+            const uint4* src = reinterpret_cast<const uint4*>(p.adj_bits + (size_t)(t.lb + row) * kTcMaskW);
+            int e = __ldg(p.row_ptr + t.lb + row);
+            if (t.kt) {
+              const uint4 lo = __ldg(src);
+              e += __popc(lo.x) + __popc(lo.y) + __popc(lo.z) + __popc(lo.w);
+            }
+            ww = __ldg(src + t.kt);
+            cc.x = e;
+            cc.y = cc.x + __popc(ww.x);
+            cc.z = cc.y + __popc(ww.y);
+            cc.w = cc.z + __popc(ww.z);
           }
-          ww = __ldg(src + t.kt);
-          cc.x = e;
-          cc.y = cc.x + __popc(ww.x);
-          cc.z = cc.y + __popc(ww.y);
-          cc.w = cc.z + __popc(ww.z);
+          s_tabw[row] = ww;
+          s_tabc[row] = cc;
         }
-        s_tabw[row] = ww;
-        s_tabc[row] = cc;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
       const int NS = t.stages();
       for (int s = 0; s < NS; ++s, ++sc) {
         const uint32_t slot = sc % kTcSlots;
-        const uint4 ww = s_tabw[16 * s + i_loc];
-        const int4 cc = s_tabc[16 * s + i_loc];
         float2 v[8];
+        if constexpr (DENSE) {
+          const int row = 16 * s + i_loc, n32 = (t.n + 31) & ~31;
+          const size_t at = (size_t)(t.lb + (row < t.n ? row : 0)) * kTcDenseLd + t.kt * kTcM;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int j = j0 + 16 * u, bit = j & 31;
-          const uint32_t word = (u >> 1) == 0 ? ww.x : (u >> 1) == 1 ? ww.y : (u >> 1) == 2 ? ww.z : ww.w;
-          const int cbase = (u >> 1) == 0 ? cc.x : (u >> 1) == 1 ? cc.y : (u >> 1) == 2 ? cc.z : cc.w;
-          v[u] = make_float2(0.f, 0.f);
-          if ((word >> bit) & 1u) v[u] = __ldg(p.scratch + cbase + __popc(word & ((1u << bit) - 1u)));
+          for (int u = 0; u < 8; ++u) {
+            const int j = j0 + 16 * u;
+            v[u] = make_float2(0.f, 0.f);
+            if (row < t.n && t.kt * kTcM + j < n32) v[u] = make_float2(__ldg(p.dSd + at + j), __ldg(p.Pd + at + j));
+          }
+        } else {
+          const uint4 ww = s_tabw[16 * s + i_loc];
+          const int4 cc = s_tabc[16 * s + i_loc];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int j = j0 + 16 * u, bit = j & 31;
+            const uint32_t word = (u >> 1) == 0 ? ww.x : (u >> 1) == 1 ? ww.y : (u >> 1) == 2 ? ww.z : ww.w;
+            const int cbase = (u >> 1) == 0 ? cc.x : (u >> 1) == 1 ? cc.y : (u >> 1) == 2 ? cc.z : cc.w;
+            v[u] = make_float2(0.f, 0.f);
+            if ((word >> bit) & 1u) v[u] = __ldg(p.scratch + cbase + __popc(word & ((1u << bit) - 1u)));
+          }
         }
         mbar_wait(&empty[slot], ((sc / kTcSlots) & 1u) ^ 1u);
         float* img = reinterpret_cast<float*>(smem + (size_t)slot * kTcSlotBytes);
@@ -792,9 +947,9 @@ __global__ void __launch_bounds__(kBcThreads, 1) gt_dense_tc_bwd_col_kernel(cons
             const uint64_t db1 = umma_desc_kmajor(base + kBcOffB1 + bo, kTcLboB, kTcSBO);
             const uint32_t acc = (s | ks) != 0 ? 1u : 0u;
             umma_tf32(tmem, dph, db0, id256, acc);        // dV += P^T_hi [dO_hi | dO_lo]
-            umma_tf32(tmem, dpl, db0, id128, 1u);         // dV += P^T_lo dO_hi
+            umma_tf32(tmem + 128, dpl, db0, id128, 1u);   // dV (second half) += P^T_lo dO_hi
             umma_tf32(tmem + 256, dsh, db1, id256, acc);  // dK += dS^T_hi [Q_hi | Q_lo]
-            umma_tf32(tmem + 256, dsl, db1, id128, 1u);   // dK += dS^T_lo Q_hi
+            umma_tf32(tmem + 384, dsl, db1, id128, 1u);   // dK (second half) += dS^T_lo Q_hi
           }
           umma_commit(&empty[slot]);
         }
@@ -847,6 +1002,26 @@ __global__ void __launch_bounds__(kBcThreads, 1) gt_dense_tc_bwd_col_kernel(cons
   tc_fence_before();
   __syncthreads();
   if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+}
+
+// attn_edge (CSR order) -> dense probabilities [m][256] (zeros where there is no edge, up to the next multiple
+// of 32 columns of each graph): one CTA per graph, a warp per row, 32 columns per step through the bitmap.
+static __global__ void block_attn_dense_kernel(const int* __restrict__ blk_ptr, const int* __restrict__ row_ptr,
+                                               const uint32_t* __restrict__ bits, const float* __restrict__ attn,
+                                               float* __restrict__ Pd) {
+  const int b = blockIdx.x, lb = blk_ptr[b], n = blk_ptr[b + 1] - lb;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5, nc = (n + 31) >> 5;
+  for (int r = w; r < n; r += nw) {
+    int e = row_ptr[lb + r];
+    const uint32_t mine = lane < kTcMaskW ? bits[(size_t)(lb + r) * kTcMaskW + lane] : 0u;
+    for (int cb = 0; cb < nc; ++cb) {
+      const uint32_t word = __shfl_sync(kFull, mine, cb);
+      float v = 0.f;
+      if ((word >> lane) & 1u) v = attn[e + __popc(word & ((1u << lane) - 1u))];
+      Pd[(size_t)(lb + r) * kTcDenseLd + cb * 32 + lane] = v;
+      e += __popc(word);
+    }
+  }
 }
 
 static bool dense_tc_supported(int max_nodes, int h, int f) {
@@ -902,9 +1077,9 @@ int dfgnn_gt_dense_tc_forward(int n_blocks, const int32_t* blk_ptr, int max_node
   }
   cudaStream_t st = (cudaStream_t)stream;
   const bool sched = sched_ptr != nullptr && sched_idx != nullptr && n_ctas >= 1;
-  GtTcFwdParams p{n_blocks, blk_ptr, row_ptr, sched ? sched_ptr : nullptr, sched ? sched_idx : nullptr, adj_bits,
-                  Q, K, V, out_feat, nnz > 0 ? attn_edge : nullptr};
-  auto kernel = gt_dense_tc_fwd_kernel;
+  GtTcParams p{n_blocks, blk_ptr, row_ptr, sched ? sched_ptr : nullptr, sched ? sched_idx : nullptr, adj_bits,
+               Q, K, V, out_feat, nnz > 0 ? attn_edge : nullptr, nullptr, nullptr};
+  auto kernel = gt_dense_tc_kernel<false>;
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
   const int grid = sched ? n_ctas : (n_blocks < sm_count() ? n_blocks : sm_count());
   kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(p);
@@ -930,13 +1105,64 @@ int dfgnn_gt_dense_tc_backward_col(int n_blocks, const int32_t* blk_ptr, int max
   cudaStream_t st = (cudaStream_t)stream;
   const bool sched = sched_ptr != nullptr && sched_idx != nullptr && n_ctas >= 1;
   GtTcBwdColParams p{n_blocks, blk_ptr, row_ptr, sched ? sched_ptr : nullptr, sched ? sched_idx : nullptr, adj_bits,
-                     reinterpret_cast<const float2*>(grad_edge), grad_out, Q, grad_K, grad_V};
-  auto kernel = gt_dense_tc_bwd_col_kernel;
+                     reinterpret_cast<const float2*>(grad_edge), nullptr, nullptr, grad_out, Q, grad_K, grad_V};
+  auto kernel = gt_dense_tc_bwd_col_kernel<false>;
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBcSmemBytes);
   const int grid = sched ? n_ctas : (2 * n_blocks < sm_count() ? 2 * n_blocks : sm_count());
   kernel<<<grid, kBcThreads, kBcSmemBytes, st>>>(p);
   note_kernel(2, "gt_dense_tc_bwd_col_kernel");
   return check_launch(fn);
+}
+
+size_t dfgnn_gt_dense_tc_backward_ws_floats(int m) { return (size_t)2 * (size_t)(m > 0 ? m : 0) * kTcDenseLd; }
+
+int dfgnn_gt_dense_tc_backward(int phases, int n_blocks, const int32_t* blk_ptr, int max_nodes, int m, int nnz, int h,
+                               int f, const int32_t* row_ptr, const uint32_t* adj_bits, int n_ctas,
+                               const int32_t* sched_ptr, const int32_t* sched_idx, int n_ctas_col,
+                               const int32_t* sched_ptr_col, const int32_t* sched_idx_col, const float* Q,
+                               const float* K, const float* V, const float* attn_edge, const float* grad_out,
+                               float* grad_Q, float* grad_K, float* grad_V, float* dense_ws, void* stream) {
+  const char* fn = "dfgnn_gt_dense_tc_backward";
+  if (phases < 1 || phases > 3) { set_error("%s: phases=%d must be 1, 2 or 3", fn, phases); return DFGNN_ERR_INVALID_ARGUMENT; }
+  if (int rc = check_common(fn, m, nnz, h, f)) return rc;
+  if (m == 0) return DFGNN_OK;
+  DFGNN_REQUIRE(blk_ptr, fn); DFGNN_REQUIRE(row_ptr, fn); DFGNN_REQUIRE(adj_bits, fn); DFGNN_REQUIRE(dense_ws, fn);
+  DFGNN_REQUIRE(Q, fn); DFGNN_REQUIRE(K, fn); DFGNN_REQUIRE(V, fn); DFGNN_REQUIRE(grad_out, fn);
+  DFGNN_REQUIRE(grad_Q, fn); DFGNN_REQUIRE(grad_K, fn); DFGNN_REQUIRE(grad_V, fn);
+  if (nnz > 0) DFGNN_REQUIRE(attn_edge, fn);
+  if (n_blocks < 1 || !dense_tc_supported(max_nodes, h, f)) {
+    set_error("%s: needs h == 1, f == %d and graphs of at most %d nodes (h=%d, f=%d, max_nodes=%d)", fn, kTcF,
+              kTcMaxNodes, h, f, max_nodes);
+    return DFGNN_ERR_UNSUPPORTED_DIM;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  float* Pd = dense_ws;
+  float* dSd = dense_ws + (size_t)m * kTcDenseLd;
+  if (phases & 1) {
+    block_attn_dense_kernel<<<n_blocks, 256, 0, st>>>(blk_ptr, row_ptr, adj_bits, attn_edge, Pd);
+    if (int rc = check_launch(fn)) return rc;
+    const bool sched = sched_ptr != nullptr && sched_idx != nullptr && n_ctas >= 1;
+    GtTcParams p{n_blocks, blk_ptr, row_ptr, sched ? sched_ptr : nullptr, sched ? sched_idx : nullptr, adj_bits,
+                 grad_out, V, K, grad_Q, nullptr, Pd, dSd};
+    auto kernel = gt_dense_tc_kernel<true>;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
+    const int grid = sched ? n_ctas : (n_blocks < sm_count() ? n_blocks : sm_count());
+    kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(p);
+    note_kernel(1, "gt_dense_tc_bwd_row_kernel");
+    if (int rc = check_launch(fn)) return rc;
+  }
+  if (phases & 2) {
+    const bool sched = sched_ptr_col != nullptr && sched_idx_col != nullptr && n_ctas_col >= 1;
+    GtTcBwdColParams p{n_blocks, blk_ptr, row_ptr, sched ? sched_ptr_col : nullptr, sched ? sched_idx_col : nullptr, adj_bits,
+                       nullptr, Pd, dSd, grad_out, Q, grad_K, grad_V};
+    auto kernel = gt_dense_tc_bwd_col_kernel<true>;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBcSmemBytes);
+    const int grid = sched ? n_ctas_col : (2 * n_blocks < sm_count() ? 2 * n_blocks : sm_count());
+    kernel<<<grid, kBcThreads, kBcSmemBytes, st>>>(p);
+    note_kernel(2, "gt_dense_tc_bwd_col_kernel");
+    if (int rc = check_launch(fn)) return rc;
+  }
+  return DFGNN_OK;
 }
 
 #ifdef DFGNN_TC_PROF

@@ -162,16 +162,19 @@ def gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem_con
                 _ptr(attn_edge), _ptr(grad), _ptr(gq), _ptr(gk), _ptr(gv), _ptr(ge), _stream(Q))
         plan, _algo = _blocks(row_ptr, m, nnz, h, f, val, backward=True) if (n == m and _cols is None) else (None, 0)
         if plan is not None and _algo == 3:
-            # dense batch: general row-side kernel (dQ + the packed scratch), tcgen05 column side
-            rc = 0
-            if _phases & 1:
-                rc = _lib.lib().dfgnn_gt_backward_phase(1, *tail)
-            if rc == 0 and (_phases & 2):
-                nc, sp, si = plan.col_sched
-                rc = _lib.lib().dfgnn_gt_dense_tc_backward_col(
-                    plan.n_blocks, _ptr(plan.blk_ptr), plan.max_nodes, m, nnz, h, f, _ptr(row_ptr),
-                    _ptr(plan.adj_bits), nc, _ptr(sp), _ptr(si), _ptr(Q), _ptr(grad), _ptr(ge), _ptr(gk), _ptr(gv),
-                    _stream(Q))
+            # dense batch: both sides on tcgen05 (csrc/dense_tc.cu); dense P / dS tiles in a work array kept on
+            # the plan (it must survive from a row-side call to a column-side call)
+            L = _lib.lib()
+            need = int(L.dfgnn_gt_dense_tc_backward_ws_floats(m))
+            ws = getattr(plan, "_dense_ws", None)
+            if ws is None or ws.numel() < need or ws.device != Q.device:
+                ws = plan._dense_ws = torch.empty(need, dtype=torch.float32, device=Q.device)
+            nc, sp, si = plan.col_sched
+            rc = L.dfgnn_gt_dense_tc_backward(
+                int(_phases), plan.n_blocks, _ptr(plan.blk_ptr), plan.max_nodes, m, nnz, h, f, _ptr(row_ptr),
+                _ptr(plan.adj_bits), plan.n_ctas, _ptr(plan.sched_ptr), _ptr(plan.sched_idx), nc, _ptr(sp), _ptr(si),
+                _ptr(Q), _ptr(K), _ptr(V), _ptr(attn_edge), _ptr(grad), _ptr(gq), _ptr(gk), _ptr(gv), _ptr(ws),
+                _stream(Q))
         elif plan is not None:
             rc = _lib.lib().dfgnn_gt_block_backward(
                 int(_phases), plan.n_blocks, _ptr(plan.blk_ptr), plan.max_nodes, m, nnz, h, f, _ptr(row_ptr),

@@ -214,10 +214,26 @@ def test_dense_tcgen05_forward(cuda, kind):
     inf = N.gt_hyper_inference(row_ptr, col_ind, rows, val, smem, Q, K, V)[0]
     assert _lib.last_kernel(0) == "gt_dense_tc_fwd_kernel"
     assert torch.equal(inf, out)
-    # backward: row side on the general kernel (writes the packed scratch), column side on tcgen05
+    # backward: both sides on tcgen05 (dense P / dS tiles in between)
     gq, gk, gv = N.gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V, attn, dO)
-    assert _lib.last_kernel(2) == "gt_dense_tc_bwd_col_kernel"
-    assert_close("grad_Q", gq, dQ)
+    assert _lib.last_kernel(1) == "gt_dense_tc_bwd_row_kernel" and _lib.last_kernel(2) == "gt_dense_tc_bwd_col_kernel"
+    # the column-side kernel also runs from the general row-side kernel's packed CSR scratch
+    bufs = N.gt_backward(row_ptr.clone(), col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V, attn, dO, _phases=1)
+    plan_ = row_ptr._dfgnn_blocks
+    nc_, sp_, si_ = plan_.col_sched
+    gk_c, gv_c = torch.empty_like(K), torch.empty_like(V)
+    rc = _lib.lib().dfgnn_gt_dense_tc_backward_col(
+        plan_.n_blocks, plan_.blk_ptr.data_ptr(), plan_.max_nodes, n, col_ind.numel(), 1, 128, row_ptr.data_ptr(),
+        plan_.adj_bits.data_ptr(), nc_, sp_.data_ptr(), si_.data_ptr(), Q.data_ptr(), dO.data_ptr(), bufs[3].data_ptr(),
+        gk_c.data_ptr(), gv_c.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "dense_tc_backward_col")
+    assert_close("grad_K from the CSR scratch", gk_c, dK)
+    assert_close("grad_V from the CSR scratch", gv_c, dV)
+    # grad_Q = sum_j p_ij (dA_ij - s_i) K_j cancels heavily and goes through two 3xTF32 products whose fp32
+    # accumulation in the tensor core truncates: a few elements per million land up to 1.5x outside
+    # 1e-4 / 1e-5 (tools/tc_error.py; the general fp32 kernel reaches 0.95x on the same inputs) -- the
+    # full-size allowance (every element within 2x, at most max(1, 1e-6 of them) outside 1x) applies
+    assert_close_bulk("grad_Q", gq[:, 0], torch.from_numpy(dQ)[:, 0])
     assert_close("grad_K", gk, dK)
     assert_close("grad_V", gv, dV)
     # other widths and weighted scores stay on the other kernels
@@ -246,15 +262,13 @@ def test_dense_tcgen05_persistent_loop_and_unsorted_fallback(cuda):
     assert _lib.last_kernel(0) == "gt_dense_tc_fwd_kernel"
     gq, gk, gv = N.gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V, attn, dO)
     assert _lib.last_kernel(2) == "gt_dense_tc_bwd_col_kernel"
-    o_g, attn_g = N.gt_hyper_forward(rp2, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V)
-    gq2, gk2, gv2 = N.gt_backward(rp2, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V, attn_g, dO)
-    assert _lib.last_kernel(2) == "gt_bwd_col_kernel"
-    assert_close("persistent loop out", o_t, o_g)
-    assert_close("persistent loop attn_edge", attn, attn_g)
-    # gradients are sums of ~20 cancelling terms computed from two slightly different attn_edge (fp32 dot
-    # products vs 3xTF32): the full-size allowance (a 1e-6 fraction of the elements up to 2x the tolerance)
-    for name, a, b in (("grad_Q", gq, gq2), ("grad_K", gk, gk2), ("grad_V", gv, gv2)):
-        assert_close_bulk("persistent loop " + name, a, b)
+    from .test_fullsize_gpu import _gt_reference_chunked
+    ro, ra, rq, rk, rv = _gt_reference_chunked(row_ptr, col_ind, Q, K, V, dO)  # fp64 on the device
+    assert_close("persistent loop out", o_t[:, 0], ro)
+    assert_close("persistent loop attn_edge", attn[0], ra)
+    assert_close_bulk("persistent loop grad_Q", gq[:, 0], rq)  # see test_dense_tcgen05_forward
+    assert_close("persistent loop grad_K", gk[:, 0], rk)
+    assert_close("persistent loop grad_V", gv[:, 0], rv)
     # reverse the column order inside every row: still a valid CSR, no longer ascending
     rp = row_ptr.long()
     pos = torch.arange(col_ind.numel(), device=cuda)
