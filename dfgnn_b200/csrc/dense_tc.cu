@@ -152,7 +152,7 @@ constexpr int kTcDenseLd = 256;  // row pitch of the dense P / dS work arrays
 // the probabilities read from the dense work array (block_attn_dense_kernel), product 2 dQ = dS K; dS is also
 // written to its dense work array for the column side (gt_backward: DFGNN/src/fused_gtconv/fused_gtconv.cu).
 template <bool BWD>
-__global__ void __launch_bounds__(kTcThreads, 1) gt_dense_tc_kernel(const GtTcParams p) {
+__device__ __forceinline__ void gt_dense_tc_body(const GtTcParams& p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t full_b[kTcSlots], full_a[kTcSlots], empty[kTcSlots], s_full, s_free, o_full, o_free;
   __shared__ uint32_t s_tmem;
@@ -692,6 +692,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gt_dense_tc_kernel(const GtTcPa
   if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
 }
 
+__global__ void __launch_bounds__(kTcThreads, 1) gt_dense_tc_fwd_kernel(const GtTcParams p) { gt_dense_tc_body<false>(p); }
+__global__ void __launch_bounds__(kTcThreads, 1) gt_dense_tc_bwd_row_kernel(const GtTcParams p) { gt_dense_tc_body<true>(p); }
+
 // adjacency bitmap of a block-diagonal batch: bit j of row r's 256 bits = (r, first node of r's graph + j)
 // is an edge.  One CTA per graph, a warp per row.
 static __global__ void block_adj_bits_kernel(int n_blocks, const int* __restrict__ blk_ptr, const int* __restrict__ row_ptr,
@@ -1079,7 +1082,7 @@ int dfgnn_gt_dense_tc_forward(int n_blocks, const int32_t* blk_ptr, int max_node
   const bool sched = sched_ptr != nullptr && sched_idx != nullptr && n_ctas >= 1;
   GtTcParams p{n_blocks, blk_ptr, row_ptr, sched ? sched_ptr : nullptr, sched ? sched_idx : nullptr, adj_bits,
                Q, K, V, out_feat, nnz > 0 ? attn_edge : nullptr, nullptr, nullptr};
-  auto kernel = gt_dense_tc_kernel<false>;
+  auto kernel = gt_dense_tc_fwd_kernel;
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
   const int grid = sched ? n_ctas : (n_blocks < sm_count() ? n_blocks : sm_count());
   kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(p);
@@ -1144,7 +1147,7 @@ int dfgnn_gt_dense_tc_backward(int phases, int n_blocks, const int32_t* blk_ptr,
     const bool sched = sched_ptr != nullptr && sched_idx != nullptr && n_ctas >= 1;
     GtTcParams p{n_blocks, blk_ptr, row_ptr, sched ? sched_ptr : nullptr, sched ? sched_idx : nullptr, adj_bits,
                  grad_out, V, K, grad_Q, nullptr, Pd, dSd};
-    auto kernel = gt_dense_tc_kernel<true>;
+    auto kernel = gt_dense_tc_bwd_row_kernel;
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
     const int grid = sched ? n_ctas : (n_blocks < sm_count() ? n_blocks : sm_count());
     kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(p);

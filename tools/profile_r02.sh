@@ -9,15 +9,15 @@
 set -u
 OUT=gpurun_out
 mkdir -p $OUT
-OURS='regex:gat_fwd|gat_bwd|dot_fwd|gt_bwd|gt_block|gt_dense'
-ALL='regex:gat_fwd|gat_bwd|dot_fwd|gt_bwd|gt_block|gt_dense|fused_|sddmm|spmm|softMax|softmax|mhsddmm|mhspmm'
+OURS='regex:gat_fwd|gat_bwd|dot_fwd|gt_bwd|gt_block|gt_dense|block_attn_dense'
+ALL='regex:gat_fwd|gat_bwd|dot_fwd|gt_bwd|gt_block|gt_dense|block_attn_dense|fused_|sddmm|spmm|softMax|softmax|mhsddmm|mhspmm'
 for W in ${WORKLOADS:-arxiv-gat pattern-gt voc-gt reddit-gt}; do
   python bench.py --workload $W --profile --profile-ref > $OUT/r02_plain_$W.log 2>&1 || { echo "plain run failed: $W"; tail -5 $OUT/r02_plain_$W.log; continue; }
   ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
       -k "$ALL" --csv --log-file $OUT/r02_traffic_$W.csv python bench.py --workload $W --profile --profile-ref > $OUT/r02_ncu1_$W.log 2>&1
   echo "traffic $W rc=$?"
   # launches per step: 6 for the staged GAT path (3 staged + 3 big-tile launches), 3 for GT
-  case $W in arxiv-gat) SKIP=6; CNT=6; SRC="--import-source on";; pattern-gt) SKIP=3; CNT=3; SRC="--import-source on";; *) SKIP=3; CNT=3; SRC="";; esac
+  case $W in arxiv-gat) SKIP=6; CNT=6; SRC="--import-source on";; pattern-gt) SKIP=4; CNT=4; SRC="--import-source on";; *) SKIP=3; CNT=3; SRC="";; esac
   python bench.py --workload $W --profile > $OUT/r02_plain2_$W.log 2>&1 &&
   ncu --set full --clock-control none $SRC -k "$OURS" -s $SKIP -c $CNT -f -o $OUT/r02_full_$W \
       python bench.py --workload $W --profile > $OUT/r02_ncu2_$W.log 2>&1
