@@ -1014,16 +1014,22 @@ static __global__ void block_attn_dense_kernel(const int* __restrict__ blk_ptr, 
                                                float* __restrict__ Pd) {
   const int b = blockIdx.x, lb = blk_ptr[b], n = blk_ptr[b + 1] - lb;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5, nc = (n + 31) >> 5;
-  for (int r = w; r < n; r += nw) {
-    int e = row_ptr[lb + r];
+  // gridDim.y CTAs share a graph; a warp keeps the loads of a whole row (up to 8 pieces) in flight
+  for (int r = w + nw * blockIdx.y; r < n; r += nw * gridDim.y) {
+    const int e0 = row_ptr[lb + r];
     const uint32_t mine = lane < kTcMaskW ? bits[(size_t)(lb + r) * kTcMaskW + lane] : 0u;
-    for (int cb = 0; cb < nc; ++cb) {
+    float v[kTcMaskW];
+    int e = e0;
+#pragma unroll
+    for (int cb = 0; cb < kTcMaskW; ++cb) {
       const uint32_t word = __shfl_sync(kFull, mine, cb);
-      float v = 0.f;
-      if ((word >> lane) & 1u) v = attn[e + __popc(word & ((1u << lane) - 1u))];
-      Pd[(size_t)(lb + r) * kTcDenseLd + cb * 32 + lane] = v;
+      v[cb] = 0.f;
+      if (cb < nc && ((word >> lane) & 1u)) v[cb] = __ldg(attn + e + __popc(word & ((1u << lane) - 1u)));
       e += __popc(word);
     }
+#pragma unroll
+    for (int cb = 0; cb < kTcMaskW; ++cb)
+      if (cb < nc) Pd[(size_t)(lb + r) * kTcDenseLd + cb * 32 + lane] = v[cb];
   }
 }
 
@@ -1142,7 +1148,7 @@ int dfgnn_gt_dense_tc_backward(int phases, int n_blocks, const int32_t* blk_ptr,
   float* Pd = dense_ws;
   float* dSd = dense_ws + (size_t)m * kTcDenseLd;
   if (phases & 1) {
-    block_attn_dense_kernel<<<n_blocks, 256, 0, st>>>(blk_ptr, row_ptr, adj_bits, attn_edge, Pd);
+    block_attn_dense_kernel<<<dim3(n_blocks, 4), 256, 0, st>>>(blk_ptr, row_ptr, adj_bits, attn_edge, Pd);
     if (int rc = check_launch(fn)) return rc;
     const bool sched = sched_ptr != nullptr && sched_idx != nullptr && n_ctas >= 1;
     GtTcParams p{n_blocks, blk_ptr, row_ptr, sched ? sched_ptr : nullptr, sched ? sched_idx : nullptr, adj_bits,
