@@ -28,7 +28,7 @@ reddit-gt row-partitioned), so that every line carries configs 2-5 at that N.
   roofline  the slowest kernel of the step on its own: algorithmic bytes (SURVEY.md 8d gather
             model) / its CUDA-event duration, against MEASURED_PEAKS.json; next to it the
             compulsory bytes (every array once) and, from the committed ncu capture of the SAME
-            kernel sources (profiles/r02_traffic.json), the DRAM traffic and frac_dram.
+            kernel sources (profiles/r03_traffic.json), the DRAM traffic and frac_dram.
   cpu_baseline   the CPU oracle (oracle/dfgnn_oracle.c, OpenMP) on the same workload.
   gpu_reference  the reference's own CUDA kernels (oracle/_ref, sm_100a): timed eagerly next to
                  OUR step timed eagerly too (like for like), plus the graph-replay number.
@@ -54,7 +54,7 @@ if ROOT not in sys.path:
 
 METRIC = "fused_conv_fwd_bwd_edges_x_dim_per_s"
 UNIT = "edges*dim/s"
-TRAFFIC_FILE = os.path.join("profiles", "r02_traffic.json")
+TRAFFIC_FILE = os.path.join("profiles", "r03_traffic.json")
 
 WORKLOADS = {
     # name: (conv, dim, graph fn, kwargs, format, BASELINE.json config index)
@@ -758,7 +758,7 @@ def time_gpu_reference(name, conv, dim, idx, d_in, flush, steps, e_total, ours_e
            "note": "both sides launched eagerly from Python with the same L2-flush protocol; the reference's "
                    "gat_forward also creates a cuRAND generator and zero-fills its outputs on every call "
                    "(fused_gatconv_kernel.cu:1073-1081), which is part of its public entry point; the "
-                   "kernel-only sum of the reference is in profiles/r02_traffic.json (reference_kernels)"}
+                   "kernel-only sum of the reference is in profiles/r03_traffic.json (reference_kernels)"}
     try:
         if conv == "gt":
             ref = ref_gpu.fused_gtconv()

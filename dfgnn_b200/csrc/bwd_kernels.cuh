@@ -349,6 +349,7 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : 16) / kNW) gat_bw
   const float* acb = p.ac + hid;
   float2* scratch = reinterpret_cast<float2*>(p.grad_edge);  // [nnz, h] x {de_e, keep-scaled p_e}
 
+  if (small_tile_exit(p.row_ptr, p.m, p.rb, p.cap)) return;
   slots_clear<1, LPR>(s_slot, vw, gl);
   const RowBlock b = rowblock_init<G>(s_rp, p.row_ptr, p.m, p.rb, vw);
   if (p.cap > 0 && b.E1 - b.E0 <= p.cap) {  // not a big tile: nothing to do here
@@ -459,6 +460,7 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR * C <= 32 ? 24 : 16) / kNW) g
   char* GFb = ra.base(p.grad_feat);
   const float2* scratch = reinterpret_cast<const float2*>(p.grad_edge);
 
+  if (small_tile_exit(p.col_ptr, p.n, p.rb_col, p.cap)) return;
   slots_clear<NR, LPR>(s_slot, vw, gl);
   const RowBlock b = rowblock_init<G>(s_cp, p.col_ptr, p.n, p.rb_col, vw);
   if (p.cap > 0 && b.E1 - b.E0 <= p.cap) {  // not a big tile: nothing to do here

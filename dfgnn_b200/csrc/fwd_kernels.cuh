@@ -241,6 +241,7 @@ __global__ void __launch_bounds__(kNW * 32, (L::NR <= 8 ? 24 : 16) / kNW) gat_fw
   char* Ob = ra.base(p.out);
   const float* acb = p.ac + hid;
 
+  if (small_tile_exit(p.row_ptr, p.m, p.rb, p.cap)) return;
   slots_clear<NR, LPR>(s_slot, vw, gl);
   const RowBlock b = rowblock_init<G>(s_rp, p.row_ptr, p.m, p.rb, vw);
   if (p.cap > 0 && b.E1 - b.E0 <= p.cap) {  // not a big tile: nothing to do here

@@ -114,4 +114,14 @@ __device__ __forceinline__ void slots_clear(float* smem, int vw, int gl) {
   if (gl < 2) Slot<NV, LPR>(smem, vw, gl).set_seg(-1);
 }
 
+// "big tiles only" launches (cap > 0) behind a staged kernel: almost every CTA owns a tile the staged
+// kernel has already done.  Decide from two segment pointers before anything is staged in shared memory.
+__device__ __forceinline__ bool small_tile_exit(const int* __restrict__ seg_ptr, int n_seg, int rb, int cap) {
+  if (cap <= 0) return false;
+  const int lb = blockIdx.x * rb, ub = min(lb + rb, n_seg);
+  if (__ldg(seg_ptr + ub) - __ldg(seg_ptr + lb) > cap) return false;
+  dependency_wait();
+  return true;
+}
+
 }  // namespace dfgnn

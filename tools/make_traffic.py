@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Turn what tools/profile_r02.sh brought back in gpurun_out/ into the committed evidence:
 
-    python tools/make_traffic.py [TAG]        (default TAG r02)
+    python tools/make_traffic.py [TAG]        (default TAG r03)
 
   profiles/TAG_traffic.json          per kernel and workload: DRAM bytes per launch
                                      (dram__bytes_read.sum + dram__bytes_write.sum) and the ncu
@@ -21,7 +21,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-TAG = sys.argv[1] if len(sys.argv) > 1 else "r02"
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r03"
 OUT = os.path.join(ROOT, "gpurun_out")
 PROF = os.path.join(ROOT, "profiles")
 UNIT = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -74,7 +74,7 @@ def main():
         per = parse(path)
         ours, ref = {}, {}
         for k, launches in per.items():
-            is_ours = k.startswith(("gat_fwd", "gat_bwd", "dot_fwd", "gt_bwd", "gt_block"))
+            is_ours = k.startswith(("gat_fwd", "gat_bwd", "dot_fwd", "gt_bwd", "gt_block", "gt_dense", "block_attn_dense"))
             use = launches[len(launches) // 3:] if (is_ours and len(launches) >= 3) else launches
             # big-tile fallback launches of the staged GAT path return at once: keep them apart
             rec = {"launches": len(launches),
@@ -100,7 +100,7 @@ def main():
     if os.path.exists(lst):
         per = parse(lst)
         tot = sum(m.get("gpu__time_duration.sum", 0) for ls in per.values() for m in ls)
-        conv = {k: ls for k, ls in per.items() if k.startswith(("gat_", "dot_fwd", "gt_bwd", "gt_block"))}
+        conv = {k: ls for k, ls in per.items() if k.startswith(("gat_", "dot_fwd", "gt_bwd", "gt_block", "gt_dense", "block_attn"))}
         tot_conv = sum(m.get("gpu__time_duration.sum", 0) for ls in conv.values() for m in ls)
         lines = [f"# {TAG}: ncu launch list, default bench (arxiv-gat)", "",
                  "`ncu --metrics gpu__time_duration.sum --clock-control none -c 600 python bench.py --steps 3 "
