@@ -202,16 +202,11 @@ def block_plan(batch_num_nodes: torch.Tensor, row_ptr: torch.Tensor, col_ind: to
     return plan
 
 
-def _balanced_schedule(bnn: torch.Tensor, dev, column_items: bool = False):
-    """Work lists for the persistent CTAs of the dense tcgen05 kernels (one CTA per SM): longest
-    processing time first over a cost model of the MMA work.  Forward / row side: one entry per
-    graph (a graph of more than 128 nodes is two row tiles over up to 256 keys).  Column side
-    (``column_items``): one entry per (graph, 128-key tile), id = 2 * graph + tile, cost = the 16-row
-    slices of the graph.  Dealing 1024 PATTERN-shaped graphs round robin leaves the busiest SM with
-    1.65x the mean work; this schedule 1.05x.  -> (number of CTAs, ptr [ctas + 1], ids)."""
+def balanced_lists(bnn, n_ctas: int, column_items: bool = False):
+    """Host part of ``_balanced_schedule`` (numpy only): -> (ctas, ptr [ctas + 1] int32, ids int32)."""
     import heapq
     import numpy as np
-    n = bnn.numpy().astype(np.int64)
+    n = np.asarray(bnn, dtype=np.int64)
     if column_items:
         slices = (n + 15) // 16
         ids = np.concatenate([2 * np.arange(len(n)), 2 * np.nonzero(n > 128)[0] + 1])
@@ -221,8 +216,7 @@ def _balanced_schedule(bnn: torch.Tensor, dev, column_items: bool = False):
         ids = np.arange(len(n))
         cost = np.where(n <= 128, 16 * 246 + slices * 4 * 246, 2 * (16 * 384 + slices * 4 * 246))
     cost = cost.astype(np.int64)
-    sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    g = int(min(len(ids), sms))
+    g = int(max(1, min(len(ids), n_ctas)))
     heap = [(0, c) for c in range(g)]
     lists = [[] for _ in range(g)]
     for k in np.argsort(-cost, kind="stable"):
@@ -232,6 +226,18 @@ def _balanced_schedule(bnn: torch.Tensor, dev, column_items: bool = False):
     ptr = np.zeros(g + 1, dtype=np.int32)
     ptr[1:] = np.cumsum([len(x) for x in lists])
     idx = np.fromiter((b for x in lists for b in x), dtype=np.int32, count=len(ids))
+    return g, ptr, idx
+
+
+def _balanced_schedule(bnn: torch.Tensor, dev, column_items: bool = False):
+    """Work lists for the persistent CTAs of the dense tcgen05 kernels (one CTA per SM): longest
+    processing time first over a cost model of the MMA work.  Forward / row side: one entry per
+    graph (a graph of more than 128 nodes is two row tiles over up to 256 keys).  Column side
+    (``column_items``): one entry per (graph, 128-key tile), id = 2 * graph + tile, cost = the 16-row
+    slices of the graph.  Dealing 1024 PATTERN-shaped graphs round robin leaves the busiest SM with
+    1.65x the mean work; this schedule 1.05x.  -> (number of CTAs, ptr [ctas + 1], ids)."""
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    g, ptr, idx = balanced_lists(bnn, sms, column_items)
     return g, torch.from_numpy(ptr).to(dev), torch.from_numpy(idx).to(dev)
 
 

@@ -43,3 +43,21 @@ def test_conv_inputs_seeded():
     a, b = graphs.conv_inputs(10, 8, 5), graphs.conv_inputs(10, 8, 5)
     assert torch.equal(a.Q, b.Q) and torch.equal(a.dO, b.dO)
     assert a.Q.shape == (10, 1, 8) and a.attn_row.shape == (10, 1)
+
+
+def test_balanced_work_lists_of_the_dense_kernels():
+    """formats.balanced_lists: every graph (or (graph, key tile) item) exactly once, loads within a few
+    per cent of each other on the PATTERN-shaped batch (round robin: 1.65x the mean on the busiest CTA)."""
+    import numpy as np
+    from dfgnn_b200.formats import balanced_lists
+    bnn = graphs.pattern_like(batch=1024).batch_num_nodes().numpy()
+    g, ptr, idx = balanced_lists(bnn, 148)
+    assert g == 148 and ptr[0] == 0 and ptr[-1] == len(bnn) and sorted(idx.tolist()) == list(range(len(bnn)))
+    tiles = np.where(bnn <= 128, 1.0, 3.0)  # a wide graph is two row tiles over twice the keys
+    load = np.array([tiles[idx[ptr[c]:ptr[c + 1]]].sum() for c in range(g)])
+    assert load.max() <= 1.15 * load.mean()
+    g2, ptr2, idx2 = balanced_lists(bnn, 148, column_items=True)
+    want = sorted([2 * b for b in range(len(bnn))] + [2 * b + 1 for b in range(len(bnn)) if bnn[b] > 128])
+    assert sorted(idx2.tolist()) == want and ptr2[-1] == len(want)
+    g3, ptr3, idx3 = balanced_lists(bnn[:5], 148)
+    assert g3 == 5 and ptr3.tolist() == [0, 1, 2, 3, 4, 5]
