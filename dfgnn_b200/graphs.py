@@ -219,6 +219,74 @@ def pascalvoc_like(batch: int = 1024, seed: int = 1005) -> Graph:
                          "PascalVOC-SP-shaped")
 
 
+def constant_degree_graph(num_nodes: int, num_neigh: int, seed: int = 0) -> Graph:
+    """Every row has ``num_neigh`` random neighbours (``DFGNN/utils/graph_generate.py:20-27``; duplicates
+    removed so that the edge list is a set, like every other generator here)."""
+    gen = _gen(seed)
+    row = torch.arange(num_nodes, dtype=torch.int64).repeat_interleave(num_neigh)
+    col = torch.randint(0, max(1, num_nodes - 1), (row.numel(),), generator=gen, dtype=torch.int64)
+    row, col = _sorted_unique_coo(row, col, num_nodes)
+    return Graph(row, col, num_nodes, None, f"constant-degree-{num_neigh}")
+
+
+# --------------------------------------------------------------------------- #
+# On-disk graph store (SURVEY.md 8f row 4): one .npz per graph -- int32 COO,     #
+# node count, graph sizes of a batch, name and the sha256 of the edge list --    #
+# so that a workload is generated once and every later run (and every rank)      #
+# reads identical bytes.  The reference's dataset loaders are commented out      #
+# (DFGNN/utils/util.py:41-148) and need DGL / OGB downloads; the store holds     #
+# the synthetic graphs of the same shapes.                                       #
+# --------------------------------------------------------------------------- #
+
+def save_graph(g: Graph, path: str) -> str:
+    """-> sha256 of the edge list (also stored in the file and checked by ``load_graph``)."""
+    import numpy as np
+    src, dst = g.edges()
+    sha = g.sha256()
+    bnn = g.batch_num_nodes().cpu().numpy().astype(np.int32) if g.batch_size > 1 else np.zeros(0, np.int32)
+    dt = np.int32 if max(g.num_nodes(), g.num_cols) < 2 ** 31 else np.int64
+    np.savez(path, src=src.cpu().numpy().astype(dt), dst=dst.cpu().numpy().astype(dt),
+             num_nodes=np.int64(g.num_nodes()), num_cols=np.int64(g.num_cols), batch_num_nodes=bnn,
+             name=np.array(g.name), sha256=np.array(sha))
+    return sha
+
+
+def load_graph(path: str) -> Graph:
+    import numpy as np
+    with np.load(path if path.endswith(".npz") else path + ".npz", allow_pickle=False) as z:
+        bnn = torch.from_numpy(z["batch_num_nodes"].astype(np.int64)) if z["batch_num_nodes"].size else None
+        g = Graph(torch.from_numpy(z["src"].astype(np.int64)), torch.from_numpy(z["dst"].astype(np.int64)),
+                  int(z["num_nodes"]), bnn, str(z["name"]), int(z["num_cols"]))
+        want = str(z["sha256"])
+    if g.sha256() != want:
+        raise RuntimeError(f"{path}: edge list does not match its recorded sha256 (corrupt or truncated file)")
+    return g
+
+
+class GraphStore:
+    """Directory of generated graphs: ``store.get("pattern_like", batch=64)`` generates on the first
+    call and loads the file afterwards."""
+
+    def __init__(self, root: str):
+        import os
+        self.root = root
+        os.makedirs(root, exist_ok=True)
+
+    def path(self, fn: str, **kw) -> str:
+        import os
+        tag = "_".join(f"{k}-{v}" for k, v in sorted(kw.items()))
+        return os.path.join(self.root, fn + ("_" + tag if tag else "") + ".npz")
+
+    def get(self, fn: str, **kw) -> Graph:
+        import os
+        path = self.path(fn, **kw)
+        if os.path.exists(path):
+            return load_graph(path)
+        g = globals()[fn](**kw)
+        save_graph(g, path)
+        return g
+
+
 @dataclass
 class ConvInputs:
     """Seeded operands for one conv call (features seed+1, dO seed+2)."""

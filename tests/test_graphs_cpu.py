@@ -61,3 +61,28 @@ def test_balanced_work_lists_of_the_dense_kernels():
     assert sorted(idx2.tolist()) == want and ptr2[-1] == len(want)
     g3, ptr3, idx3 = balanced_lists(bnn[:5], 148)
     assert g3 == 5 and ptr3.tolist() == [0, 1, 2, 3, 4, 5]
+
+
+def test_graph_store_round_trip(tmp_path):
+    """graphs.save_graph / load_graph / GraphStore: identical edge lists, batch sizes and fingerprints;
+    a damaged file is refused."""
+    import numpy as np
+    store = graphs.GraphStore(str(tmp_path))
+    g = store.get("pattern_like", batch=6)
+    g2 = store.get("pattern_like", batch=6)  # second call reads the file
+    assert g2.sha256() == g.sha256() and g2.num_nodes() == g.num_nodes() and g2.batch_size == 6
+    assert torch.equal(g2.batch_num_nodes(), g.batch_num_nodes())
+    for a, b in zip(g.edges(), g2.edges()):
+        assert torch.equal(a, b)
+    c = graphs.constant_degree_graph(100, 5, seed=3)
+    deg = torch.bincount(c.edges()[0], minlength=100)
+    assert c.num_nodes() == 100 and int(deg.max()) <= 5 and int(deg.min()) >= 1
+    path = str(tmp_path / "c.npz")
+    graphs.save_graph(c, path)
+    z = dict(np.load(path))
+    z["dst"] = z["dst"].copy()
+    z["dst"][0] += 1
+    np.savez(path, **z)
+    import pytest
+    with pytest.raises(RuntimeError, match="sha256"):
+        graphs.load_graph(path)
