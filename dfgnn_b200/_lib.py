@@ -54,8 +54,8 @@ _SIGNATURES = {
     "dfgnn_block_adj_bits": (c_int, [c_int] * 4 + [_P] * 4 + [_P]),
     "dfgnn_gt_dense_tc_forward": (c_int, [c_int, _P] + [c_int] * 5 + [_P, _P, c_int, _P, _P] + [_P] * 5 + [_P]),
     "dfgnn_gt_dense_tc_backward_col": (c_int, [c_int, _P] + [c_int] * 5 + [_P, _P, c_int, _P, _P] + [_P] * 5 + [_P]),
-    "dfgnn_gt_dense_tc_backward_ws_floats": (c_size_t, [c_int]),
-    "dfgnn_gt_dense_tc_backward": (c_int, [c_int, c_int, _P] + [c_int] * 5 + [_P, _P, c_int, _P, _P, c_int, _P, _P] + [_P] * 9 + [_P]),
+    "dfgnn_gt_dense_tc_backward_ws_floats": (c_size_t, [c_int, c_int]),
+    "dfgnn_gt_dense_tc_backward": (c_int, [c_int, c_int, _P] + [c_int] * 5 + [_P, _P, c_int, _P, _P, c_int, _P, _P] + [_P] * 10 + [_P]),
     "dfgnn_gt_block_forward": (c_int, [c_int, _P] + [c_int] * 5 + [_P] * 8 + [_P]),
     "dfgnn_gt_block_backward": (c_int, [c_int, c_int, _P] + [c_int] * 5 + [_P] * 15 + [_P]),
     "dfgnn_proj_weight_image_floats": (c_size_t, [c_int, c_int]),

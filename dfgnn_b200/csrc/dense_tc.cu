@@ -103,8 +103,8 @@ __device__ unsigned long long g_tc_prof[32];
 // graph sizes) a CTA walks its own list; without one, graphs blockIdx.x, blockIdx.x + gridDim.x, ...
 struct TcTiles {
   const int *blk, *sidx;
-  int i, i_end, step, mt, MT, lb, n;
-  __device__ TcTiles(const int* blk_, int nb, const int* sched_ptr, const int* sched_idx) : blk(blk_), sidx(sched_idx), mt(0), MT(0), lb(0), n(0) {
+  int i, i_end, step, mt, MT, lb, n, b;
+  __device__ TcTiles(const int* blk_, int nb, const int* sched_ptr, const int* sched_idx) : blk(blk_), sidx(sched_idx), mt(0), MT(0), lb(0), n(0), b(0) {
     if (sched_ptr) {
       i = __ldg(sched_ptr + blockIdx.x) - 1;
       i_end = __ldg(sched_ptr + blockIdx.x + 1);
@@ -118,7 +118,7 @@ struct TcTiles {
   __device__ bool next() {
     if (++mt < MT) return true;
     for (i += step; i < i_end; i += step) {
-      const int b = sidx ? __ldg(sidx + i) : i;
+      b = sidx ? __ldg(sidx + i) : i;
       lb = __ldg(blk + b);
       n = __ldg(blk + b + 1) - lb;
       if (n > 0) {
@@ -142,10 +142,17 @@ struct GtTcParams {
   const uint32_t* adj_bits;  // [m][8] (forward)
   const float *a1, *b1, *b2;  // forward: Q, K, V; backward row side: dO, V, K
   float *out, *attn;          // forward: out, attn_edge (may be null: inference); backward: dQ, unused
-  const float* Pd;            // backward: dense probabilities [m][256]
-  float* dSd;                 // backward: dense dS [m][256] (written here, read by the column side)
+  const float* Pd;            // backward: dense probabilities, tile images (below)
+  float* dSd;                 // backward: dense dS, tile images (written here, read by the column side)
+  const int* tile_ptr;        // backward: [n_blocks + 1] first row tile of every graph
 };
-constexpr int kTcDenseLd = 256;  // row pitch of the dense P / dS work arrays
+// Dense P / dS work arrays of the backward: one 128-row x 256-column image per row tile, "chunk major" like
+// the operand images (4-column chunk c of row r at (c * 128 + r) * 4 floats), so that the row threads of a
+// warp (thread = row) read and write 512 contiguous bytes per instruction.
+constexpr int kTcTileFloats = kTcM * kTcMaxNodes;
+__device__ __forceinline__ size_t tile_at(int tile, int r, int j) {
+  return (size_t)tile * kTcTileFloats + (size_t)(j >> 2) * (kTcM * 4) + r * 4 + (j & 3);
+}
 
 // BWD = false: forward (S = Q K^T, softmax, O = P V).  BWD = true: row side of the backward with the same
 // pipeline -- product 1 dA = dO V^T, then per row s_i = sum_j p_ij dA_ij and dS_ij = p_ij (dA_ij - s_i) with
@@ -381,8 +388,10 @@ __device__ __forceinline__ void gt_dense_tc_body(const GtTcParams& p) {
       const uint32_t sc2 = sc + t.stages1();
       const int row = t.mt * kTcM + r;
       const bool valid = row < t.n;
-      const float4* prow = reinterpret_cast<const float4*>(p.Pd + (size_t)(t.lb + (valid ? row : 0)) * kTcDenseLd);
-      float4* dsrow = reinterpret_cast<float4*>(p.dSd + (size_t)(t.lb + (valid ? row : 0)) * kTcDenseLd);
+      const int tile = __ldg(p.tile_ptr + t.b) + t.mt;
+      // float4 (chunk c, row r) of this tile's images: c * 128 + r
+      const float4* prow = reinterpret_cast<const float4*>(p.Pd + (size_t)tile * kTcTileFloats) + r;
+      float4* dsrow = reinterpret_cast<float4*>(p.dSd + (size_t)tile * kTcTileFloats) + r;
       auto load_da = [&](int cb, float (&s)[32]) {  // 32 columns of dA (narrow tiles: the sum of the two halves)
         tmem_ld32(lane_base + cb * 32, s);
         if (narrow) {
@@ -400,7 +409,7 @@ __device__ __forceinline__ void gt_dense_tc_body(const GtTcParams& p) {
       for (int cb = sg; cb < NS2; cb += 2) {
         float4 pv[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) pv[c] = valid ? __ldg(prow + cb * 8 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < 8; ++c) pv[c] = valid ? __ldg(prow + (cb * 8 + c) * kTcM) : make_float4(0.f, 0.f, 0.f, 0.f);
         float s[32];
         load_da(cb, s);
         float a0 = 0.f, a1 = 0.f;
@@ -421,7 +430,7 @@ __device__ __forceinline__ void gt_dense_tc_body(const GtTcParams& p) {
       for (int cb = sg; cb < NS2; cb += 2) {
         float4 pv[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) pv[c] = valid ? __ldg(prow + cb * 8 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < 8; ++c) pv[c] = valid ? __ldg(prow + (cb * 8 + c) * kTcM) : make_float4(0.f, 0.f, 0.f, 0.f);
         float s[32];
         load_da(cb, s);
 #pragma unroll
@@ -446,7 +455,7 @@ __device__ __forceinline__ void gt_dense_tc_body(const GtTcParams& p) {
         mbar_arrive(&full_a[slot]);
         if (valid) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) dsrow[cb * 8 + c] = pv[c];
+          for (int c = 0; c < 8; ++c) dsrow[(cb * 8 + c) * kTcM] = pv[c];
         }
       }
       tc_fence_before();
@@ -743,8 +752,8 @@ constexpr size_t kBcSmemBytes = kBcOffStage + (size_t)2 * kTcM * kTcStgLd * 4;
 
 struct TcItems {  // (graph, key tile) items of this CTA; item id = 2 * graph + kt
   const int *blk, *sidx;
-  int i, i_end, step, lb, n, kt;
-  __device__ TcItems(const int* blk_, int nb, const int* sched_ptr, const int* sched_idx) : blk(blk_), sidx(sched_idx), lb(0), n(0), kt(0) {
+  int i, i_end, step, lb, n, kt, b;
+  __device__ TcItems(const int* blk_, int nb, const int* sched_ptr, const int* sched_idx) : blk(blk_), sidx(sched_idx), lb(0), n(0), kt(0), b(0) {
     if (sched_ptr) {
       i = __ldg(sched_ptr + blockIdx.x) - 1;
       i_end = __ldg(sched_ptr + blockIdx.x + 1);
@@ -758,7 +767,7 @@ struct TcItems {  // (graph, key tile) items of this CTA; item id = 2 * graph + 
   __device__ bool next() {
     for (i += step; i < i_end; i += step) {
       const int item = sidx ? __ldg(sidx + i) : i;
-      const int b = item >> 1;
+      b = item >> 1;
       kt = item & 1;
       lb = __ldg(blk + b);
       n = __ldg(blk + b + 1) - lb;
@@ -774,7 +783,8 @@ struct GtTcBwdColParams {
   const int *blk_ptr, *row_ptr, *sched_ptr, *sched_idx;
   const uint32_t* adj_bits;
   const float2* scratch;  // [nnz] {dS_e, p_e} (DENSE = false)
-  const float *Pd, *dSd;  // dense [m][256] probabilities and dS (DENSE = true)
+  const float *Pd, *dSd;  // dense probabilities and dS, tile images (DENSE = true)
+  const int* tile_ptr;    // [n_blocks + 1] first row tile of every graph (DENSE = true)
   const float *dO, *Q;
   float *dK, *dV;
 };
@@ -849,12 +859,15 @@ __global__ void __launch_bounds__(kBcThreads, 1) gt_dense_tc_bwd_col_kernel(cons
         float2 v[8];
         if constexpr (DENSE) {
           const int row = 16 * s + i_loc, n32 = (t.n + 31) & ~31;
-          const size_t at = (size_t)(t.lb + (row < t.n ? row : 0)) * kTcDenseLd + t.kt * kTcM;
+          const int tile = __ldg(p.tile_ptr + t.b) + (row >> 7);
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const int j = j0 + 16 * u;
+            const int j = j0 + 16 * u, jg = t.kt * kTcM + j;
             v[u] = make_float2(0.f, 0.f);
-            if (row < t.n && t.kt * kTcM + j < n32) v[u] = make_float2(__ldg(p.dSd + at + j), __ldg(p.Pd + at + j));
+            if (row < t.n && jg < n32) {
+              const size_t at = tile_at(tile, row & 127, jg);
+              v[u] = make_float2(__ldg(p.dSd + at), __ldg(p.Pd + at));
+            }
           }
         } else {
           const uint4 ww = s_tabw[16 * s + i_loc];
@@ -1011,8 +1024,8 @@ __global__ void __launch_bounds__(kBcThreads, 1) gt_dense_tc_bwd_col_kernel(cons
 // of 32 columns of each graph): one CTA per graph, a warp per row, 32 columns per step through the bitmap.
 static __global__ void block_attn_dense_kernel(const int* __restrict__ blk_ptr, const int* __restrict__ row_ptr,
                                                const uint32_t* __restrict__ bits, const float* __restrict__ attn,
-                                               float* __restrict__ Pd) {
-  const int b = blockIdx.x, lb = blk_ptr[b], n = blk_ptr[b + 1] - lb;
+                                               const int* __restrict__ tile_ptr, float* __restrict__ Pd) {
+  const int b = blockIdx.x, lb = blk_ptr[b], n = blk_ptr[b + 1] - lb, tile0 = tile_ptr[b];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5, nc = (n + 31) >> 5;
   // gridDim.y CTAs share a graph; a warp keeps the loads of a whole row (up to 8 pieces) in flight
   for (int r = w + nw * blockIdx.y; r < n; r += nw * gridDim.y) {
@@ -1029,7 +1042,7 @@ static __global__ void block_attn_dense_kernel(const int* __restrict__ blk_ptr, 
     }
 #pragma unroll
     for (int cb = 0; cb < kTcMaskW; ++cb)
-      if (cb < nc) Pd[(size_t)(lb + r) * kTcDenseLd + cb * 32 + lane] = v[cb];
+      if (cb < nc) Pd[tile_at(tile0 + (r >> 7), r & 127, cb * 32 + lane)] = v[cb];
   }
 }
 
@@ -1087,7 +1100,7 @@ int dfgnn_gt_dense_tc_forward(int n_blocks, const int32_t* blk_ptr, int max_node
   cudaStream_t st = (cudaStream_t)stream;
   const bool sched = sched_ptr != nullptr && sched_idx != nullptr && n_ctas >= 1;
   GtTcParams p{n_blocks, blk_ptr, row_ptr, sched ? sched_ptr : nullptr, sched ? sched_idx : nullptr, adj_bits,
-               Q, K, V, out_feat, nnz > 0 ? attn_edge : nullptr, nullptr, nullptr};
+               Q, K, V, out_feat, nnz > 0 ? attn_edge : nullptr, nullptr, nullptr, nullptr};
   auto kernel = gt_dense_tc_fwd_kernel;
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
   const int grid = sched ? n_ctas : (n_blocks < sm_count() ? n_blocks : sm_count());
@@ -1114,7 +1127,7 @@ int dfgnn_gt_dense_tc_backward_col(int n_blocks, const int32_t* blk_ptr, int max
   cudaStream_t st = (cudaStream_t)stream;
   const bool sched = sched_ptr != nullptr && sched_idx != nullptr && n_ctas >= 1;
   GtTcBwdColParams p{n_blocks, blk_ptr, row_ptr, sched ? sched_ptr : nullptr, sched ? sched_idx : nullptr, adj_bits,
-                     reinterpret_cast<const float2*>(grad_edge), nullptr, nullptr, grad_out, Q, grad_K, grad_V};
+                     reinterpret_cast<const float2*>(grad_edge), nullptr, nullptr, nullptr, grad_out, Q, grad_K, grad_V};
   auto kernel = gt_dense_tc_bwd_col_kernel<false>;
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBcSmemBytes);
   const int grid = sched ? n_ctas : (2 * n_blocks < sm_count() ? 2 * n_blocks : sm_count());
@@ -1123,19 +1136,25 @@ int dfgnn_gt_dense_tc_backward_col(int n_blocks, const int32_t* blk_ptr, int max
   return check_launch(fn);
 }
 
-size_t dfgnn_gt_dense_tc_backward_ws_floats(int m) { return (size_t)2 * (size_t)(m > 0 ? m : 0) * kTcDenseLd; }
+size_t dfgnn_gt_dense_tc_backward_ws_floats(int m, int n_blocks) {
+  // two arrays of one 128 x 256 image per row tile; sum over graphs of ceil(n / 128) <= m / 128 + n_blocks
+  const size_t tiles = (size_t)(m > 0 ? m : 0) / kTcM + (size_t)(n_blocks > 0 ? n_blocks : 0) + 1;
+  return 2 * tiles * kTcTileFloats;
+}
 
 int dfgnn_gt_dense_tc_backward(int phases, int n_blocks, const int32_t* blk_ptr, int max_nodes, int m, int nnz, int h,
                                int f, const int32_t* row_ptr, const uint32_t* adj_bits, int n_ctas,
                                const int32_t* sched_ptr, const int32_t* sched_idx, int n_ctas_col,
                                const int32_t* sched_ptr_col, const int32_t* sched_idx_col, const float* Q,
                                const float* K, const float* V, const float* attn_edge, const float* grad_out,
-                               float* grad_Q, float* grad_K, float* grad_V, float* dense_ws, void* stream) {
+                               float* grad_Q, float* grad_K, float* grad_V, const int32_t* tile_ptr, float* dense_ws,
+                               void* stream) {
   const char* fn = "dfgnn_gt_dense_tc_backward";
   if (phases < 1 || phases > 3) { set_error("%s: phases=%d must be 1, 2 or 3", fn, phases); return DFGNN_ERR_INVALID_ARGUMENT; }
   if (int rc = check_common(fn, m, nnz, h, f)) return rc;
   if (m == 0) return DFGNN_OK;
   DFGNN_REQUIRE(blk_ptr, fn); DFGNN_REQUIRE(row_ptr, fn); DFGNN_REQUIRE(adj_bits, fn); DFGNN_REQUIRE(dense_ws, fn);
+  DFGNN_REQUIRE(tile_ptr, fn);
   DFGNN_REQUIRE(Q, fn); DFGNN_REQUIRE(K, fn); DFGNN_REQUIRE(V, fn); DFGNN_REQUIRE(grad_out, fn);
   DFGNN_REQUIRE(grad_Q, fn); DFGNN_REQUIRE(grad_K, fn); DFGNN_REQUIRE(grad_V, fn);
   if (nnz > 0) DFGNN_REQUIRE(attn_edge, fn);
@@ -1146,13 +1165,13 @@ int dfgnn_gt_dense_tc_backward(int phases, int n_blocks, const int32_t* blk_ptr,
   }
   cudaStream_t st = (cudaStream_t)stream;
   float* Pd = dense_ws;
-  float* dSd = dense_ws + (size_t)m * kTcDenseLd;
+  float* dSd = dense_ws + dfgnn_gt_dense_tc_backward_ws_floats(m, n_blocks) / 2;
   if (phases & 1) {
-    block_attn_dense_kernel<<<dim3(n_blocks, 4), 256, 0, st>>>(blk_ptr, row_ptr, adj_bits, attn_edge, Pd);
+    block_attn_dense_kernel<<<dim3(n_blocks, 4), 256, 0, st>>>(blk_ptr, row_ptr, adj_bits, attn_edge, tile_ptr, Pd);
     if (int rc = check_launch(fn)) return rc;
     const bool sched = sched_ptr != nullptr && sched_idx != nullptr && n_ctas >= 1;
     GtTcParams p{n_blocks, blk_ptr, row_ptr, sched ? sched_ptr : nullptr, sched ? sched_idx : nullptr, adj_bits,
-                 grad_out, V, K, grad_Q, nullptr, Pd, dSd};
+                 grad_out, V, K, grad_Q, nullptr, Pd, dSd, tile_ptr};
     auto kernel = gt_dense_tc_bwd_row_kernel;
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
     const int grid = sched ? n_ctas : (n_blocks < sm_count() ? n_blocks : sm_count());
@@ -1163,7 +1182,7 @@ int dfgnn_gt_dense_tc_backward(int phases, int n_blocks, const int32_t* blk_ptr,
   if (phases & 2) {
     const bool sched = sched_ptr_col != nullptr && sched_idx_col != nullptr && n_ctas_col >= 1;
     GtTcBwdColParams p{n_blocks, blk_ptr, row_ptr, sched ? sched_ptr_col : nullptr, sched ? sched_idx_col : nullptr, adj_bits,
-                       nullptr, Pd, dSd, grad_out, Q, grad_K, grad_V};
+                       nullptr, Pd, dSd, tile_ptr, grad_out, Q, grad_K, grad_V};
     auto kernel = gt_dense_tc_bwd_col_kernel<true>;
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBcSmemBytes);
     const int grid = sched ? n_ctas_col : (2 * n_blocks < sm_count() ? 2 * n_blocks : sm_count());

@@ -130,6 +130,7 @@ class BlockPlan:
         self.adj_bits = None                    # [m, 8] int32 adjacency bitmap (dense tcgen05 kernels)
         self.n_ctas, self.sched_ptr, self.sched_idx = 0, None, None  # balanced graph lists of the persistent CTAs
         self.col_sched = (0, None, None)        # the same for the (graph, key tile) items of the column-side backward
+        self.tile_ptr = None                    # [n_blocks + 1] first 128-row tile of every graph (dense work arrays)
         self._ok = {}
 
     def algorithm(self, m: int, nnz: int, h: int, f: int, unweighted: bool, training: bool = False) -> int:
@@ -199,6 +200,9 @@ def block_plan(batch_num_nodes: torch.Tensor, row_ptr: torch.Tensor, col_ind: to
         plan.adj_bits = bits
         plan.n_ctas, plan.sched_ptr, plan.sched_idx = _balanced_schedule(bnn, dev)
         plan.col_sched = _balanced_schedule(bnn, dev, column_items=True)
+        tp = torch.zeros(bnn.numel() + 1, dtype=torch.int32)
+        tp[1:] = torch.cumsum((bnn + 127) // 128, 0).to(torch.int32)
+        plan.tile_ptr = tp.to(dev)
     return plan
 
 

@@ -165,7 +165,7 @@ def gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem_con
             # dense batch: both sides on tcgen05 (csrc/dense_tc.cu); dense P / dS tiles in a work array kept on
             # the plan (it must survive from a row-side call to a column-side call)
             L = _lib.lib()
-            need = int(L.dfgnn_gt_dense_tc_backward_ws_floats(m))
+            need = int(L.dfgnn_gt_dense_tc_backward_ws_floats(m, plan.n_blocks))
             ws = getattr(plan, "_dense_ws", None)
             if ws is None or ws.numel() < need or ws.device != Q.device:
                 ws = plan._dense_ws = torch.empty(need, dtype=torch.float32, device=Q.device)
@@ -173,8 +173,8 @@ def gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem_con
             rc = L.dfgnn_gt_dense_tc_backward(
                 int(_phases), plan.n_blocks, _ptr(plan.blk_ptr), plan.max_nodes, m, nnz, h, f, _ptr(row_ptr),
                 _ptr(plan.adj_bits), plan.n_ctas, _ptr(plan.sched_ptr), _ptr(plan.sched_idx), nc, _ptr(sp), _ptr(si),
-                _ptr(Q), _ptr(K), _ptr(V), _ptr(attn_edge), _ptr(grad), _ptr(gq), _ptr(gk), _ptr(gv), _ptr(ws),
-                _stream(Q))
+                _ptr(Q), _ptr(K), _ptr(V), _ptr(attn_edge), _ptr(grad), _ptr(gq), _ptr(gk), _ptr(gv), _ptr(plan.tile_ptr),
+                _ptr(ws), _stream(Q))
         elif plan is not None:
             rc = _lib.lib().dfgnn_gt_block_backward(
                 int(_phases), plan.n_blocks, _ptr(plan.blk_ptr), plan.max_nodes, m, nnz, h, f, _ptr(row_ptr),

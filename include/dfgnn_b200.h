@@ -242,19 +242,20 @@ int dfgnn_gt_dense_tc_backward_col(int n_blocks, const int32_t *blk_ptr, int max
  * dense per-graph tiles, then the row side runs with the forward's pipeline (dA = grad_out V^T, dS =
  * P (dA - rowsum(P dA)), grad_Q = dS K) and leaves dS as dense tiles; phases & 2: the column side
  * (grad_V = P^T grad_out, grad_K = dS^T Q) from those tiles.  dense_ws: device scratch of
- * dfgnn_gt_dense_tc_backward_ws_floats(m) floats that must persist between a phases = 1 and a phases = 2
- * call.  The first schedule lists graphs (row side), the second (graph, key tile) items (column side).
+ * dfgnn_gt_dense_tc_backward_ws_floats(m, n_blocks) floats that must persist between a phases = 1 and a
+ * phases = 2 call; tile_ptr [n_blocks + 1]: exclusive prefix sum of ceil(nodes / 128) over the graphs (the
+ * dense tiles are stored one 128-row image per row tile).  The first schedule lists graphs (row side), the second (graph, key tile) items (column side).
  * Same results as dfgnn_gt_backward (DFGNN/src/fused_gtconv/fused_gtconv.cpp:125-172).
  */
-size_t dfgnn_gt_dense_tc_backward_ws_floats(int m);
+size_t dfgnn_gt_dense_tc_backward_ws_floats(int m, int n_blocks);
 int dfgnn_gt_dense_tc_backward(int phases, int n_blocks, const int32_t *blk_ptr, int max_nodes, int m,
                                int nnz, int h, int f, const int32_t *row_ptr,
                                const uint32_t *adj_bits, int n_ctas, const int32_t *sched_ptr,
                                const int32_t *sched_idx, int n_ctas_col, const int32_t *sched_ptr_col,
                                const int32_t *sched_idx_col, const float *Q, const float *K,
                                const float *V, const float *attn_edge, const float *grad_out,
-                               float *grad_Q, float *grad_K, float *grad_V, float *dense_ws,
-                               void *stream);
+                               float *grad_Q, float *grad_K, float *grad_V,
+                               const int32_t *tile_ptr, float *dense_ws, void *stream);
 /* = dfgnn_gt_backward_phase on a square block-diagonal adjacency (n == m). */
 int dfgnn_gt_block_backward(int phases, int n_blocks, const int32_t *blk_ptr, int max_nodes, int m,
                             int nnz, int h, int f, const int32_t *row_ptr, const int32_t *col_ind,

@@ -277,3 +277,25 @@ def test_dense_tcgen05_persistent_loop_and_unsorted_fallback(cuda):
     ci_rev = col_ind[rev].contiguous()
     plan = formats.block_plan(g.batch_num_nodes(), row_ptr, ci_rev)
     assert not plan.ascending and plan.algorithm(n, ci_rev.numel(), 1, 128, True) != 3
+
+
+def test_adjacency_bitmap_and_schedules_are_exact(cuda):
+    """The formats of the dense tcgen05 kernels (integer work: bit-exact): adj_bits[r] has bit j set iff
+    (r, first node of r's graph + j) is an edge; the work lists hold every graph / (graph, key tile) item
+    exactly once."""
+    g = _batch_tc("wide")
+    row_ptr, col_ind, rows, val, smem = preprocess_Hyper(g.to(cuda))
+    plan = row_ptr._dfgnn_blocks
+    assert plan.ascending and plan.adj_bits is not None and plan.adj_bits.shape == (g.num_nodes(), 8)
+    rp, ci = row_ptr.cpu().numpy(), col_ind.cpu().numpy()
+    blk = plan.blk_ptr.cpu().numpy()
+    want = np.zeros((g.num_nodes(), 8), dtype=np.uint32)
+    for b in range(plan.n_blocks):
+        for r in range(blk[b], blk[b + 1]):
+            j = ci[rp[r]:rp[r + 1]] - blk[b]
+            np.bitwise_or.at(want[r], j >> 5, (np.uint32(1) << (j & 31).astype(np.uint32)))
+    assert np.array_equal(plan.adj_bits.cpu().numpy().view(np.uint32), want)
+    assert sorted(plan.sched_idx.cpu().tolist()) == list(range(plan.n_blocks))
+    bnn = g.batch_num_nodes().numpy()
+    items = sorted([2 * b for b in range(plan.n_blocks)] + [2 * b + 1 for b in range(plan.n_blocks) if bnn[b] > 128])
+    assert sorted(plan.col_sched[2].cpu().tolist()) == items
