@@ -8,11 +8,12 @@
 // GEMMs per 128-row tile the kernel is bound by reading Q, K, V once and writing O and attn_edge once.
 //
 // fp32 parity (1e-4 relative) from TF32 tensor cores by the 3xTF32 split: x = hi + lo with hi = x
-// truncated to TF32, a b ~ a_hi b_hi + a_hi b_lo + a_lo b_hi, fp32 accumulation in tensor memory.
+// rounded to TF32, a b ~ a_hi b_hi + a_hi b_lo + a_lo b_hi, fp32 accumulation in tensor memory.
 // A tcgen05.mma kind::tf32 costs ~118 cycles for any N <= 128 and 128 cycles for N = 256 (measured,
 // tools/umma_bench.cu), so the hi and lo images of the B operand are STACKED along N: one N = 256 MMA
-// gives a_hi b_hi (columns 0-127) and a_hi b_lo (columns 128-255), one N = 128 MMA adds a_lo b_hi;
-// the two column halves are summed when the accumulator is read.
+// gives a_hi b_hi (columns 0-127) and a_hi b_lo (columns 128-255), one N = 128 MMA adds a_lo b_hi to
+// the second half (the small cross terms stay together: the tensor core adds with truncation); the two
+// column halves are summed when the accumulator is read.
 //
 // The adjacency of the batch comes as a bitmap (dfgnn_block_adj_bits: 256 bits per row, bit j = key j
 // of the row's own graph), a format built once per batch like the CSC: the kernel never reads col_ind.
@@ -21,10 +22,11 @@
 // rows.  Roles (warp specialised, mbarriers only):
 //   warps 0-7    softmax / epilogue, two groups of 4 warps that share every tile: group g takes the
 //                32-column pieces cb with (cb & 1) == g; thread r of either group owns tile row r = TMEM
-//                lane r.  Pass 1 row max (combined through shared memory), pass 2 p = 2^(s - max)
-//                (unnormalised) split into the A images of the second product, pass 3 (training)
-//                normalised probabilities to attn_edge through a warp transposition (coalesced stores);
-//                finally O * (1 / row sum) -> out through a staging buffer (coalesced stores).
+//                lane r.  Pass 1: online row max and row sum of 2^(s - max) straight from tensor memory,
+//                combined across the groups through shared memory; pass 2: normalised probabilities,
+//                split into the A images of the second product and (training) written to attn_edge
+//                through a warp transposition (a store writes two rows' contiguous pieces); finally
+//                O -> out through a staging buffer (coalesced stores).
 //   warp  8      MMA issue (one lane).  Product 1: S[128 x keys] += Q_slice K_slice^T over slices of the
 //                feature dimension; product 2: O[128 x 128] += P_slice V_slice over 32-key slices.
 //   warps 9-16   two loader groups of 4 warps taking alternate ring stages: global -> registers (issued
@@ -39,6 +41,9 @@
 //   product 2, K = 32 keys:              P_hi | P_lo (128 rows) | B = V^T_hi over V^T_lo (256 rows)
 // Tensor memory: S in columns [0, 256) (narrow tiles: two halves to be summed), O in [256, 512) (two
 // halves to be summed).
+//
+// The backward runs on the same machinery: gt_dense_tc_body<true> (row side: dA = dO V^T, dS, dQ = dS K)
+// and gt_dense_tc_bwd_col_kernel (column side: dV = P^T dO, dK = dS^T Q), further down.
 //
 // Requirements (checked by the block plan, formats.py / dfgnn_block_plan_check): h == 1, f == 128,
 // unweighted scores, graphs of at most 256 nodes, column ids strictly ascending inside every row (no
@@ -1020,29 +1025,43 @@ __global__ void __launch_bounds__(kBcThreads, 1) gt_dense_tc_bwd_col_kernel(cons
   if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
 }
 
-// attn_edge (CSR order) -> dense probabilities [m][256] (zeros where there is no edge, up to the next multiple
-// of 32 columns of each graph): one CTA per graph, a warp per row, 32 columns per step through the bitmap.
+// attn_edge (CSR order) -> dense probabilities as tile images (tile_at; zeros where there is no edge, up to the
+// next multiple of 32 columns of each graph).  gridDim.y CTAs share a graph; a warp takes 8 rows at a time:
+// lane = (row r8 = lane & 7, 4-column quad q = lane >> 3), 16 columns per step, so that a store instruction
+// writes four 128-byte runs of the chunk-major image (8 rows x one float4 each per quad).
 static __global__ void block_attn_dense_kernel(const int* __restrict__ blk_ptr, const int* __restrict__ row_ptr,
                                                const uint32_t* __restrict__ bits, const float* __restrict__ attn,
                                                const int* __restrict__ tile_ptr, float* __restrict__ Pd) {
   const int b = blockIdx.x, lb = blk_ptr[b], n = blk_ptr[b + 1] - lb, tile0 = tile_ptr[b];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5, nc = (n + 31) >> 5;
-  // gridDim.y CTAs share a graph; a warp keeps the loads of a whole row (up to 8 pieces) in flight
-  for (int r = w + nw * blockIdx.y; r < n; r += nw * gridDim.y) {
-    const int e0 = row_ptr[lb + r];
-    const uint32_t mine = lane < kTcMaskW ? bits[(size_t)(lb + r) * kTcMaskW + lane] : 0u;
-    float v[kTcMaskW];
-    int e = e0;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5, n32 = (n + 31) & ~31;
+  const int r8 = lane & 7, q = lane >> 3;
+  for (int rb = 8 * (w + nw * blockIdx.y); rb < n; rb += 8 * nw * gridDim.y) {
+    const int r = rb + r8;
+    if (r >= n) continue;  // no warp-level operations below
+    const uint4* src = reinterpret_cast<const uint4*>(bits + (size_t)(lb + r) * kTcMaskW);
+    const uint4 w0 = __ldg(src), w1 = __ldg(src + 1);
+    const uint32_t wd[kTcMaskW] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    const float* arow = attn + __ldg(row_ptr + lb + r);
+    float4* img = reinterpret_cast<float4*>(Pd + (size_t)(tile0 + (r >> 7)) * kTcTileFloats) + (r & 127);
+    int before = 0;  // set bits of the words in front of the current one
 #pragma unroll
-    for (int cb = 0; cb < kTcMaskW; ++cb) {
-      const uint32_t word = __shfl_sync(kFull, mine, cb);
-      v[cb] = 0.f;
-      if (cb < nc && ((word >> lane) & 1u)) v[cb] = __ldg(attn + e + __popc(word & ((1u << lane) - 1u)));
-      e += __popc(word);
+    for (int k = 0; k < kTcMaskW; ++k) {
+      if (32 * k < n32) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int bit = 16 * half + 4 * q;  // first of this thread's four columns inside word k
+          const uint32_t nib = (wd[k] >> bit) & 0xFu;
+          const float* at = arow + before + __popc(wd[k] & ((1u << bit) - 1u));
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (nib & 1u) v.x = __ldg(at);
+          if (nib & 2u) v.y = __ldg(at + __popc(nib & 1u));
+          if (nib & 4u) v.z = __ldg(at + __popc(nib & 3u));
+          if (nib & 8u) v.w = __ldg(at + __popc(nib & 7u));
+          img[(size_t)((32 * k + bit) >> 2) * kTcM] = v;
+        }
+        before += __popc(wd[k]);
+      }
     }
-#pragma unroll
-    for (int cb = 0; cb < kTcMaskW; ++cb)
-      if (cb < nc) Pd[tile_at(tile0 + (r >> 7), r & 127, cb * 32 + lane)] = v[cb];
   }
 }
 
