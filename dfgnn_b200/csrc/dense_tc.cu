@@ -741,14 +741,15 @@ static __global__ void block_adj_bits_kernel(int n_blocks, const int* __restrict
 // CSR scratch through the adjacency bitmap (a warp covers 8 keys x 4 rows = 128 contiguous bytes of an image,
 // every element of the image is written, zeros where there is no edge).  B operands: dO^T / Q^T slices
 // (rows = features), hi over lo stacked along N like in the forward.
-//   warps 0-7   workers: per item a table of the tile's bitmap words and CSR positions per row, then per
-//               stage 8 scratch loads per thread -> hi / lo -> the four A images; after the item's last stage
+//   warps 0-7   workers, two groups of 4 warps taking alternate stages: per item a table of the tile's bitmap
+//               words and CSR positions per row (CSR input), then per stage 16 loads per thread -> hi / lo -> the four A images; after the item's last stage
 //               the epilogue (group 0: dV, group 1: dK; two column halves summed, staged, coalesced stores)
 //   warp  8     MMA issue: per K = 8 and product one N = 256 MMA (A_hi x [B_hi over B_lo]) + one N = 128 MMA
 //               (A_lo x B_hi); dV in tensor-memory columns [0, 256), dK in [256, 512)
-//   warps 9-12  loaders of the B images (thread = feature, coalesced scalar loads of 16 rows)
-constexpr int kBcWorkWarps = 8, kBcLoadWarps = 4;
-constexpr int kBcThreads = (kBcWorkWarps + 1 + kBcLoadWarps) * 32;  // 416
+//   warps 9-16  loaders of the B images, two groups taking alternate stages (thread = feature, coalesced
+//               scalar loads of 16 rows)
+constexpr int kBcWorkWarps = 8, kBcLoadWarps = 8;  // two groups of 4 warps each, taking alternate ring stages
+constexpr int kBcThreads = (kBcWorkWarps + 1 + kBcLoadWarps) * 32;  // 544
 constexpr int kBcA = 8 * 1024;                       // one A image: 4 chunks x 128 rows x 16 B
 constexpr int kBcOffB0 = 4 * kBcA, kBcOffB1 = 4 * kBcA + 16 * 1024;  // dO^T / Q^T images (256 rows, hi over lo)
 constexpr size_t kBcOffTab = (size_t)kTcSlots * kTcSlotBytes;          // [256 rows][uint4 words | int4 positions]
@@ -804,8 +805,8 @@ __global__ void __launch_bounds__(kBcThreads, 1) gt_dense_tc_bwd_col_kernel(cons
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   if (tid == 0) {
     for (int i = 0; i < kTcSlots; ++i) {
-      mbar_init(&full_a[i], kBcWorkWarps * 32);
-      mbar_init(&full_b[i], kBcLoadWarps * 32);
+      mbar_init(&full_a[i], 128);  // one group of four worker warps
+      mbar_init(&full_b[i], 128);  // one group of four loader warps
       mbar_init(&empty[i], 1);
     }
     mbar_init(&acc_full, 1);
@@ -830,7 +831,8 @@ __global__ void __launch_bounds__(kBcThreads, 1) gt_dense_tc_bwd_col_kernel(cons
     float* stg = reinterpret_cast<float*>(smem + kBcOffStage) + (size_t)eg * kTcM * kTcStgLd;
     const uint32_t lane_base = tmem + ((uint32_t)((w & 3) * 32) << 16) + eg * 256;
     const int i_loc = 4 * (w & 3) + (lane & 3);  // this thread's row inside a 16-row slice
-    const int j0 = 8 * (w >> 2) + (lane >> 2);   // its key in iteration u: j0 + 16 u
+    const int j0 = lane >> 2;                    // its key in iteration u: j0 + 8 u
+    const uint32_t wg = w >> 2;                  // worker group: takes the stages with (stage & 1) == wg
     uint32_t sc = 0, tc = 0;
     TcItems t(p.blk_ptr, p.n_blocks, p.sched_ptr, p.sched_idx);
     while (t.next()) {
@@ -859,29 +861,33 @@ __global__ void __launch_bounds__(kBcThreads, 1) gt_dense_tc_bwd_col_kernel(cons
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       const int NS = t.stages();
+      const int tile0 = DENSE ? __ldg(p.tile_ptr + t.b) : 0;
       for (int s = 0; s < NS; ++s, ++sc) {
+        if ((sc & 1u) != wg) continue;
         const uint32_t slot = sc % kTcSlots;
-        float2 v[8];
+        float2 v[16];
         if constexpr (DENSE) {
+          // element (row, key jg = 128 kt + j0 + 8 u) of a tile image: (jg >> 2) * 512 + r * 4 + (jg & 3) floats,
+          // i.e. a per-thread base plus u * 1024
           const int row = 16 * s + i_loc, n32 = (t.n + 31) & ~31;
-          const int tile = __ldg(p.tile_ptr + t.b) + (row >> 7);
+          const size_t base = (size_t)(tile0 + (row >> 7)) * kTcTileFloats +
+                              (size_t)(t.kt * 32 + (j0 >> 2)) * (kTcM * 4) + (row & 127) * 4 + (j0 & 3);
+          const float* ps = p.dSd + base;
+          const float* pp = p.Pd + base;
+          const int jmax = row < t.n ? n32 - t.kt * kTcM - j0 : 0;  // keys j0 + 8 u < jmax are valid
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int j = j0 + 16 * u, jg = t.kt * kTcM + j;
+          for (int u = 0; u < 16; ++u) {
             v[u] = make_float2(0.f, 0.f);
-            if (row < t.n && jg < n32) {
-              const size_t at = tile_at(tile, row & 127, jg);
-              v[u] = make_float2(__ldg(p.dSd + at), __ldg(p.Pd + at));
-            }
+            if (8 * u < jmax) v[u] = make_float2(__ldg(ps + u * (2 * kTcM * 4)), __ldg(pp + u * (2 * kTcM * 4)));
           }
         } else {
           const uint4 ww = s_tabw[16 * s + i_loc];
           const int4 cc = s_tabc[16 * s + i_loc];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int j = j0 + 16 * u, bit = j & 31;
-            const uint32_t word = (u >> 1) == 0 ? ww.x : (u >> 1) == 1 ? ww.y : (u >> 1) == 2 ? ww.z : ww.w;
-            const int cbase = (u >> 1) == 0 ? cc.x : (u >> 1) == 1 ? cc.y : (u >> 1) == 2 ? cc.z : cc.w;
+          for (int u = 0; u < 16; ++u) {
+            const int bit = j0 + 8 * (u & 3);  // key j0 + 8 u lies in word u >> 2
+            const uint32_t word = (u >> 2) == 0 ? ww.x : (u >> 2) == 1 ? ww.y : (u >> 2) == 2 ? ww.z : ww.w;
+            const int cbase = (u >> 2) == 0 ? cc.x : (u >> 2) == 1 ? cc.y : (u >> 2) == 2 ? cc.z : cc.w;
             v[u] = make_float2(0.f, 0.f);
             if ((word >> bit) & 1u) v[u] = __ldg(p.scratch + cbase + __popc(word & ((1u << bit) - 1u)));
           }
@@ -889,8 +895,8 @@ __global__ void __launch_bounds__(kBcThreads, 1) gt_dense_tc_bwd_col_kernel(cons
         mbar_wait(&empty[slot], ((sc / kTcSlots) & 1u) ^ 1u);
         float* img = reinterpret_cast<float*>(smem + (size_t)slot * kTcSlotBytes);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int j = j0 + 16 * u;
+        for (int u = 0; u < 16; ++u) {
+          const int j = j0 + 8 * u;
           const int at = ((w & 3) * kTcM + j) * 4 + (lane & 3);  // chunk (w & 3), image row j, word i % 4
           const float ph = round_tf32(v[u].y), dh = round_tf32(v[u].x);
           img[at] = ph;
@@ -980,12 +986,14 @@ __global__ void __launch_bounds__(kBcThreads, 1) gt_dense_tc_bwd_col_kernel(cons
     }
   } else {
     // =============================== loaders: dO^T and Q^T slices ==================================
-    const int lf = tid - (kBcWorkWarps + 1) * 32;  // feature
+    const uint32_t lg = (w - kBcWorkWarps - 1) >> 2;             // loader group: stages with (stage & 1) == lg
+    const int lf = (tid - (kBcWorkWarps + 1) * 32) & 127;         // feature
     uint32_t sc = 0;
     TcItems t(p.blk_ptr, p.n_blocks, p.sched_ptr, p.sched_idx);
     while (t.next()) {
       const int NS = t.stages();
       for (int s = 0; s < NS; ++s, ++sc) {
+        if ((sc & 1u) != lg) continue;
         const uint32_t slot = sc % kTcSlots;
         const float* gsrc = p.dO + (size_t)(t.lb + 16 * s) * kTcF + lf;
         const float* qsrc = p.Q + (size_t)(t.lb + 16 * s) * kTcF + lf;
