@@ -299,3 +299,22 @@ def test_adjacency_bitmap_and_schedules_are_exact(cuda):
     bnn = g.batch_num_nodes().numpy()
     items = sorted([2 * b for b in range(plan.n_blocks)] + [2 * b + 1 for b in range(plan.n_blocks) if bnn[b] > 128])
     assert sorted(plan.col_sched[2].cpu().tolist()) == items
+
+
+def test_dense_tcgen05_path_is_bit_reproducible(cuda):
+    """No atomics anywhere on the dense tcgen05 path (the reference's backward accumulates with atomicAdd):
+    two runs on the same inputs give identical bits, forward and backward."""
+    _lib.lib().dfgnn_set_block_mode(4)
+    g = _batch_tc("wide")
+    n = g.num_nodes()
+    X = graphs.conv_inputs(n, 128, 37)
+    A, rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx, smem = preprocess_Hyper_fw_bw(g.to(cuda))
+    Q, K, V, dO = (t.to(cuda) for t in (X.Q, X.K, X.V, X.dO))
+    runs = []
+    for _ in range(2):
+        out, attn = N.gt_hyper_forward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V)
+        gq, gk, gv = N.gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V, attn, dO)
+        runs.append((out, attn, gq, gk, gv))
+    assert _lib.last_kernel(0) == "gt_dense_tc_fwd_kernel" and _lib.last_kernel(1) == "gt_dense_tc_bwd_row_kernel"
+    for a, b in zip(*runs):
+        assert torch.equal(a, b)
