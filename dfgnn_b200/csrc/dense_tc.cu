@@ -49,6 +49,12 @@
 // unweighted scores, graphs of at most 256 nodes, column ids strictly ascending inside every row (no
 // duplicate edges: a bitmap cannot count an edge twice).  Reference counterpart:
 // fused_gtconv_hyper.cu:31-163 (forward) and, for the maths, DFGNN/layers/GT/gtconv_layer.py:28-45.
+#include <algorithm>
+#include <functional>
+#include <queue>
+#include <utility>
+#include <vector>
+
 #include "abi_common.h"
 #include "tc_common.cuh"
 
@@ -1092,6 +1098,49 @@ static int sm_count() {
 using namespace dfgnn;
 
 extern "C" {
+
+// Host-side work lists for the persistent CTAs (no device work): longest processing time first over a cost
+// model of the MMA work.  column_items = 0: one entry per graph (forward / backward row side; a graph of more
+// than 128 nodes is two row tiles over up to 256 keys); 1: one entry per (graph, 128-key tile), id = 2 * graph
+// + tile (backward column side; cost = 16-row slices of the graph + the epilogue).  nodes: host array
+// [n_blocks].  ptr_out [n_ctas_out + 1], idx_out [items]; returns the number of CTAs (<= n_ctas), or < 0.
+int dfgnn_tc_balanced_lists(int n_blocks, const int32_t* nodes, int n_ctas, int column_items, int32_t* ptr_out,
+                            int32_t* idx_out) {
+  if (n_blocks < 1 || n_ctas < 1 || !nodes || !ptr_out || !idx_out) return DFGNN_ERR_INVALID_ARGUMENT;
+  struct Item { long long cost; int id; };
+  std::vector<Item> items;
+  items.reserve(2 * (size_t)n_blocks);
+  for (int b = 0; b < n_blocks; ++b) {
+    const long long n = nodes[b] > 0 ? nodes[b] : 0;
+    if (column_items) {
+      const long long c = ((n + 15) / 16) * 1000 + 4000;
+      items.push_back({c, 2 * b});
+      if (n > kTcM) items.push_back({c, 2 * b + 1});
+    } else {
+      const long long sl = (n + 31) / 32;
+      items.push_back({n <= kTcM ? 16 * 246 + sl * 4 * 246 : 2 * (16 * 384 + sl * 4 * 246), b});
+    }
+  }
+  std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.cost > b.cost; });
+  const int g = (int)std::min<size_t>(items.size(), (size_t)n_ctas);
+  using Load = std::pair<long long, int>;  // (load, cta): smallest load first, ties to the lower CTA
+  std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
+  for (int c = 0; c < g; ++c) heap.push({0, c});
+  std::vector<std::vector<int>> lists(g);
+  for (const Item& it : items) {
+    Load l = heap.top();
+    heap.pop();
+    lists[l.second].push_back(it.id);
+    heap.push({l.first + it.cost, l.second});
+  }
+  int at = 0;
+  for (int c = 0; c < g; ++c) {
+    ptr_out[c] = at;
+    for (int id : lists[c]) idx_out[at++] = id;
+  }
+  ptr_out[g] = at;
+  return g;
+}
 
 int dfgnn_gt_dense_tc_supported(int max_nodes, int h, int f) { return dense_tc_supported(max_nodes, h, f) ? 1 : 0; }
 

@@ -207,30 +207,18 @@ def block_plan(batch_num_nodes: torch.Tensor, row_ptr: torch.Tensor, col_ind: to
 
 
 def balanced_lists(bnn, n_ctas: int, column_items: bool = False):
-    """Host part of ``_balanced_schedule`` (numpy only): -> (ctas, ptr [ctas + 1] int32, ids int32)."""
-    import heapq
+    """Host part of ``_balanced_schedule``: longest-processing-time-first lists from the graph sizes
+    (``dfgnn_tc_balanced_lists``, plain C++ on the host: the plan is built per batch, a Python heap loop
+    over 2400 items cost more than the conv step).  -> (ctas, ptr [ctas + 1] int32, ids int32)."""
     import numpy as np
-    n = np.asarray(bnn, dtype=np.int64)
-    if column_items:
-        slices = (n + 15) // 16
-        ids = np.concatenate([2 * np.arange(len(n)), 2 * np.nonzero(n > 128)[0] + 1])
-        cost = np.concatenate([slices, slices[n > 128]]) * 1000 + 4000   # + epilogue
-    else:
-        slices = (n + 31) // 32
-        ids = np.arange(len(n))
-        cost = np.where(n <= 128, 16 * 246 + slices * 4 * 246, 2 * (16 * 384 + slices * 4 * 246))
-    cost = cost.astype(np.int64)
-    g = int(max(1, min(len(ids), n_ctas)))
-    heap = [(0, c) for c in range(g)]
-    lists = [[] for _ in range(g)]
-    for k in np.argsort(-cost, kind="stable"):
-        load, c = heapq.heappop(heap)
-        lists[c].append(int(ids[k]))
-        heapq.heappush(heap, (load + int(cost[k]), c))
-    ptr = np.zeros(g + 1, dtype=np.int32)
-    ptr[1:] = np.cumsum([len(x) for x in lists])
-    idx = np.fromiter((b for x in lists for b in x), dtype=np.int32, count=len(ids))
-    return g, ptr, idx
+    n = np.ascontiguousarray(np.asarray(bnn, dtype=np.int32))
+    ptr = np.zeros(int(n_ctas) + 1, dtype=np.int32)
+    idx = np.zeros(2 * len(n), dtype=np.int32)
+    g = _lib.lib().dfgnn_tc_balanced_lists(len(n), n.ctypes.data, int(n_ctas), int(bool(column_items)),
+                                           ptr.ctypes.data, idx.ctypes.data)
+    if g < 1:
+        raise RuntimeError("dfgnn_tc_balanced_lists: invalid arguments")
+    return g, ptr[: g + 1].copy(), idx[: int(ptr[g])].copy()
 
 
 def _balanced_schedule(bnn: torch.Tensor, dev, column_items: bool = False):

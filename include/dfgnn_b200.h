@@ -215,6 +215,12 @@ int dfgnn_gt_dense_forward(int n_blocks, const int32_t *blk_ptr, int max_nodes, 
  * sizes, which it knows from batch_num_nodes); NULL = graphs dealt round robin over the SMs.
  */
 int dfgnn_gt_dense_tc_supported(int max_nodes, int h, int f);
+/* Host-only helper: balanced work lists for the persistent CTAs from the graph sizes (nodes: HOST array
+ * [n_blocks]); column_items = 0 lists graphs (forward, backward row side), 1 lists (graph, key tile) items
+ * with id = 2 * graph + tile (backward column side).  ptr_out [n_ctas + 1], idx_out [2 * n_blocks] (host);
+ * returns the number of CTAs used (<= n_ctas) or a negative error code. */
+int dfgnn_tc_balanced_lists(int n_blocks, const int32_t *nodes, int n_ctas, int column_items,
+                            int32_t *ptr_out, int32_t *idx_out);
 int dfgnn_block_adj_bits(int n_blocks, int max_nodes, int m, int nnz, const int32_t *blk_ptr,
                          const int32_t *row_ptr, const int32_t *col_ind, uint32_t *adj_bits,
                          void *stream);
