@@ -51,6 +51,7 @@ _SIGNATURES = {
     "dfgnn_gt_dense_supported": (c_int, [c_int] * 3),
     "dfgnn_gt_dense_forward": (c_int, [c_int, _P] + [c_int] * 5 + [_P] * 7 + [_P]),
     "dfgnn_gt_dense_tc_supported": (c_int, [c_int] * 3),
+    "dfgnn_tc_poison_tmem": (c_int, [_P]),
     "dfgnn_tc_balanced_lists": (c_int, [c_int, _P, c_int, c_int, _P, _P]),
     "dfgnn_block_adj_bits": (c_int, [c_int] * 4 + [_P] * 4 + [_P]),
     "dfgnn_gt_dense_tc_forward": (c_int, [c_int, _P] + [c_int] * 5 + [_P, _P, c_int, _P, _P] + [_P] * 5 + [_P]),

@@ -544,7 +544,10 @@ __device__ __forceinline__ void gt_dense_tc_body(const GtTcParams& p) {
           }
         } else {
           // wide tile: up to 256 keys in one MMA, 3 MMAs per K = 8, K = 16 per stage
-          const uint32_t idk = umma_idesc_tf32(kTcM, (t.n + 15) & ~15);
+          // N = every column the softmax threads read (whole 32-column pieces): the K / V rows behind the graph's
+          // last key are zero in the images, so those columns are 0, never stale tensor memory (the backward
+          // multiplies them by p = 0, which would not survive a NaN)
+          const uint32_t idk = umma_idesc_tf32(kTcM, ((t.n + 31) >> 5) << 5);
           for (int q = 0; q < 8; ++q, ++sc) {
             const uint32_t slot = sc % kTcSlots, k = sc / kTcSlots;
             TC_TIMED(9, mbar_wait(&full_b[slot], k & 1u));
@@ -1079,6 +1082,31 @@ static __global__ void block_attn_dense_kernel(const int* __restrict__ blk_ptr, 
   }
 }
 
+// Test hook: fills all 512 tensor-memory columns of every SM with NaN bit patterns, so that a kernel that reads
+// tensor memory it has not written shows up in the parity tests (tensor memory keeps its contents between kernels).
+static __global__ void __launch_bounds__(128, 1) tc_poison_tmem_kernel() {
+  __shared__ uint32_t s_tmem;
+  const int w = threadIdx.x >> 5;
+  if (w == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem, nan = 0x7fc00000u;
+  for (int c = 0; c < 512; c += 8)
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(
+                     tmem + ((uint32_t)(w * 32) << 16) + c),
+                 "r"(nan)
+                 : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+}
+
 static bool dense_tc_supported(int max_nodes, int h, int f) {
   return h == 1 && f == kTcF && max_nodes >= 1 && max_nodes <= kTcMaxNodes;
 }
@@ -1140,6 +1168,11 @@ int dfgnn_tc_balanced_lists(int n_blocks, const int32_t* nodes, int n_ctas, int 
   }
   ptr_out[g] = at;
   return g;
+}
+
+int dfgnn_tc_poison_tmem(void* stream) {
+  tc_poison_tmem_kernel<<<4 * sm_count(), 128, 0, (cudaStream_t)stream>>>();
+  return check_launch("dfgnn_tc_poison_tmem");
 }
 
 int dfgnn_gt_dense_tc_supported(int max_nodes, int h, int f) { return dense_tc_supported(max_nodes, h, f) ? 1 : 0; }

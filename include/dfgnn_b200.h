@@ -215,6 +215,9 @@ int dfgnn_gt_dense_forward(int n_blocks, const int32_t *blk_ptr, int max_nodes, 
  * sizes, which it knows from batch_num_nodes); NULL = graphs dealt round robin over the SMs.
  */
 int dfgnn_gt_dense_tc_supported(int max_nodes, int h, int f);
+/* Test hook: writes NaN into every tensor-memory column of every SM (tensor memory keeps its contents
+ * between kernels; the parity tests run the tcgen05 kernels after it). */
+int dfgnn_tc_poison_tmem(void *stream);
 /* Host-only helper: balanced work lists for the persistent CTAs from the graph sizes (nodes: HOST array
  * [n_blocks]); column_items = 0 lists graphs (forward, backward row side), 1 lists (graph, key tile) items
  * with id = 2 * graph + tile (backward column side).  ptr_out [n_ctas + 1], idx_out [2 * n_blocks] (host);

@@ -318,3 +318,33 @@ def test_dense_tcgen05_path_is_bit_reproducible(cuda):
     assert _lib.last_kernel(0) == "gt_dense_tc_fwd_kernel" and _lib.last_kernel(1) == "gt_dense_tc_bwd_row_kernel"
     for a, b in zip(*runs):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("kind", ["wide", "ragged"])
+def test_dense_tcgen05_kernels_read_no_stale_tensor_memory(cuda, kind):
+    """Tensor memory keeps its contents between kernels.  Poison all of it with NaN, then run forward and
+    backward: a column read without having been written (padding keys of a wide graph, the second
+    accumulator half) would turn up as NaN."""
+    _lib.lib().dfgnn_set_block_mode(4)
+    g = _batch_tc(kind)
+    n = g.num_nodes()
+    X = graphs.conv_inputs(n, 128, 41)
+    A, rows, row_ptr, col_ind, val, col_ptr, row_ind, val_idx, smem = preprocess_Hyper_fw_bw(g.to(cuda))
+    Q, K, V, dO = (t.to(cuda) for t in (X.Q, X.K, X.V, X.dO))
+    st = torch.cuda.current_stream().cuda_stream
+    o64, a64, dQ, dK, dV = _oracle(g, X)
+    _lib.check(_lib.lib().dfgnn_tc_poison_tmem(st), "poison")
+    out, attn = N.gt_hyper_forward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V)
+    assert _lib.last_kernel(0) == "gt_dense_tc_fwd_kernel"
+    _lib.check(_lib.lib().dfgnn_tc_poison_tmem(st), "poison")
+    bufs = N.gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V, attn, dO, _phases=1)
+    _lib.check(_lib.lib().dfgnn_tc_poison_tmem(st), "poison")
+    gq, gk, gv = N.gt_backward(row_ptr, col_ind, rows, val, col_ptr, row_ind, val_idx, smem, Q, K, V, attn, dO,
+                               _phases=2, _buffers=bufs)
+    for t in (out, attn, gq, gk, gv):
+        assert bool(torch.isfinite(t).all())
+    assert_close("out", out, o64)
+    assert_close("attn_edge", attn, a64)
+    assert_close_bulk("grad_Q", gq[:, 0], torch.from_numpy(dQ)[:, 0])
+    assert_close("grad_K", gk, dK)
+    assert_close("grad_V", gv, dV)
