@@ -485,7 +485,8 @@ def measure(env, args, name: str, full: bool):
         halo.pop_times()
         for _ in range(n_c):
             flush.fill_(1.0)
-            step_device()
+            barrier()  # ranks start every measured step together: an NCCL kernel otherwise also waits out the
+            step_device()  # skew of ranks that are a step apart in this un-synchronised eager loop
         t = halo.pop_times()
         halo.record = False
         ag_t, rs_t = t["allgather_ms"] / n_c, t["reduce_scatter_ms"] / n_c
