@@ -671,8 +671,9 @@ def measure(env, args, name: str, full: bool):
                              "exposed_ms": max(0.0, ms - (k_fwd + k_row + k_col)),
                              "note": "backend p2p = pull-based exchange over NVLink peer memory (symmetric memory, "
                                      "copy engines), nccl = coalesced NCCL all-gather / reduce-scatter; durations "
-                                     "bracketed by CUDA events in an eager pass; exposed_ms = step - sum of the three "
-                                     "kernels timed alone",
+                                     "bracketed by CUDA events in an eager pass (an NCCL kernel also waits for the slowest rank to "
+                                     "arrive, so they include the load imbalance of the step); exposed_ms = step - sum of "
+                                     "the three kernels timed alone",
                              "bytes_in_per_rank": (world - 1) * part.max_rows * (2 * dim if conv == "gt" else dim + 1) * 4}
                             if halo.active else None),
         }
