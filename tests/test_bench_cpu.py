@@ -33,3 +33,23 @@ def test_reference_arm_prints_the_contract_line():
     assert line["value"] > 0 and line["higher_is_better"] is True and line["config"]["workload"] == "cora-gt"
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+
+
+def test_tf32_split_properties():
+    """The 3xTF32 split of csrc/tc_common.cuh (round_tf32 / split4), restated in numpy: hi has 10 mantissa
+    bits, hi + lo == x exactly in fp32, |lo| <= 2^-11 |x| (rounding, not truncation), and the three-term
+    product a_hi b_hi + a_hi b_lo + a_lo b_hi is within 2^-21 |a b| of the exact product."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal(200000) * np.exp(rng.uniform(-20, 20, 200000))).astype(np.float32)
+    bits = x.view(np.uint32)
+    hi = ((bits + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+    lo = x - hi
+    assert np.all((hi.view(np.uint32) & np.uint32(0x1FFF)) == 0)
+    assert np.array_equal(hi + lo, x)
+    assert np.all(np.abs(lo) <= np.abs(x) * 2.0 ** -11 * (1 + 1e-6))
+    a, b = x[:100000].astype(np.float64), x[100000:].astype(np.float64)
+    ah, al = hi[:100000].astype(np.float64), lo[:100000].astype(np.float64)
+    bh, bl = hi[100000:].astype(np.float64), lo[100000:].astype(np.float64)
+    approx = ah * bh + ah * bl + al * bh
+    assert np.all(np.abs(approx - a * b) <= np.abs(a * b) * 2.0 ** -21)
