@@ -119,6 +119,11 @@ class BlockPlan:
 
     # dense tensor-core kernels from this fill ratio of the diagonal blocks on (automatic mode)
     DENSE_MIN_FILL = 0.15
+    # ... and, for the tcgen05 kernels, from this many edges per 128-row tile on: their cost is per TILE
+    # (~54 us of one SM for forward + backward, whatever the tile holds) while the per-edge kernels cost
+    # ~0.21 ns per edge of the whole GPU (measured on the PATTERN-shaped batch); batches of tiny graphs stay
+    # on the per-edge kernels
+    TC_MIN_EDGES_PER_TILE = 1800
 
     def __init__(self, blk_ptr: torch.Tensor, n_blocks: int, max_nodes: int, sum_sq_nodes: int = 0,
                  ascending: bool = True):
@@ -131,6 +136,7 @@ class BlockPlan:
         self.n_ctas, self.sched_ptr, self.sched_idx = 0, None, None  # balanced graph lists of the persistent CTAs
         self.col_sched = (0, None, None)        # the same for the (graph, key tile) items of the column-side backward
         self.tile_ptr = None                    # [n_blocks + 1] first 128-row tile of every graph (dense work arrays)
+        self.n_tiles = 0
         self._ok = {}
 
     def algorithm(self, m: int, nnz: int, h: int, f: int, unweighted: bool, training: bool = False) -> int:
@@ -148,7 +154,7 @@ class BlockPlan:
             dense_ok = unweighted and self.ascending and nnz > 0
             if (dense_ok and self.adj_bits is not None and mode in (0, 4)
                     and L.dfgnn_gt_dense_tc_supported(self.max_nodes, h, f)):
-                if mode == 4 or fill >= self.DENSE_MIN_FILL:
+                if mode == 4 or self.prefers_dense_tc(nnz):
                     algo = 3
             if algo == 0 and dense_ok and L.dfgnn_gt_dense_supported(self.max_nodes, h, f):
                 if mode == 3 or (fill >= self.DENSE_MIN_FILL and not training):
@@ -157,6 +163,11 @@ class BlockPlan:
                 algo = 1
             self._ok[key] = algo
         return self._ok[key]
+
+    def prefers_dense_tc(self, nnz: int) -> bool:
+        """Automatic mode: dense enough blocks AND enough edges per 128-row tile for the tcgen05 kernels."""
+        fill = nnz / self.sum_sq_nodes if self.sum_sq_nodes > 0 else 0.0
+        return fill >= self.DENSE_MIN_FILL and nnz >= self.TC_MIN_EDGES_PER_TILE * max(1, self.n_tiles)
 
     def supported(self, m: int, nnz: int, h: int, f: int) -> bool:
         key = (m, nnz, h, f, _lib.lib().dfgnn_set_block_mode(-1))
@@ -203,6 +214,7 @@ def block_plan(batch_num_nodes: torch.Tensor, row_ptr: torch.Tensor, col_ind: to
         tp = torch.zeros(bnn.numel() + 1, dtype=torch.int32)
         tp[1:] = torch.cumsum((bnn + 127) // 128, 0).to(torch.int32)
         plan.tile_ptr = tp.to(dev)
+        plan.n_tiles = int(tp[-1])
     return plan
 
 

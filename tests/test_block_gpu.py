@@ -178,7 +178,7 @@ def test_dense_tensor_core_forward(cuda, kind, dim):
     _lib.lib().dfgnn_set_block_mode(0)
     plan = row_ptr._dfgnn_blocks
     dense = col_ind.numel() / plan.sum_sq_nodes >= plan.DENSE_MIN_FILL
-    tc = dense and dim == 128
+    tc = dim == 128 and plan.prefers_dense_tc(col_ind.numel())  # dense AND enough edges per 128-row tile
     assert plan.algorithm(n, col_ind.numel(), 1, dim, True) == (3 if tc else 2 if dense else 0)
     assert plan.algorithm(n, col_ind.numel(), 1, dim, True, training=True) == (3 if tc else 0)
     inf2 = N.gt_hyper_inference(row_ptr, col_ind, rows, val, smem, Q, K, V)[0]
